@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — the dense-LU hot path on B200 (BASELINE.json metric: FP64 LU GFLOP/s
+counted as 2/3 n^3).
+
+A "step" is one pass of the hot path over one synthetic problem:
+    getrf of a fresh n x n FP64 matrix  +  getrs for `nrhs` right-hand sides with
+    the cached factors (LinearCache reuse, BASELINE config 2: n = 8192, 100 RHS).
+`value`  : whole-job GFLOP/s = N * (2/3 n^3) / step time, inputs resident in HBM
+           (device pointers through the C ABI, CUDA-event timed, max over ranks).
+`e2e`    : same metric through the public API (LinearProblem/init/solve!) with
+           PINNED HOST buffers, H2D of A and every b and D2H of every x inside the
+           timed region.
+`roofline`: the trailing-update DMMA GEMM, bracketed in situ by CUDA events on its
+           launching stream (B200LU_OPT_PROFILE), against the FP64 tensor peak
+           measured on this box by the library's register-resident DMMA probe
+           (MEASURED_PEAKS.json carries no FP64 figure).
+`cpu_baseline` / `--impl reference`: LAPACK dgetrf+dgetrs (scipy OpenBLAS: the
+           arithmetic of the reference's LUFactorization) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--n", type=int, default=8192)
+    p.add_argument("--nrhs", type=int, default=100)
+    p.add_argument("--workload", default="lu", choices=["lu", "batched", "mixed"])
+    p.add_argument("--batch", type=int, default=65536)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--nb", type=int, default=0)
+    p.add_argument("--lookahead", type=int, default=-1)
+    return p.parse_args()
+
+
+def lu_flops(n):
+    return 2.0 / 3.0 * n ** 3
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_lu_step(A, B):
+    """the reference CPU path's arithmetic: LAPACK dgetrf + dgetrs (all BLAS threads)"""
+    from scipy.linalg import lapack
+    lu, piv, info = lapack.dgetrf(A, overwrite_a=False)
+    x, info2 = lapack.dgetrs(lu, piv, B)
+    return x
+
+
+def run_reference(args, rank, world):
+    """--impl reference: LAPACK on the host cores, same config/metric. Rank 0 only."""
+    if rank != 0:
+        return
+    n, nrhs = args.n, args.nrhs
+    rng = np.random.default_rng(123)
+    A = np.asfortranarray(rng.random((n, n)))
+    B = np.asfortranarray(rng.random((n, nrhs)))
+    for _ in range(min(args.warmup, 1)):
+        cpu_lu_step(A, B)
+    ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        cpu_lu_step(A, B)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.mean(ts))
+    val = lu_flops(n) / t / 1e9
+    line = {
+        "impl": "reference", "metric": "FP64 LU GFLOP/s (2/3 n^3), getrf + getrs over nrhs right-hand sides",
+        "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"f64 getrf n={n} + getrs {nrhs} rhs (LinearCache reuse)", "n": n, "nrhs": nrhs},
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": host_threads(), "kind": "port",
+                         "sample": f"full workload per step, {args.steps} steps; LAPACK dgetrf+dgetrs via scipy "
+                                   "OpenBLAS = arithmetic of the reference's LUFactorization (Julia not runnable here)"},
+        "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import linearsolve_jl_b200 as ls
+    C = ls._capi
+
+    if not os.path.exists(C.LIB_PATH):
+        raise SystemExit("libb200lu.so missing — run `python __graft_entry__.py build` (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n, nrhs = args.n, args.nrhs
+    dtype_code = {"lu": C.F64, "mixed": C.MIXED, "batched": C.F64}[args.workload]
+    h = ls.Handle(dtype_code, device=local)
+    if args.nb:
+        h.set_option(C.OPT_NB, args.nb)
+    if args.lookahead >= 0:
+        h.set_option(C.OPT_LOOKAHEAD, args.lookahead)
+
+    if args.workload == "batched":
+        return bench_batched(args, ls, h, torch, dev, rank, world, barrier, max_over_ranks)
+
+    # ---------------- synthetic inputs resident in HBM (seeded, per rank) ----------------
+    shift = 5.0 if args.workload == "mixed" else 0.0
+    A_dev = torch.empty((n, n), dtype=torch.float64, device=dev)      # column-major n x n (lda = n)
+    B_dev = torch.empty((nrhs, n), dtype=torch.float64, device=dev)   # nrhs columns of length n
+    X_dev = torch.empty_like(B_dev)
+    h.fill_uniform_device(A_dev.data_ptr(), n, n, n, seed=123 + rank, diag_shift=shift)
+    h.fill_uniform_device(B_dev.data_ptr(), n, n, nrhs, seed=977 + rank)
+
+    def step_device():
+        info = h.factor_device(A_dev.data_ptr(), n, n)
+        t_f = h.timing(C.T_FACTOR) + h.timing(C.T_H2D)
+        h.solve_device(B_dev.data_ptr(), n, X_dev.data_ptr(), n, nrhs)
+        return info, t_f, h.timing(C.T_SOLVE)
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = ls.launch_count()
+    t0 = time.perf_counter()
+    tf = ts = 0.0
+    for _ in range(args.steps):
+        info, a, b = step_device()
+        tf += a
+        ts += b
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = ls.launch_count() - l0
+    clocks = sampler.stop()
+    assert info == 0
+    dev_ms = max_over_ranks((tf + ts) / args.steps)
+    wall_ms = max_over_ranks(wall / args.steps * 1e3)
+    value = world * lu_flops(n) / (dev_ms * 1e-3) / 1e9
+
+    # residual check of the last step (not timed): the answer must be right
+    Ah = A_dev.cpu().numpy().T  # (n, n) matrix: element [i, j] = A_dev[j, i]
+    xh = X_dev[0].cpu().numpy()
+    bh = B_dev[0].cpu().numpy()
+    berr = float(np.linalg.norm(Ah @ xh - bh) / (np.linalg.norm(Ah) * np.linalg.norm(xh)))
+    assert berr <= 10 * n * np.finfo(np.float64).eps, f"backward error {berr}"
+
+    # ---------------- in-situ roofline of the dominant kernel (extra profiled steps) -------
+    h.set_option(C.OPT_PROFILE, 1)
+    g_ms = g_fl = g_n = 0.0
+    for _ in range(2):
+        h.factor_device(A_dev.data_ptr(), n, n)
+        g_ms += h.timing(C.T_GEMM); g_fl += h.counter(C.C_GEMM_FLOPS); g_n += h.counter(C.C_GEMM_LAUNCHES)
+        t_fact_prof = h.timing(C.T_FACTOR)
+    h.set_option(C.OPT_PROFILE, 0)
+    peak_dmma = h.probe_peak(C.PEAK_FP64_DMMA)
+    peak_dfma = h.probe_peak(C.PEAK_FP64_DFMA)
+    hbm_copy = h.probe_peak(C.PEAK_HBM_COPY)
+    achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    peaks_file = {}
+    try:
+        peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
+    roofline = {
+        "bound": "tensor", "kernel": "dgemm_sub_kernel (FP64 DMMA trailing update)",
+        "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma if peak_dmma else None,
+        "traffic": None,
+        "peak_source": "library DMMA.8x8x4 register-resident probe on this GPU (no FP64 entry in MEASURED_PEAKS.json)",
+        "launches_profiled": int(g_n), "gemm_share_of_getrf": (g_ms / 2) / t_fact_prof if t_fact_prof else None,
+        "dfma_probe_tflops": peak_dfma, "hbm_copy_probe_gbs": hbm_copy,
+        "getrf_frac_of_fp64_peak": (lu_flops(n) / ((tf / args.steps) * 1e-3) / 1e12) / peak_dmma if peak_dmma else None,
+        "getrs": {"bound": "hbm",
+                  "achieved": (1 if nrhs == 1 else -(-nrhs // 8)) * 8.0 * n * n / ((ts / args.steps) * 1e-3) / 1e9,
+                  "peak": hbm_peak, "unit": "GB/s",
+                  "note": "8 n^2 bytes of factors per pass; nrhs > 1 runs ceil(nrhs/8) passes of 8 right-hand sides"},
+    }
+
+    line = {
+        "metric": "FP64 LU GFLOP/s (2/3 n^3), getrf + getrs over nrhs right-hand sides",
+        "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if args.workload == "lu" else "f32 factor + f64 refine", "data": "synthetic",
+        "config": {"workload": f"f64 getrf n={n} + getrs {nrhs} rhs (LinearCache reuse)", "n": n, "nrhs": nrhs,
+                   "multi_gpu": "independent replicas per rank" if world > 1 else "single GPU",
+                   "l2": "inputs (A = %.0f MiB) larger than L2" % (n * n * 8 / 2 ** 20),
+                   "nb": h.get_option(C.OPT_NB), "lookahead": h.get_option(C.OPT_LOOKAHEAD)},
+        "getrf_ms": tf / args.steps, "getrs_ms": ts / args.steps, "wall_ms_per_step": wall_ms,
+        "getrf_gflops": lu_flops(n) / ((tf / args.steps) * 1e-3) / 1e9,
+        "backward_error": berr, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+    }
+
+    # ---------------- e2e through the public API with pinned host buffers -----------------
+    if not args.no_e2e:
+        A_pin = torch.empty((n, n), dtype=torch.float64).pin_memory()
+        A_pin.copy_(A_dev.cpu())
+        A_host = A_pin.numpy().T            # Fortran-ordered view: [i, j] = entry (i, j)
+        B_pin = torch.empty((nrhs, n), dtype=torch.float64).pin_memory()
+        B_pin.copy_(B_dev.cpu())
+        B_host = B_pin.numpy()
+        cache = ls.init(ls.LinearProblem(A_host, B_host[0]), ls.B200LUFactorization(device=local),
+                        alias_A=True, alias_b=True)
+
+        def step_e2e():
+            cache.A = A_host                 # fresh matrix -> refactor (H2D of A inside)
+            for r in range(nrhs):
+                cache.b = B_host[r]          # cache reuse: getrs only (H2D b, D2H x inside)
+                sol = ls.solve_(cache)
+            return sol
+
+        e2e_steps = max(1, min(args.steps, 3))
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sol = step_e2e()
+        barrier()
+        te = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        assert sol.retcode == ls.ReturnCode.Success
+        line["e2e"] = {"value": world * lu_flops(n) / te / 1e9, "unit": "GFLOP/s",
+                       "h2d_bytes_per_step": n * n * 8 + nrhs * n * 8,
+                       "d2h_bytes_per_step": nrhs * n * 8 + n * 8, "ms_per_step": te * 1e3, "steps": e2e_steps,
+                       "api": "init(LinearProblem) ; cache.A = A ; 100 x (cache.b = b_i ; solve!(cache))"}
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only) --------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Af = np.asfortranarray(Ah)
+        Bf = np.asfortranarray(B_dev.cpu().numpy().T)
+        t0 = time.perf_counter()
+        cpu_lu_step(Af, Bf)
+        tc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": lu_flops(n) / tc / 1e9, "unit": "GFLOP/s", "cores": host_threads(),
+                                "kind": "port", "sample": "the full workload once (LAPACK dgetrf + dgetrs, scipy OpenBLAS)",
+                                "seconds": tc}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_batched(args, ls, h, torch, dev, rank, world, barrier, max_over_ranks):
+    """BASELINE config 4: `batch` independent 64x64 FP64 systems sharded by batch index."""
+    C = ls._capi
+    n = 64
+    per = args.batch // world
+    A_dev = torch.empty((per, n, n), dtype=torch.float64, device=dev)
+    b_dev = torch.empty((per, n), dtype=torch.float64, device=dev)
+    x_dev = torch.empty_like(b_dev)
+    h.fill_uniform_device(A_dev.data_ptr(), n, n, per * n, seed=5 + rank, diag_shift=0.0)
+    A_dev += 64.0 * torch.eye(n, device=dev, dtype=torch.float64)
+    h.fill_uniform_device(b_dev.data_ptr(), n, n, per, seed=6 + rank)
+
+    def step():
+        bad = h.factor_batched_device(A_dev.data_ptr(), per, n)
+        tf = h.timing(C.T_FACTOR)
+        h.solve_batched_device(b_dev.data_ptr(), x_dev.data_ptr(), 1)
+        return bad, tf, h.timing(C.T_SOLVE)
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    barrier()
+    sampler.start()
+    l0 = ls.launch_count()
+    tf = ts = 0.0
+    for _ in range(args.steps):
+        bad, a, b = step()
+        tf += a; ts += b
+    barrier()
+    clocks = sampler.stop()
+    launches = ls.launch_count() - l0
+    assert bad == 0
+    ms = max_over_ranks((tf + ts) / args.steps)
+    value = world * per / (ms * 1e-3)
+    r = torch.einsum("sji,sj->si", A_dev, x_dev) - b_dev
+    assert float(r.abs().max()) < 1e-10
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    bytes_factor = per * (2 * n * n * 8 + n * 4 + 4)
+    ach = bytes_factor / ((tf / args.steps) * 1e-3) / 1e9
+    line = {"metric": "batched independent 64x64 FP64 solves/s (factor + solve, factors kept)", "value": value,
+            "unit": "systems/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": f"{args.batch} systems of 64x64 f64, sharded by batch index",
+                                            "l2": "inputs (%.0f MiB) larger than L2" % (per * n * n * 8 / 2 ** 20)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "getrf_batched_kernel<double,64>", "achieved": ach, "peak": hbm,
+                         "unit": "GB/s", "frac": ach / hbm, "traffic": None}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

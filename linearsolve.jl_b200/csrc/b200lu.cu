@@ -1,0 +1,1287 @@
+// b200lu.cu — host driver and C ABI of libb200lu.so (see include/b200lu.h).
+//
+// getrf driver: right-looking blocked LU with a recursive panel and one-panel
+// look-ahead on a high-priority stream — the GPU restatement of the
+// reference's `_blocked_lufact!` (src/blocked_lufact.jl:658-679): panel ->
+// laswp (left + right) -> unit-lower TRSM -> Schur GEMM.  Everything is
+// stream-ordered; the host never synchronises inside a factorization.
+#include "../../include/b200lu.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "batched.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "laswp.cuh"
+#include "panel.cuh"
+#include "trsm.cuh"
+#include "trsv.cuh"
+#include "util_kernels.cuh"
+
+namespace b200lu {
+unsigned long long g_launch_count = 0;
+}
+using namespace b200lu;
+
+#define B200LU_VERSION 100
+
+// ------------------------------------------------------------------ handle --
+struct b200lu_handle {
+    int dtype = 0;
+    int dev = 0;
+    cudaStream_t s_main = nullptr, s_panel = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_next = nullptr;
+    std::vector<cudaEvent_t> ev_panel;
+    char err[512] = {0};
+    double timing[B200LU_T_COUNT] = {0};
+    int64_t opt[B200LU_OPT_COUNT];
+
+    // single large system
+    int64_t n = 0, ldd = 0, cap_n = 0;
+    void* dA = nullptr;        // factors (double for F64, float for F32/MIXED)
+    double* dA64 = nullptr;    // MIXED: FP64 copy of A for residuals
+    int* d_ipiv = nullptr;
+    int* d_perm = nullptr;
+    int* d_info = nullptr;
+    int* d_deverr = nullptr;
+    LaswpPlan* d_plans = nullptr;
+    int cap_plans = 0;
+    void* d_panelsync = nullptr;
+    int panel_epoch = 0;
+    bool factored = false;
+    int64_t info = 0;
+    // solve state
+    bool solve_ready = false;
+    void* d_dinvL = nullptr;
+    void* d_dinvU = nullptr;
+    int* d_tflags = nullptr;
+    int* d_tticket = nullptr;
+    int cap_tgroups = 0;
+    int trsv_epoch = 0;
+    void* d_B = nullptr;       // staging for host solves / permuted rhs
+    void* d_X = nullptr;
+    int64_t cap_rhs = 0;
+    // refinement scratch (MIXED)
+    double* d_r = nullptr;     // residual (n)
+    float* d_r32 = nullptr;    // residual cast / correction (n)
+    double* d_scal = nullptr;  // [4] norms
+    double normA_F = 0.0;
+    int last_refine_iters = 0;
+    // pinned host staging
+    long long* h_ipiv = nullptr;
+    int64_t cap_hipiv = 0;
+    int* h_small = nullptr;    // [16] info/deverr/...
+    double* h_scal = nullptr;  // [4]
+
+    // batched
+    int64_t b_batch = 0, b_n = 0, b_cap_bytes = 0, b_cap_batch_n = 0;
+    void* dB_LU = nullptr;
+    int* dB_ipiv = nullptr;
+    int* dB_info = nullptr;
+    void* dB_in = nullptr;     // host-path staging for A
+    int64_t b_cap_in = 0;
+    void* dB_rhs = nullptr;
+    void* dB_x = nullptr;
+    int64_t b_cap_rhs = 0;
+    long long* hB_ipiv = nullptr;
+    int* hB_info = nullptr;
+    int64_t hb_cap = 0;
+    bool b_factored = false;
+
+    // profiling (B200LU_OPT_PROFILE)
+    std::vector<cudaEvent_t> prof_ev;
+    int prof_used = 0;
+    double prof_flops = 0.0;
+    double counters[B200LU_C_COUNT] = {0};
+
+    // distributed (filled by dist.cuh)
+    void* comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+static int set_err(b200lu_handle* h, int status, const char* fmt, ...) {
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+    }
+    return status;
+}
+
+#define CU_TRY(h, expr)                                                                        \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return set_err((h), 1, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, \
+                           __LINE__, cudaGetErrorString(_e));                                  \
+    } while (0)
+
+#define LAUNCH_CHECK(h)                                                                        \
+    do {                                                                                       \
+        B200LU_COUNT_LAUNCH();                                                                 \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess)                                                                 \
+            return set_err((h), 1, "kernel launch failed %s at %s:%d: %s", cudaGetErrorName(_e), \
+                           __FILE__, __LINE__, cudaGetErrorString(_e));                        \
+    } while (0)
+
+static size_t elem_size(const b200lu_handle* h) { return h->dtype == B200LU_F64 ? 8 : 4; }
+static size_t iface_size(const b200lu_handle* h) { return h->dtype == B200LU_F32 ? 4 : 8; }
+
+template <typename P>
+static void free_dev(P*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+// --------------------------------------------------------- panel sync blob --
+struct PanelSyncLayout {
+    size_t off_flags, off_cval, off_cidx, off_rowbuf, off_toprow, off_progress, total;
+};
+static PanelSyncLayout panel_sync_layout() {
+    PanelSyncLayout L;
+    size_t o = 0;
+    L.off_flags = o;   o += sizeof(int) * 2 * PANEL_GMAX;
+    L.off_cidx = o;    o += sizeof(int) * 2 * PANEL_GMAX;
+    L.off_progress = o; o += 64;
+    o = (o + 255) & ~(size_t)255;
+    L.off_cval = o;    o += sizeof(double) * 2 * PANEL_GMAX;
+    L.off_toprow = o;  o += sizeof(double) * 2 * PANEL_WMAX;
+    L.off_rowbuf = o;  o += sizeof(double) * 2 * PANEL_GMAX * PANEL_WMAX;
+    L.total = o;
+    return L;
+}
+
+// ------------------------------------------------------------ kernel launch --
+constexpr int BASE_W = 16;    // base panel width (columns held in registers)
+constexpr int BASE_RPT = 2;   // rows per thread
+constexpr int BASE_NT = 256;  // threads per panel CTA
+
+template <typename T>
+static int launch_panel_base(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda, int nrows,
+                             int j0, int wc, int pc0, int pc1) {
+    const PanelSyncLayout L = panel_sync_layout();
+    char* blob = (char*)h->d_panelsync;
+    PanelArgs<T> p;
+    p.A = A;
+    p.lda = lda;
+    p.j0 = j0;
+    p.m = nrows - j0;
+    p.wc = wc;
+    p.pc0 = pc0;
+    p.pc1 = pc1;
+    p.ipiv = h->d_ipiv;
+    p.info = h->d_info;
+    const int rows_per_cta = BASE_NT * BASE_RPT;
+    int G = cdiv(p.m, rows_per_cta);
+    const int gmax = (int)std::min<int64_t>(PANEL_GMAX, h->opt[B200LU_OPT_PANEL_CTAS]);
+    if (G > gmax)
+        return set_err(h, 2, "panel of %d rows needs %d CTAs > limit %d", p.m, G, gmax);
+    p.G = G;
+    if (h->panel_epoch > (1 << 30)) {
+        CU_TRY(h, cudaMemsetAsync(blob, 0, L.off_cval, st));
+        h->panel_epoch = 0;
+    }
+    p.epoch = h->panel_epoch;
+    h->panel_epoch += BASE_W;
+    p.flags = (int*)(blob + L.off_flags);
+    p.cand_idx = (int*)(blob + L.off_cidx);
+    p.progress = (int*)(blob + L.off_progress);
+    p.cand_val = (T*)(blob + L.off_cval);
+    p.toprow = (T*)(blob + L.off_toprow);
+    p.rowbuf = (T*)(blob + L.off_rowbuf);
+    p.deverr = h->d_deverr;
+    const int has_swapper = (pc1 - pc0) > wc ? 1 : 0;
+    panel_base_kernel<T, BASE_W, BASE_RPT, BASE_NT><<<G + has_swapper, BASE_NT, 0, st>>>(p);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+template <typename T>
+static int launch_trsm(b200lu_handle* h, cudaStream_t st, const T* Lp, int64_t ldl, T* Bp,
+                       int64_t ldb, int w, int ncols) {
+    if (w <= 0 || ncols <= 0) return 0;
+    constexpr int CC = 4, NWARP = 8;
+    const int grid = cdiv(ncols, CC * NWARP);
+    const int rpl = cdiv(w, 32);
+#define TRSM_CASE(R)                                                                             \
+    {                                                                                            \
+        const size_t smem = (size_t)32 * (R * 32) * sizeof(T);                                   \
+        static bool attr_set = false;                                                            \
+        if (!attr_set) {                                                                         \
+            CU_TRY(h, cudaFuncSetAttribute(trsm_lunit_kernel<T, R, CC, NWARP>,                   \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_set = true;                                                                     \
+        }                                                                                        \
+        trsm_lunit_kernel<T, R, CC, NWARP><<<grid, NWARP * 32, smem, st>>>(Lp, ldl, Bp, ldb, w, ncols); \
+    }
+    if (rpl <= 1) TRSM_CASE(1)
+    else if (rpl <= 2) TRSM_CASE(2)
+    else if (rpl <= 4) TRSM_CASE(4)
+    else if (rpl <= 8) TRSM_CASE(8)
+    else return set_err(h, 2, "trsm block %d too wide", w);
+#undef TRSM_CASE
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// FP64 Schur update on DMMA
+using DCfg = DgemmCfg<128, 64, 16, 2, 2, 3>;
+static int launch_gemm(b200lu_handle* h, cudaStream_t st, int M, int N, int K, const double* A,
+                       int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    auto kern = dgemm_sub_kernel<128, 64, 16, 2, 2, 3, 2>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)DCfg::SMEM));
+        attr_set = true;
+    }
+    const int tm = cdiv(M, 128), tn = cdiv(N, 64);
+    kern<<<tm * tn, DCfg::NT, DCfg::SMEM, st>>>(M, N, K, A, lda, B, ldb, C, ldc, tm, tn, 16);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+static int launch_gemm(b200lu_handle* h, cudaStream_t st, int M, int N, int K, const float* A,
+                       int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    dim3 grid(cdiv(M, 128), cdiv(N, 128));
+    sgemm_sub_kernel<128, 128, 8><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// trailing-update GEMM, optionally bracketed by events for the in-situ roofline
+template <typename T>
+static int launch_gemm_prof(b200lu_handle* h, cudaStream_t st, int M, int N, int K, const T* A,
+                            int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    const bool prof = h->opt[B200LU_OPT_PROFILE] != 0;
+    if (prof) {
+        while ((int)h->prof_ev.size() < h->prof_used + 2) {
+            cudaEvent_t e;
+            CU_TRY(h, cudaEventCreate(&e));
+            h->prof_ev.push_back(e);
+        }
+        CU_TRY(h, cudaEventRecord(h->prof_ev[h->prof_used], st));
+    }
+    int rc = launch_gemm(h, st, M, N, K, A, lda, B, ldb, C, ldc);
+    if (rc) return rc;
+    if (prof) {
+        CU_TRY(h, cudaEventRecord(h->prof_ev[h->prof_used + 1], st));
+        h->prof_used += 2;
+        h->prof_flops += 2.0 * M * (double)N * K;
+    }
+    return 0;
+}
+
+template <typename T>
+static int launch_laswp(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda, int c0, int c1,
+                        const LaswpPlan* plan) {
+    if (c1 <= c0) return 0;
+    constexpr int CW = 8, NT = 256;
+    const int grid = std::min(cdiv(c1 - c0, CW), 148 * 8);
+    laswp_apply_kernel<T, CW, NT><<<grid, NT, 0, st>>>(A, lda, c0, c1, plan);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// ---------------------------------------------------------- recursive panel --
+// Factor columns [j0, j0+w) of the nrows x * matrix (rows j0..nrows-1) inside the
+// outer panel [pc0, pc1).  Interchanges are applied to the whole outer panel by
+// the base kernel's swapper CTA, so no laswp appears here.
+template <typename T>
+static int panel_recursive(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda, int nrows, int j0,
+                           int w, int pc0, int pc1) {
+    if (w <= BASE_W) return launch_panel_base<T>(h, st, A, lda, nrows, j0, w, pc0, pc1);
+    const int w1 = ((w / 2 + BASE_W - 1) / BASE_W) * BASE_W;
+    const int w2 = w - w1;
+    int rc = panel_recursive<T>(h, st, A, lda, nrows, j0, w1, pc0, pc1);
+    if (rc) return rc;
+    T* L11 = A + (int64_t)j0 * lda + j0;
+    T* A12 = A + (int64_t)(j0 + w1) * lda + j0;
+    rc = launch_trsm<T>(h, st, L11, lda, A12, lda, w1, w2);
+    if (rc) return rc;
+    const int mrest = nrows - (j0 + w1);
+    rc = launch_gemm(h, st, mrest, w2, w1, A + (int64_t)j0 * lda + (j0 + w1), lda, A12, lda,
+                     A + (int64_t)(j0 + w1) * lda + (j0 + w1), lda);
+    if (rc) return rc;
+    return panel_recursive<T>(h, st, A, lda, nrows, j0 + w1, w2, pc0, pc1);
+}
+
+static int ensure_events(b200lu_handle* h, int count) {
+    while ((int)h->ev_panel.size() < count) {
+        cudaEvent_t e;
+        CU_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_panel.push_back(e);
+    }
+    return 0;
+}
+
+// getrf of the n x n matrix in `A` (device, leading dim lda): columns [0, ncols)
+// are local.  Single-GPU: ncols == n.
+template <typename T>
+static int getrf_device(b200lu_handle* h, T* A, int64_t lda, int n) {
+    const int nb = (int)h->opt[B200LU_OPT_NB];
+    const bool la = h->opt[B200LU_OPT_LOOKAHEAD] != 0;
+    const int nblk = cdiv(n, nb);
+    int rc = ensure_events(h, nblk + 1);
+    if (rc) return rc;
+    cudaStream_t sm = h->s_main;
+    cudaStream_t sp = la ? h->s_panel : h->s_main;
+
+    CU_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), sm));
+    iota_kernel<<<cdiv(n, 256), 256, 0, sm>>>(h->d_perm, n);
+    LAUNCH_CHECK(h);
+    if (la) {
+        CU_TRY(h, cudaEventRecord(h->ev_fork, sm));
+        CU_TRY(h, cudaStreamWaitEvent(sp, h->ev_fork, 0));
+    }
+    {
+        const int jb = std::min(nb, n);
+        rc = panel_recursive<T>(h, sp, A, lda, n, 0, jb, 0, jb);
+        if (rc) return rc;
+        laswp_plan_kernel<<<1, 32, 0, sp>>>(h->d_ipiv, 0, jb, h->d_plans + 0);
+        LAUNCH_CHECK(h);
+        if (la) CU_TRY(h, cudaEventRecord(h->ev_panel[0], sp));
+    }
+    for (int k = 0; k < nblk; ++k) {
+        const int j0 = k * nb;
+        const int jb = std::min(nb, n - j0);
+        const int j1 = j0 + jb;
+        const LaswpPlan* plan = h->d_plans + k;
+        if (la) CU_TRY(h, cudaStreamWaitEvent(sm, h->ev_panel[k], 0));
+        rc = launch_laswp<T>(h, sm, A, lda, 0, j0, plan);
+        if (rc) return rc;
+        rc = launch_laswp<T>(h, sm, A, lda, j1, n, plan);
+        if (rc) return rc;
+        rc = launch_laswp<int>(h, sm, h->d_perm, n, 0, 1, plan);
+        if (rc) return rc;
+        if (j1 >= n) break;
+        T* L11 = A + (int64_t)j0 * lda + j0;
+        T* L21 = A + (int64_t)j0 * lda + j1;
+        const int jb2 = std::min(nb, n - j1);
+        // next panel's columns first (look-ahead)
+        rc = launch_trsm<T>(h, sm, L11, lda, A + (int64_t)j1 * lda + j0, lda, jb, jb2);
+        if (rc) return rc;
+        rc = launch_gemm(h, sm, n - j1, jb2, jb, L21, lda, A + (int64_t)j1 * lda + j0, lda,
+                         A + (int64_t)j1 * lda + j1, lda);
+        if (rc) return rc;
+        if (la) {
+            CU_TRY(h, cudaEventRecord(h->ev_next, sm));
+            CU_TRY(h, cudaStreamWaitEvent(sp, h->ev_next, 0));
+        }
+        rc = panel_recursive<T>(h, sp, A, lda, n, j1, jb2, j1, j1 + jb2);
+        if (rc) return rc;
+        laswp_plan_kernel<<<1, 32, 0, sp>>>(h->d_ipiv, j1, jb2, h->d_plans + (k + 1));
+        LAUNCH_CHECK(h);
+        if (la) CU_TRY(h, cudaEventRecord(h->ev_panel[k + 1], sp));
+        // rest of the trailing matrix
+        const int c2 = j1 + jb2;
+        if (c2 < n) {
+            rc = launch_trsm<T>(h, sm, L11, lda, A + (int64_t)c2 * lda + j0, lda, jb, n - c2);
+            if (rc) return rc;
+            rc = launch_gemm_prof<T>(h, sm, n - j1, n - c2, jb, L21, lda, A + (int64_t)c2 * lda + j0, lda,
+                                     A + (int64_t)c2 * lda + j1, lda);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------- capacity --
+static int ensure_capacity(b200lu_handle* h, int64_t n) {
+    if (n <= h->cap_n) {
+        if (n != h->n) {
+            h->n = n;
+            h->ldd = ((n + 15) / 16) * 16;
+            // keep padding rows finite for the 16-byte chunk loads
+            CU_TRY(h, cudaMemsetAsync(h->dA, 0, (size_t)h->ldd * n * elem_size(h), h->s_main));
+        }
+        return 0;
+    }
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    free_dev(h->dA);
+    free_dev(h->dA64);
+    free_dev(h->d_ipiv);
+    free_dev(h->d_perm);
+    free_dev(h->d_plans);
+    free_dev(h->d_dinvL);
+    free_dev(h->d_dinvU);
+    free_dev(h->d_r);
+    free_dev(h->d_r32);
+    h->n = n;
+    h->ldd = ((n + 15) / 16) * 16;
+    h->cap_n = n;
+    const size_t es = elem_size(h);
+    CU_TRY(h, cudaMalloc(&h->dA, (size_t)h->ldd * n * es));
+    CU_TRY(h, cudaMemsetAsync(h->dA, 0, (size_t)h->ldd * n * es, h->s_main));
+    if (h->dtype == B200LU_MIXED) {
+        CU_TRY(h, cudaMalloc((void**)&h->dA64, (size_t)h->ldd * n * 8));
+        CU_TRY(h, cudaMalloc((void**)&h->d_r, (size_t)n * 8));
+        CU_TRY(h, cudaMalloc((void**)&h->d_r32, (size_t)n * 4));
+    }
+    CU_TRY(h, cudaMalloc((void**)&h->d_ipiv, (size_t)n * sizeof(int)));
+    CU_TRY(h, cudaMalloc((void**)&h->d_perm, (size_t)n * sizeof(int)));
+    h->cap_plans = cdiv(n, 16) + 1;
+    CU_TRY(h, cudaMalloc((void**)&h->d_plans, (size_t)h->cap_plans * sizeof(LaswpPlan)));
+    const int nblk = cdiv(n, TRSV_TB);
+    CU_TRY(h, cudaMalloc(&h->d_dinvL, (size_t)nblk * TRSV_TB * TRSV_TB * es));
+    CU_TRY(h, cudaMalloc(&h->d_dinvU, (size_t)nblk * TRSV_TB * TRSV_TB * es));
+    free_dev(h->d_tflags);
+    h->cap_tgroups = 0;
+    if (n > h->cap_hipiv) {
+        if (h->h_ipiv) cudaFreeHost(h->h_ipiv);
+        CU_TRY(h, cudaMallocHost((void**)&h->h_ipiv, (size_t)n * sizeof(long long)));
+        h->cap_hipiv = n;
+    }
+    h->cap_rhs = 0;
+    free_dev(h->d_B);
+    free_dev(h->d_X);
+    return 0;
+}
+
+static int ensure_rhs(b200lu_handle* h, int64_t nrhs) {
+    if (nrhs <= h->cap_rhs) return 0;
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    free_dev(h->d_B);
+    free_dev(h->d_X);
+    CU_TRY(h, cudaMalloc(&h->d_B, (size_t)h->cap_n * nrhs * 8));
+    CU_TRY(h, cudaMalloc(&h->d_X, (size_t)h->cap_n * nrhs * 8));
+    h->cap_rhs = nrhs;
+    return 0;
+}
+
+static int ensure_trsv_groups(b200lu_handle* h, int groups) {
+    if (groups <= h->cap_tgroups) return 0;
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    free_dev(h->d_tflags);
+    free_dev(h->d_tticket);
+    const int nblk = cdiv(h->cap_n, TRSV_TB);
+    CU_TRY(h, cudaMalloc((void**)&h->d_tflags, (size_t)groups * nblk * sizeof(int)));
+    CU_TRY(h, cudaMemset(h->d_tflags, 0, (size_t)groups * nblk * sizeof(int)));
+    CU_TRY(h, cudaMalloc((void**)&h->d_tticket, (size_t)groups * sizeof(int)));
+    h->cap_tgroups = groups;
+    h->trsv_epoch = 0;
+    return 0;
+}
+
+// ------------------------------------------------------------------- getrs --
+template <typename T>
+static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, T* X, int64_t ldx,
+                       int nrhs) {
+    cudaStream_t st = h->s_main;
+    const int nblk = cdiv(n, TRSV_TB);
+    if (!h->solve_ready) {
+        const size_t tsm = sizeof(T) * TRSV_TB * (2 * TRSV_TB + 1);
+        static bool attr_set = false;
+        if (!attr_set) {
+            CU_TRY(h, cudaFuncSetAttribute(trtri_diag_kernel<T>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+            attr_set = true;
+        }
+        trtri_diag_kernel<T><<<nblk, TRSV_TB, tsm, st>>>(A, lda, n, (T*)h->d_dinvL, 0);
+        LAUNCH_CHECK(h);
+        trtri_diag_kernel<T><<<nblk, TRSV_TB, tsm, st>>>(A, lda, n, (T*)h->d_dinvU, 1);
+        LAUNCH_CHECK(h);
+        h->solve_ready = true;
+    }
+    const int tile = (int)h->opt[B200LU_OPT_SOLVE_NRHS_TILE];
+    const int NR = nrhs == 1 ? 1 : (tile >= 8 ? 8 : (tile >= 4 ? 4 : 1));
+    const int groups = cdiv(nrhs, NR);
+    int rc = ensure_trsv_groups(h, groups);
+    if (rc) return rc;
+    TrsvSync sy{h->d_tflags, h->d_tticket, h->d_deverr};
+    dim3 grid(nblk, groups);
+    for (int upper = 0; upper < 2; ++upper) {
+        if (h->trsv_epoch > (1 << 30)) {
+            CU_TRY(h, cudaMemsetAsync(h->d_tflags, 0, (size_t)h->cap_tgroups * cdiv(h->cap_n, TRSV_TB) * sizeof(int), st));
+            h->trsv_epoch = 0;
+        }
+        const int epoch = ++h->trsv_epoch;
+        CU_TRY(h, cudaMemsetAsync(h->d_tticket, 0, (size_t)groups * sizeof(int), st));
+        const T* dinv = (const T*)(upper ? h->d_dinvU : h->d_dinvL);
+#define TRSV_LAUNCH(NRV)                                                                      \
+    if (upper)                                                                                \
+        trsv_block_kernel<T, NRV, true><<<grid, 256, 0, st>>>(A, lda, n, dinv, X, ldx, nrhs, sy, \
+                                                              epoch, 0, nblk);               \
+    else                                                                                      \
+        trsv_block_kernel<T, NRV, false><<<grid, 256, 0, st>>>(A, lda, n, dinv, X, ldx, nrhs, sy, \
+                                                               epoch, 0, nblk);
+        if (NR == 1) { TRSV_LAUNCH(1) }
+        else if (NR == 4) { TRSV_LAUNCH(4) }
+        else { TRSV_LAUNCH(8) }
+#undef TRSV_LAUNCH
+        LAUNCH_CHECK(h);
+    }
+    return 0;
+}
+
+// X = A^{-1} B on the device with the cached factors, all in the factor type T.
+// B and X may alias.
+template <typename T>
+static int getrs_device(b200lu_handle* h, const T* B, int64_t ldb, T* X, int64_t ldx, int nrhs) {
+    const int n = (int)h->n;
+    cudaStream_t st = h->s_main;
+    const T* src = B;
+    int64_t lds = ldb;
+    if ((const void*)B == (const void*)X) {
+        // in-place permutation is not a gather: stage through d_B
+        int rc = ensure_rhs(h, nrhs);
+        if (rc) return rc;
+        CU_TRY(h, cudaMemcpy2DAsync(h->d_B, (size_t)n * sizeof(T), B, (size_t)ldb * sizeof(T),
+                                    (size_t)n * sizeof(T), nrhs, cudaMemcpyDeviceToDevice, st));
+        src = (const T*)h->d_B;
+        lds = n;
+    }
+    dim3 pg(cdiv(n, 256), nrhs);
+    permute_rows_kernel<T><<<pg, 256, 0, st>>>(src, lds, X, ldx, h->d_perm, n, nrhs, 0);
+    LAUNCH_CHECK(h);
+    return trsv_sweeps<T>(h, (const T*)h->dA, h->ldd, n, X, ldx, nrhs);
+}
+
+// MIXED: FP32 factors + FP64 residual refinement, one right-hand side at a time.
+static int refine_solve_device(b200lu_handle* h, const double* B, int64_t ldb, double* X,
+                               int64_t ldx, int nrhs) {
+    const int n = (int)h->n;
+    cudaStream_t st = h->s_main;
+    const int maxit = (int)h->opt[B200LU_OPT_REFINE_MAXIT];
+    const double eps = 2.220446049250313e-16;
+    int rc = ensure_rhs(h, 1);
+    if (rc) return rc;
+    float* w32 = (float*)h->d_X;  // n floats of scratch
+    h->last_refine_iters = 0;
+    for (int c = 0; c < nrhs; ++c) {
+        const double* b = B + (int64_t)c * ldb;
+        double* x = X + (int64_t)c * ldx;
+        // x0 = fl64( solve32( fl32(b) ) )
+        cast2d_kernel<double, float><<<dim3(cdiv(n, 256), 1), 256, 0, st>>>(b, n, h->d_r32, n, n, 1);
+        LAUNCH_CHECK(h);
+        rc = getrs_device<float>(h, h->d_r32, n, w32, n, 1);
+        if (rc) return rc;
+        // b may alias x: keep a copy of b in d_r's sibling (d_B, FP64)
+        double* bcopy = (double*)h->d_B;
+        CU_TRY(h, cudaMemcpyAsync(bcopy, b, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+        cast2d_kernel<float, double><<<dim3(cdiv(n, 256), 1), 256, 0, st>>>(w32, n, x, n, n, 1);
+        LAUNCH_CHECK(h);
+        double prev = 1e300;
+        for (int it = 0; it < maxit; ++it) {
+            // r = b - A x in FP64
+            CU_TRY(h, cudaMemcpyAsync(h->d_r, bcopy, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+            const int cchunk = 512;
+            residual_gemv_kernel<double><<<dim3(cdiv(n, 256), cdiv(n, cchunk)), 256, 0, st>>>(
+                h->dA64, h->ldd, n, x, h->d_r, cchunk);
+            LAUNCH_CHECK(h);
+            CU_TRY(h, cudaMemsetAsync(h->d_scal, 0, 4 * sizeof(double), st));
+            sumsq_kernel<<<std::min(cdiv(n, 256), 1024), 256, 0, st>>>(h->d_r, n, h->d_scal + 0);
+            LAUNCH_CHECK(h);
+            sumsq_kernel<<<std::min(cdiv(n, 256), 1024), 256, 0, st>>>(x, n, h->d_scal + 1);
+            LAUNCH_CHECK(h);
+            CU_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 2 * sizeof(double),
+                                      cudaMemcpyDeviceToHost, st));
+            CU_TRY(h, cudaStreamSynchronize(st));
+            const double rn = sqrt(h->h_scal[0]), xn = sqrt(h->h_scal[1]);
+            const double berr = rn / (h->normA_F * xn + 1e-300);
+            h->last_refine_iters = std::max(h->last_refine_iters, it);
+            // converged to FP64 working accuracy, or stagnating
+            if (!(berr > 2.0 * eps) || !(berr < 0.5 * prev)) {
+                if (!(berr == berr)) return set_err(h, 3, "refinement produced NaN");
+                break;
+            }
+            prev = berr;
+            cast2d_kernel<double, float><<<dim3(cdiv(n, 256), 1), 256, 0, st>>>(h->d_r, n, h->d_r32, n, n, 1);
+            LAUNCH_CHECK(h);
+            rc = getrs_device<float>(h, h->d_r32, n, w32, n, 1);
+            if (rc) return rc;
+            axpy_f32_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, w32, n);
+            LAUNCH_CHECK(h);
+            h->last_refine_iters = std::max(h->last_refine_iters, it + 1);
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------- C ABI --
+extern "C" {
+
+int b200lu_version(void) { return B200LU_VERSION; }
+int64_t b200lu_launch_count(void) { return (int64_t)g_launch_count; }
+
+int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices) {
+    if (!out) return -1;
+    *out = nullptr;
+    if (dtype < 0 || dtype > 2) return -2;
+    if (ngpus != 1) return -3;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return 1;  // no CPU fallback
+    const int dev = devices ? devices[0] : 0;
+    if (dev < 0 || dev >= ndev) return -4;
+    if (cudaSetDevice(dev) != cudaSuccess) return 1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 1;
+    if (prop.major < 10) return 1;  // sm_100a code only
+    b200lu_handle* h = new b200lu_handle();
+    h->dtype = dtype;
+    h->dev = dev;
+    h->opt[B200LU_OPT_NB] = 256;
+    h->opt[B200LU_OPT_LOOKAHEAD] = 1;
+    h->opt[B200LU_OPT_REFINE_MAXIT] = 10;
+    h->opt[B200LU_OPT_PANEL_CTAS] = PANEL_GMAX;
+    h->opt[B200LU_OPT_SOLVE_NRHS_TILE] = 8;
+    h->opt[B200LU_OPT_PROFILE] = 0;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&h->s_panel, cudaStreamNonBlocking, hi) == cudaSuccess;
+    ok = ok && cudaEventCreate(&h->ev_a) == cudaSuccess && cudaEventCreate(&h->ev_b) == cudaSuccess;
+    ok = ok && cudaEventCreate(&h->ev_c) == cudaSuccess && cudaEventCreate(&h->ev_d) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_next, cudaEventDisableTiming) == cudaSuccess;
+    const PanelSyncLayout L = panel_sync_layout();
+    ok = ok && cudaMalloc(&h->d_panelsync, L.total) == cudaSuccess;
+    ok = ok && cudaMemset(h->d_panelsync, 0, L.total) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_info, 64) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_deverr, 64) == cudaSuccess;
+    ok = ok && cudaMemset(h->d_deverr, 0, 64) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->d_scal, 64) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&h->h_small, 64) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&h->h_scal, 64) == cudaSuccess;
+    if (!ok) {
+        b200lu_destroy(h);
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+void b200lu_destroy(b200lu_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->dev);
+    if (h->s_main) cudaStreamSynchronize(h->s_main);
+    if (h->s_panel) cudaStreamSynchronize(h->s_panel);
+    free_dev(h->dA); free_dev(h->dA64); free_dev(h->d_ipiv); free_dev(h->d_perm);
+    free_dev(h->d_info); free_dev(h->d_deverr); free_dev(h->d_plans); free_dev(h->d_panelsync);
+    free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_tflags); free_dev(h->d_tticket);
+    free_dev(h->d_B); free_dev(h->d_X); free_dev(h->d_r); free_dev(h->d_r32); free_dev(h->d_scal);
+    free_dev(h->dB_LU); free_dev(h->dB_ipiv); free_dev(h->dB_info); free_dev(h->dB_in);
+    free_dev(h->dB_rhs); free_dev(h->dB_x);
+    if (h->h_ipiv) cudaFreeHost(h->h_ipiv);
+    if (h->h_small) cudaFreeHost(h->h_small);
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    if (h->hB_ipiv) cudaFreeHost(h->hB_ipiv);
+    if (h->hB_info) cudaFreeHost(h->hB_info);
+    for (cudaEvent_t e : h->ev_panel) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    cudaEvent_t evs[] = {h->ev_a, h->ev_b, h->ev_c, h->ev_d, h->ev_fork, h->ev_next};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
+    if (h->s_main) cudaStreamDestroy(h->s_main);
+    if (h->s_panel) cudaStreamDestroy(h->s_panel);
+    delete h;
+}
+
+const char* b200lu_last_error(const b200lu_handle* h) { return h ? h->err : "null handle"; }
+
+double b200lu_last_timing(const b200lu_handle* h, int phase) {
+    if (!h || phase < 0 || phase >= B200LU_T_COUNT) return -1.0;
+    return h->timing[phase];
+}
+
+double b200lu_last_counter(const b200lu_handle* h, int which) {
+    if (!h || which < 0 || which >= B200LU_C_COUNT) return -1.0;
+    if (which == B200LU_C_REFINE_ITERS) return (double)h->last_refine_iters;
+    return h->counters[which];
+}
+
+int b200lu_probe_peak(b200lu_handle* h, int kind, double* out) {
+    if (!h || !out) return -1;
+    CU_TRY(h, cudaSetDevice(h->dev));
+    cudaStream_t st = h->s_main;
+    int sms = 0;
+    CU_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->dev));
+    double* sink = nullptr;
+    CU_TRY(h, cudaMalloc((void**)&sink, 1 << 20));
+    float best = 1e30f;
+    if (kind == B200LU_PEAK_FP64_DMMA || kind == B200LU_PEAK_FP64_DFMA) {
+        const int iters = 4096, ctas = sms * 4, thr = 256;
+        for (int rep = 0; rep < 5; ++rep) {
+            CU_TRY(h, cudaEventRecord(h->ev_a, st));
+            if (kind == B200LU_PEAK_FP64_DMMA) probe_dmma_kernel<<<ctas, thr, 0, st>>>(sink, iters);
+            else probe_dfma_kernel<<<ctas, thr, 0, st>>>(sink, iters);
+            LAUNCH_CHECK(h);
+            CU_TRY(h, cudaEventRecord(h->ev_b, st));
+            CU_TRY(h, cudaStreamSynchronize(st));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+            if (rep > 0) best = std::min(best, ms);
+        }
+        // per thread per iteration: DMMA probe = 16 m8n8k4 (256 FMA / 32 lanes each); DFMA probe = 16 FMAs
+        const double fma_per_thread_iter = (kind == B200LU_PEAK_FP64_DMMA) ? 16.0 * 8.0 : 16.0;
+        *out = 2.0 * fma_per_thread_iter * iters * (double)ctas * thr / (best * 1e-3) / 1e12;
+    } else if (kind == B200LU_PEAK_HBM_COPY) {
+        const size_t bytes = (size_t)1 << 30;
+        void *a = nullptr, *b = nullptr;
+        CU_TRY(h, cudaMalloc(&a, bytes));
+        CU_TRY(h, cudaMalloc(&b, bytes));
+        for (int rep = 0; rep < 5; ++rep) {
+            CU_TRY(h, cudaEventRecord(h->ev_a, st));
+            CU_TRY(h, cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice, st));
+            CU_TRY(h, cudaEventRecord(h->ev_b, st));
+            CU_TRY(h, cudaStreamSynchronize(st));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+            if (rep > 0) best = std::min(best, ms);
+        }
+        cudaFree(a);
+        cudaFree(b);
+        *out = 2.0 * (double)bytes / (best * 1e-3) / 1e9;
+    } else {
+        cudaFree(sink);
+        return set_err(h, -2, "unknown peak kind");
+    }
+    cudaFree(sink);
+    return 0;
+}
+
+int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
+    if (!h) return -1;
+    if (option < 0 || option >= B200LU_OPT_COUNT) return -2;
+    if (option == B200LU_OPT_NB) {
+        if (value < 16 || value > 256 || value % 16 != 0) return -3;
+    }
+    if (option == B200LU_OPT_PANEL_CTAS && (value < 1 || value > PANEL_GMAX)) return -3;
+    if (option == B200LU_OPT_REFINE_MAXIT && value < 0) return -3;
+    h->opt[option] = value;
+    return 0;
+}
+int64_t b200lu_get_option(const b200lu_handle* h, int option) {
+    if (!h || option < 0 || option >= B200LU_OPT_COUNT) return -1;
+    return h->opt[option];
+}
+
+// factor whatever already sits in h->dA (and dA64 for MIXED)
+static int factor_resident(b200lu_handle* h, int64_t n, int64_t* info) {
+    int rc;
+    h->factored = false;
+    h->solve_ready = false;
+    h->prof_used = 0;
+    h->prof_flops = 0.0;
+    CU_TRY(h, cudaEventRecord(h->ev_b, h->s_main));
+    if (h->dtype == B200LU_F64) {
+        rc = getrf_device<double>(h, (double*)h->dA, h->ldd, (int)n);
+    } else {
+        if (h->dtype == B200LU_MIXED) {
+            CU_TRY(h, cudaMemsetAsync(h->d_scal, 0, 4 * sizeof(double), h->s_main));
+            sumsq2d_kernel<<<dim3(cdiv(n, 256), 256), 256, 0, h->s_main>>>(h->dA64, h->ldd, (int)n,
+                                                                             h->d_scal + 2);
+            LAUNCH_CHECK(h);
+            cast2d_kernel<double, float><<<dim3(cdiv(n, 256), 512), 256, 0, h->s_main>>>(
+                h->dA64, h->ldd, (float*)h->dA, h->ldd, (int)n, (int)n);
+            LAUNCH_CHECK(h);
+        }
+        rc = getrf_device<float>(h, (float*)h->dA, h->ldd, (int)n);
+    }
+    if (rc) return rc;
+    CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
+    CU_TRY(h, cudaMemcpyAsync(h->h_small, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
+    CU_TRY(h, cudaMemcpyAsync(h->h_small + 1, h->d_deverr, sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
+    if (h->dtype == B200LU_MIXED)
+        CU_TRY(h, cudaMemcpyAsync(h->h_scal + 2, h->d_scal + 2, sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    if (h->opt[B200LU_OPT_LOOKAHEAD]) CU_TRY(h, cudaStreamSynchronize(h->s_panel));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_b, h->ev_c);
+    h->timing[B200LU_T_FACTOR] = ms;
+    if (h->h_small[1] != 0) {
+        cudaMemset(h->d_deverr, 0, sizeof(int));
+        return set_err(h, 4, "device watchdog fired during getrf (code %d)", h->h_small[1]);
+    }
+    if (h->dtype == B200LU_MIXED) h->normA_F = sqrt(h->h_scal[2]);
+    {
+        double gms = 0.0;
+        for (int i = 0; i + 1 < h->prof_used; i += 2) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]);
+            gms += t;
+        }
+        h->timing[B200LU_T_GEMM] = gms;
+        h->counters[B200LU_C_GEMM_FLOPS] = h->prof_flops;
+        h->counters[B200LU_C_GEMM_LAUNCHES] = h->prof_used / 2;
+    }
+    h->info = h->h_small[0];
+    h->factored = true;
+    if (info) *info = h->info;
+    return 0;
+}
+
+int b200lu_factor(b200lu_handle* h, int64_t n, const void* A_host, int64_t lda, int64_t* ipiv_out,
+                  int64_t* info) {
+    if (!h) return -1;
+    if (n < 0 || n > 131072) return set_err(h, -2, "n out of range");
+    if (!A_host && n > 0) return set_err(h, -3, "A is NULL");
+    if (lda < std::max<int64_t>(1, n)) return set_err(h, -4, "lda < max(1,n)");
+    if (info) *info = 0;
+    if (n == 0) { h->n = 0; h->factored = true; h->info = 0; return 0; }
+    CU_TRY(h, cudaSetDevice(h->dev));
+    int rc = ensure_capacity(h, n);
+    if (rc) return rc;
+    const size_t is = iface_size(h);
+    void* dst = (h->dtype == B200LU_MIXED) ? (void*)h->dA64 : h->dA;
+    CU_TRY(h, cudaEventRecord(h->ev_a, h->s_main));
+    CU_TRY(h, cudaMemcpy2DAsync(dst, (size_t)h->ldd * is, A_host, (size_t)lda * is, (size_t)n * is,
+                                (size_t)n, cudaMemcpyHostToDevice, h->s_main));
+    rc = factor_resident(h, n, info);
+    if (rc) return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+    h->timing[B200LU_T_H2D] = ms;
+    if (ipiv_out) {
+        rc = b200lu_get_ipiv(h, ipiv_out);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int b200lu_factor_device(b200lu_handle* h, int64_t n, const void* A_dev, int64_t lda, int64_t* info) {
+    if (!h) return -1;
+    if (n < 0 || n > 131072) return set_err(h, -2, "n out of range");
+    if (!A_dev && n > 0) return set_err(h, -3, "A is NULL");
+    if (lda < std::max<int64_t>(1, n)) return set_err(h, -4, "lda < max(1,n)");
+    if (info) *info = 0;
+    if (n == 0) { h->n = 0; h->factored = true; h->info = 0; return 0; }
+    CU_TRY(h, cudaSetDevice(h->dev));
+    int rc = ensure_capacity(h, n);
+    if (rc) return rc;
+    const size_t is = iface_size(h);
+    void* dst = (h->dtype == B200LU_MIXED) ? (void*)h->dA64 : h->dA;
+    CU_TRY(h, cudaEventRecord(h->ev_a, h->s_main));
+    if (A_dev != dst)
+        CU_TRY(h, cudaMemcpy2DAsync(dst, (size_t)h->ldd * is, A_dev, (size_t)lda * is, (size_t)n * is,
+                                    (size_t)n, cudaMemcpyDeviceToDevice, h->s_main));
+    rc = factor_resident(h, n, info);
+    if (rc) return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+    h->timing[B200LU_T_H2D] = ms;  // device-to-device staging of A into the factor buffer
+    return 0;
+}
+
+static int check_solve_args(b200lu_handle* h, char trans, int64_t nrhs, const void* B, int64_t ldb,
+                            void* X, int64_t ldx) {
+    if (!h) return -1;
+    if (trans != 'N' && trans != 'n')
+        return set_err(h, -2, "trans='%c' not implemented (only 'N')", trans);
+    if (nrhs < 0) return set_err(h, -3, "nrhs < 0");
+    if (!h->factored) return set_err(h, 3, "no factorization cached");
+    if (h->info != 0) return set_err(h, 3, "cached factorization is singular (info=%lld)", (long long)h->info);
+    if (h->n > 0 && nrhs > 0) {
+        if (!B) return set_err(h, -4, "B is NULL");
+        if (ldb < h->n) return set_err(h, -5, "ldb < n");
+        if (!X) return set_err(h, -6, "X is NULL");
+        if (ldx < h->n) return set_err(h, -7, "ldx < n");
+    }
+    return 0;
+}
+
+static int finish_solve(b200lu_handle* h) {
+    CU_TRY(h, cudaMemcpyAsync(h->h_small + 1, h->d_deverr, sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    if (h->h_small[1] != 0) {
+        cudaMemset(h->d_deverr, 0, sizeof(int));
+        return set_err(h, 4, "device watchdog fired during getrs (code %d)", h->h_small[1]);
+    }
+    return 0;
+}
+
+int b200lu_solve_device(b200lu_handle* h, char trans, int64_t nrhs, const void* B_dev, int64_t ldb,
+                        void* X_dev, int64_t ldx) {
+    int rc = check_solve_args(h, trans, nrhs, B_dev, ldb, X_dev, ldx);
+    if (rc) return rc;
+    if (h->n == 0 || nrhs == 0) return 0;
+    CU_TRY(h, cudaSetDevice(h->dev));
+    CU_TRY(h, cudaEventRecord(h->ev_b, h->s_main));
+    if (h->dtype == B200LU_F64)
+        rc = getrs_device<double>(h, (const double*)B_dev, ldb, (double*)X_dev, ldx, (int)nrhs);
+    else if (h->dtype == B200LU_F32)
+        rc = getrs_device<float>(h, (const float*)B_dev, ldb, (float*)X_dev, ldx, (int)nrhs);
+    else
+        rc = refine_solve_device(h, (const double*)B_dev, ldb, (double*)X_dev, ldx, (int)nrhs);
+    if (rc) return rc;
+    CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
+    rc = finish_solve(h);
+    if (rc) return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_b, h->ev_c);
+    h->timing[B200LU_T_SOLVE] = ms;
+    return 0;
+}
+
+int b200lu_solve(b200lu_handle* h, char trans, int64_t nrhs, const void* B_host, int64_t ldb,
+                 void* X_host, int64_t ldx) {
+    int rc = check_solve_args(h, trans, nrhs, B_host, ldb, X_host, ldx);
+    if (rc) return rc;
+    if (h->n == 0 || nrhs == 0) return 0;
+    CU_TRY(h, cudaSetDevice(h->dev));
+    // d_B/d_X are also scratch of the in-place / refinement paths: keep the host
+    // staging in the upper half of a 2*nrhs allocation
+    rc = ensure_rhs(h, 2 * nrhs + 2);
+    if (rc) return rc;
+    const size_t is = iface_size(h);
+    const int64_t n = h->n;
+    char* dBs = (char*)h->d_B + (size_t)h->cap_n * (nrhs + 1) * 8;
+    char* dXs = (char*)h->d_X + (size_t)h->cap_n * (nrhs + 1) * 8;
+    CU_TRY(h, cudaEventRecord(h->ev_a, h->s_main));
+    CU_TRY(h, cudaMemcpy2DAsync(dBs, (size_t)n * is, B_host, (size_t)ldb * is, (size_t)n * is,
+                                (size_t)nrhs, cudaMemcpyHostToDevice, h->s_main));
+    CU_TRY(h, cudaEventRecord(h->ev_b, h->s_main));
+    if (h->dtype == B200LU_F64)
+        rc = getrs_device<double>(h, (const double*)dBs, n, (double*)dXs, n, (int)nrhs);
+    else if (h->dtype == B200LU_F32)
+        rc = getrs_device<float>(h, (const float*)dBs, n, (float*)dXs, n, (int)nrhs);
+    else
+        rc = refine_solve_device(h, (const double*)dBs, n, (double*)dXs, n, (int)nrhs);
+    if (rc) return rc;
+    CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
+    CU_TRY(h, cudaMemcpy2DAsync(X_host, (size_t)ldx * is, dXs, (size_t)n * is, (size_t)n * is,
+                                (size_t)nrhs, cudaMemcpyDeviceToHost, h->s_main));
+    CU_TRY(h, cudaEventRecord(h->ev_d, h->s_main));
+    rc = finish_solve(h);
+    if (rc) return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_a, h->ev_b); h->timing[B200LU_T_H2D] = ms;
+    cudaEventElapsedTime(&ms, h->ev_b, h->ev_c); h->timing[B200LU_T_SOLVE] = ms;
+    cudaEventElapsedTime(&ms, h->ev_c, h->ev_d); h->timing[B200LU_T_D2H] = ms;
+    return 0;
+}
+
+int b200lu_get_factors(b200lu_handle* h, void* LU_host, int64_t ldlu) {
+    if (!h) return -1;
+    if (!h->factored) return set_err(h, 3, "no factorization cached");
+    if (!LU_host) return set_err(h, -2, "LU is NULL");
+    if (ldlu < h->n) return set_err(h, -3, "ldlu < n");
+    if (h->n == 0) return 0;
+    CU_TRY(h, cudaSetDevice(h->dev));
+    const size_t es = elem_size(h);
+    CU_TRY(h, cudaMemcpy2DAsync(LU_host, (size_t)ldlu * es, h->dA, (size_t)h->ldd * es,
+                                (size_t)h->n * es, (size_t)h->n, cudaMemcpyDeviceToHost, h->s_main));
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    return 0;
+}
+
+int b200lu_get_ipiv(b200lu_handle* h, int64_t* ipiv_out) {
+    if (!h) return -1;
+    if (!h->factored) return set_err(h, 3, "no factorization cached");
+    if (!ipiv_out) return set_err(h, -2, "ipiv is NULL");
+    if (h->n == 0) return 0;
+    CU_TRY(h, cudaSetDevice(h->dev));
+    // widen on the device into d_X-free scratch: reuse d_plans? no — a dedicated pass via pinned ints
+    const int n = (int)h->n;
+    int* tmp = (int*)h->h_ipiv;  // pinned, n*8 bytes: first n ints as staging
+    CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
+    CU_TRY(h, cudaMemcpyAsync(tmp + n, h->d_ipiv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
+    CU_TRY(h, cudaEventRecord(h->ev_d, h->s_main));
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    for (int i = 0; i < n; ++i) ipiv_out[i] = (int64_t)tmp[n + i] + 1;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_c, h->ev_d);
+    h->timing[B200LU_T_D2H] = ms;
+    return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ batched --
+static int ensure_batched(b200lu_handle* h, int64_t batch, int64_t n) {
+    const size_t es = elem_size(h) == 8 ? 8 : 4;
+    const size_t fs = (h->dtype == B200LU_F64) ? 8 : 4;
+    (void)es;
+    const int64_t need = batch * n * n * (int64_t)fs;
+    if (need > h->b_cap_bytes) {
+        CU_TRY(h, cudaStreamSynchronize(h->s_main));
+        free_dev(h->dB_LU);
+        CU_TRY(h, cudaMalloc(&h->dB_LU, (size_t)need));
+        h->b_cap_bytes = need;
+    }
+    if (batch * n > h->b_cap_batch_n) {
+        CU_TRY(h, cudaStreamSynchronize(h->s_main));
+        free_dev(h->dB_ipiv);
+        free_dev(h->dB_info);
+        CU_TRY(h, cudaMalloc((void**)&h->dB_ipiv, (size_t)(batch * n) * sizeof(int)));
+        CU_TRY(h, cudaMalloc((void**)&h->dB_info, (size_t)(batch * n) * sizeof(int)));
+        h->b_cap_batch_n = batch * n;
+    }
+    h->b_batch = batch;
+    h->b_n = n;
+    return 0;
+}
+
+template <typename T>
+static int batched_factor_launch(b200lu_handle* h, const T* A, int64_t lda, int64_t strideA) {
+    const int n = (int)h->b_n;
+    const int64_t batch = h->b_batch;
+    T* LU = (T*)h->dB_LU;
+    cudaStream_t st = h->s_main;
+    if (n <= 16)
+        getrf_batched_kernel<T, 16><<<(unsigned)batch, 16, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_info, n);
+    else if (n <= 32)
+        getrf_batched_kernel<T, 32><<<(unsigned)batch, 32, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_info, n);
+    else
+        getrf_batched_kernel<T, 64><<<(unsigned)batch, 64, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_info, n);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+template <typename T>
+static int batched_solve_launch(b200lu_handle* h, int nrhs, const T* B, int64_t ldb, int64_t strideB,
+                                T* X, int64_t ldx, int64_t strideX) {
+    const int n = (int)h->b_n;
+    const int64_t batch = h->b_batch;
+    const T* LU = (const T*)h->dB_LU;
+    cudaStream_t st = h->s_main;
+    if (n <= 16)
+        getrs_batched_kernel<T, 16><<<(unsigned)batch, 16, 0, st>>>(LU, n, (int64_t)n * n, h->dB_ipiv, B, ldb, strideB, X, ldx, strideX, n, nrhs);
+    else if (n <= 32)
+        getrs_batched_kernel<T, 32><<<(unsigned)batch, 32, 0, st>>>(LU, n, (int64_t)n * n, h->dB_ipiv, B, ldb, strideB, X, ldx, strideX, n, nrhs);
+    else
+        getrs_batched_kernel<T, 64><<<(unsigned)batch, 64, 0, st>>>(LU, n, (int64_t)n * n, h->dB_ipiv, B, ldb, strideB, X, ldx, strideX, n, nrhs);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+extern "C" {
+
+static int check_batched_args(b200lu_handle* h, int64_t batch, int64_t n, const void* A, int64_t lda,
+                              int64_t strideA) {
+    if (!h) return -1;
+    if (h->dtype == B200LU_MIXED) return set_err(h, -1, "batched mode supports F64 and F32 handles");
+    if (batch < 0) return set_err(h, -2, "batch < 0");
+    if (n < 0 || n > 64) return set_err(h, -3, "batched n must be in [0, 64]");
+    if (batch > 0 && n > 0) {
+        if (!A) return set_err(h, -4, "A is NULL");
+        if (lda < n) return set_err(h, -5, "lda < n");
+        if (batch > 1 && strideA < lda * (n - 1) + n) return set_err(h, -6, "strideA overlaps");
+    }
+    return 0;
+}
+
+int b200lu_factor_batched_device(b200lu_handle* h, int64_t batch, int64_t n, const void* A_dev,
+                                 int64_t lda, int64_t strideA, int64_t* any_info) {
+    int rc = check_batched_args(h, batch, n, A_dev, lda, strideA);
+    if (rc) return rc;
+    if (any_info) *any_info = 0;
+    h->b_factored = false;
+    if (batch == 0 || n == 0) { h->b_batch = batch; h->b_n = n; h->b_factored = true; return 0; }
+    CU_TRY(h, cudaSetDevice(h->dev));
+    rc = ensure_batched(h, batch, n);
+    if (rc) return rc;
+    CU_TRY(h, cudaEventRecord(h->ev_b, h->s_main));
+    if (h->dtype == B200LU_F64) rc = batched_factor_launch<double>(h, (const double*)A_dev, lda, strideA);
+    else rc = batched_factor_launch<float>(h, (const float*)A_dev, lda, strideA);
+    if (rc) return rc;
+    CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
+    h->b_factored = true;
+    if (any_info) {
+        // count failures: max over info on the host side is done by the host path; here a cheap flag
+        CU_TRY(h, cudaStreamSynchronize(h->s_main));
+        std::vector<int> tmp((size_t)batch);
+        CU_TRY(h, cudaMemcpy(tmp.data(), h->dB_info, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost));
+        int64_t bad = 0;
+        for (int64_t i = 0; i < batch; ++i) bad += tmp[(size_t)i] != 0;
+        *any_info = bad;
+    } else {
+        CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_b, h->ev_c);
+    h->timing[B200LU_T_FACTOR] = ms;
+    return 0;
+}
+
+int b200lu_solve_batched_device(b200lu_handle* h, int64_t nrhs, const void* B_dev, int64_t ldb,
+                                int64_t strideB, void* X_dev, int64_t ldx, int64_t strideX) {
+    if (!h) return -1;
+    if (!h->b_factored) return set_err(h, 3, "no batched factorization cached");
+    if (nrhs < 0) return set_err(h, -2, "nrhs < 0");
+    if (h->b_batch == 0 || h->b_n == 0 || nrhs == 0) return 0;
+    if (!B_dev || !X_dev) return set_err(h, -3, "B or X is NULL");
+    if (ldb < h->b_n || ldx < h->b_n) return set_err(h, -4, "ldb/ldx < n");
+    CU_TRY(h, cudaSetDevice(h->dev));
+    int rc;
+    CU_TRY(h, cudaEventRecord(h->ev_b, h->s_main));
+    if (h->dtype == B200LU_F64)
+        rc = batched_solve_launch<double>(h, (int)nrhs, (const double*)B_dev, ldb, strideB, (double*)X_dev, ldx, strideX);
+    else
+        rc = batched_solve_launch<float>(h, (int)nrhs, (const float*)B_dev, ldb, strideB, (float*)X_dev, ldx, strideX);
+    if (rc) return rc;
+    CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_b, h->ev_c);
+    h->timing[B200LU_T_SOLVE] = ms;
+    return 0;
+}
+
+int b200lu_factor_batched(b200lu_handle* h, int64_t batch, int64_t n, const void* A_host, int64_t lda,
+                          int64_t strideA, int64_t* ipiv_out, int64_t* info_out) {
+    int rc = check_batched_args(h, batch, n, A_host, lda, strideA);
+    if (rc) return rc;
+    h->b_factored = false;
+    if (batch == 0 || n == 0) { h->b_batch = batch; h->b_n = n; h->b_factored = true; return 0; }
+    CU_TRY(h, cudaSetDevice(h->dev));
+    const size_t is = iface_size(h);
+    // stage A compactly (lda -> n) so one 2D copy moves the whole batch when lda == n, strideA == n*n
+    const int64_t in_bytes = batch * n * n * (int64_t)is;
+    if (in_bytes > h->b_cap_in) {
+        CU_TRY(h, cudaStreamSynchronize(h->s_main));
+        free_dev(h->dB_in);
+        CU_TRY(h, cudaMalloc(&h->dB_in, (size_t)in_bytes));
+        h->b_cap_in = in_bytes;
+    }
+    CU_TRY(h, cudaEventRecord(h->ev_a, h->s_main));
+    if (lda == n && (strideA == n * n || batch == 1)) {
+        CU_TRY(h, cudaMemcpyAsync(h->dB_in, A_host, (size_t)in_bytes, cudaMemcpyHostToDevice, h->s_main));
+    } else {
+        for (int64_t i = 0; i < batch; ++i)
+            CU_TRY(h, cudaMemcpy2DAsync((char*)h->dB_in + (size_t)(i * n * n) * is, (size_t)n * is,
+                                        (const char*)A_host + (size_t)(i * strideA) * is, (size_t)lda * is,
+                                        (size_t)n * is, (size_t)n, cudaMemcpyHostToDevice, h->s_main));
+    }
+    rc = b200lu_factor_batched_device(h, batch, n, h->dB_in, n, n * n, nullptr);
+    if (rc) return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+    h->timing[B200LU_T_H2D] = ms;
+    if (ipiv_out || info_out) return b200lu_get_factors_batched(h, nullptr, 0, 0, ipiv_out, info_out);
+    return 0;
+}
+
+int b200lu_get_factors_batched(b200lu_handle* h, void* LU_host, int64_t lda, int64_t strideA,
+                               int64_t* ipiv_out, int64_t* info_out) {
+    if (!h) return -1;
+    if (!h->b_factored) return set_err(h, 3, "no batched factorization cached");
+    const int64_t batch = h->b_batch, n = h->b_n;
+    if (batch == 0 || n == 0) return 0;
+    CU_TRY(h, cudaSetDevice(h->dev));
+    const size_t fs = (h->dtype == B200LU_F64) ? 8 : 4;
+    if (LU_host) {
+        if (lda < n) return set_err(h, -3, "lda < n");
+        if (lda == n && strideA == n * n) {
+            CU_TRY(h, cudaMemcpy(LU_host, h->dB_LU, (size_t)(batch * n * n) * fs, cudaMemcpyDeviceToHost));
+        } else {
+            for (int64_t i = 0; i < batch; ++i)
+                CU_TRY(h, cudaMemcpy2D((char*)LU_host + (size_t)(i * strideA) * fs, (size_t)lda * fs,
+                                       (const char*)h->dB_LU + (size_t)(i * n * n) * fs, (size_t)n * fs,
+                                       (size_t)n * fs, (size_t)n, cudaMemcpyDeviceToHost));
+        }
+    }
+    if (ipiv_out) {
+        std::vector<int> tmp((size_t)(batch * n));
+        CU_TRY(h, cudaMemcpy(tmp.data(), h->dB_ipiv, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tmp.size(); ++i) ipiv_out[i] = (int64_t)tmp[i] + 1;
+    }
+    if (info_out) {
+        std::vector<int> tmp((size_t)batch);
+        CU_TRY(h, cudaMemcpy(tmp.data(), h->dB_info, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tmp.size(); ++i) info_out[i] = tmp[i];
+    }
+    return 0;
+}
+
+int b200lu_solve_batched(b200lu_handle* h, int64_t nrhs, const void* B_host, int64_t ldb,
+                         int64_t strideB, void* X_host, int64_t ldx, int64_t strideX) {
+    if (!h) return -1;
+    if (!h->b_factored) return set_err(h, 3, "no batched factorization cached");
+    if (nrhs < 0) return set_err(h, -2, "nrhs < 0");
+    const int64_t batch = h->b_batch, n = h->b_n;
+    if (batch == 0 || n == 0 || nrhs == 0) return 0;
+    if (!B_host || !X_host) return set_err(h, -3, "B or X is NULL");
+    if (ldb < n || ldx < n) return set_err(h, -4, "ldb/ldx < n");
+    CU_TRY(h, cudaSetDevice(h->dev));
+    const size_t is = iface_size(h);
+    const int64_t bytes = batch * n * nrhs * (int64_t)is;
+    if (bytes > h->b_cap_rhs) {
+        CU_TRY(h, cudaStreamSynchronize(h->s_main));
+        free_dev(h->dB_rhs);
+        free_dev(h->dB_x);
+        CU_TRY(h, cudaMalloc(&h->dB_rhs, (size_t)bytes));
+        CU_TRY(h, cudaMalloc(&h->dB_x, (size_t)bytes));
+        h->b_cap_rhs = bytes;
+    }
+    CU_TRY(h, cudaEventRecord(h->ev_a, h->s_main));
+    const bool compactB = (ldb == n) && (strideB == n * nrhs || batch == 1);
+    if (compactB) {
+        CU_TRY(h, cudaMemcpyAsync(h->dB_rhs, B_host, (size_t)bytes, cudaMemcpyHostToDevice, h->s_main));
+    } else {
+        for (int64_t i = 0; i < batch; ++i)
+            CU_TRY(h, cudaMemcpy2DAsync((char*)h->dB_rhs + (size_t)(i * n * nrhs) * is, (size_t)n * is,
+                                        (const char*)B_host + (size_t)(i * strideB) * is, (size_t)ldb * is,
+                                        (size_t)n * is, (size_t)nrhs, cudaMemcpyHostToDevice, h->s_main));
+    }
+    int rc = b200lu_solve_batched_device(h, nrhs, h->dB_rhs, n, n * nrhs, h->dB_x, n, n * nrhs);
+    if (rc) return rc;
+    const bool compactX = (ldx == n) && (strideX == n * nrhs || batch == 1);
+    CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
+    if (compactX) {
+        CU_TRY(h, cudaMemcpyAsync(X_host, h->dB_x, (size_t)bytes, cudaMemcpyDeviceToHost, h->s_main));
+    } else {
+        for (int64_t i = 0; i < batch; ++i)
+            CU_TRY(h, cudaMemcpy2DAsync((char*)X_host + (size_t)(i * strideX) * is, (size_t)ldx * is,
+                                        (const char*)h->dB_x + (size_t)(i * n * nrhs) * is, (size_t)n * is,
+                                        (size_t)n * is, (size_t)nrhs, cudaMemcpyDeviceToHost, h->s_main));
+    }
+    CU_TRY(h, cudaEventRecord(h->ev_d, h->s_main));
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_c, h->ev_d);
+    h->timing[B200LU_T_D2H] = ms;
+    return 0;
+}
+
+// --------------------------------------------------------------- synthetic --
+int b200lu_fill_uniform_device(b200lu_handle* h, void* A_dev, int64_t lda, int64_t n, int64_t ncols,
+                               int64_t first_global_col, int64_t col_block, int64_t col_block_stride,
+                               uint64_t seed, double diag_shift) {
+    if (!h) return -1;
+    if (!A_dev || lda < n || n <= 0 || ncols <= 0 || col_block <= 0) return set_err(h, -2, "bad fill arguments");
+    CU_TRY(h, cudaSetDevice(h->dev));
+    dim3 grid(cdiv(n, 256), (unsigned)std::min<int64_t>(ncols, 4096));
+    if (h->dtype == B200LU_F32)
+        fill_uniform_kernel<float><<<grid, 256, 0, h->s_main>>>((float*)A_dev, lda, n, ncols, first_global_col,
+                                                                 col_block, col_block_stride, seed, diag_shift);
+    else
+        fill_uniform_kernel<double><<<grid, 256, 0, h->s_main>>>((double*)A_dev, lda, n, ncols, first_global_col,
+                                                                  col_block, col_block_stride, seed, diag_shift);
+    LAUNCH_CHECK(h);
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    return 0;
+}
+
+// ------------------------------------------------------------- distributed --
+// (implemented in a later milestone; the symbols exist so the ABI is stable)
+int b200lu_comm_unique_id(void* id128) { (void)id128; return 5; }
+int b200lu_comm_init(b200lu_handle* h, const void* id128, int rank, int nranks) {
+    (void)id128; (void)rank; (void)nranks;
+    return set_err(h, 5, "distributed mode not built");
+}
+int b200lu_dist_local_cols(const b200lu_handle* h, int64_t n, int64_t* ncols_local) {
+    (void)h; (void)n; (void)ncols_local;
+    return 5;
+}
+int b200lu_factor_dist(b200lu_handle* h, int64_t n, const void* Aloc_dev, int64_t lda, int64_t* info) {
+    (void)n; (void)Aloc_dev; (void)lda; (void)info;
+    return set_err(h, 5, "distributed mode not built");
+}
+int b200lu_solve_dist(b200lu_handle* h, int64_t nrhs, const void* B_dev, int64_t ldb, void* X_dev, int64_t ldx) {
+    (void)nrhs; (void)B_dev; (void)ldb; (void)X_dev; (void)ldx;
+    return set_err(h, 5, "distributed mode not built");
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// util_kernels.cuh — small bandwidth kernels around the LU path: precision
+// casts for the FP32-factor mode (reference `A_32 .= T32.(A)`,
+// src/openblas.jl:497-500), norms/axpy for the FP64 refinement loop, iota, and
+// the counter-based synthetic fill used by benches at sizes that do not fit
+// the host.
+#pragma once
+#include "common.cuh"
+
+namespace b200lu {
+
+__global__ void iota_kernel(int* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+template <typename TS, typename TD>
+__global__ void cast2d_kernel(const TS* __restrict__ S, long long lds, TD* __restrict__ D,
+                              long long ldd, int rows, int cols) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    for (int c = blockIdx.y; c < cols; c += gridDim.y)
+        D[(long long)c * ldd + r] = (TD)S[(long long)c * lds + r];
+}
+
+// out[0] += sum x^2
+__global__ void sumsq_kernel(const double* __restrict__ x, long long n, double* out) {
+    double s = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        s = fma(x[i], x[i], s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    __shared__ double sh[32];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (threadIdx.x == 0) atomicAdd(out, s);
+    }
+}
+
+// Frobenius norm^2 of an n x n column-major matrix with leading dimension lda
+__global__ void sumsq2d_kernel(const double* __restrict__ A, long long lda, int n, double* out) {
+    double s = 0.0;
+    for (int c = blockIdx.y; c < n; c += gridDim.y) {
+        const int r = blockIdx.x * blockDim.x + threadIdx.x;
+        if (r < n) {
+            const double v = A[(long long)c * lda + r];
+            s = fma(v, v, s);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+// x += (double) d
+__global__ void axpy_f32_kernel(double* __restrict__ x, const float* __restrict__ d, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += (double)d[i];
+}
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// A[i, jl] = U[0,1)(seed, i, j_global) (+ diag_shift on the diagonal);
+// local column jl maps to global column
+//   first_global_col + (jl / col_block) * col_block_stride + jl % col_block.
+template <typename T>
+__global__ void fill_uniform_kernel(T* __restrict__ A, long long lda, long long n, long long ncols,
+                                    long long first_global_col, long long col_block,
+                                    long long col_block_stride, unsigned long long seed,
+                                    double diag_shift) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (long long jl = blockIdx.y; jl < ncols; jl += gridDim.y) {
+        const long long jg = first_global_col + (jl / col_block) * col_block_stride + jl % col_block;
+        const unsigned long long h =
+            splitmix64(seed ^ splitmix64((unsigned long long)jg * 0x100000001B3ULL + (unsigned long long)i));
+        double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+        if (i == jg) u += diag_shift;
+        A[jl * lda + i] = (T)u;
+    }
+}
+
+// ---- roofline probes: register-resident FP64 issue loops (no memory traffic) ----
+__global__ void __launch_bounds__(256) probe_dmma_kernel(double* sink, int iters) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) sink[threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) probe_dfma_kernel(double* sink, int iters) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = i;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456) sink[threadIdx.x] = s;
+}
+
+}  // namespace b200lu

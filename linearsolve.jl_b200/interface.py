@@ -1,0 +1,422 @@
+"""Host-side mirror of the reference's SciML interface for the dense-LU path.
+
+The reference is Julia; no Julia toolchain exists in this environment, so the
+host side above the C ABI is written in Python with the SAME names, argument
+meaning and error behaviour as the reference, so that the parity tests read
+like the reference's own tests.  The file a Julia maintainer would add is
+`julia/B200LUFactorization.jl` (same logic, `ccall` instead of ctypes).
+
+Mirrored (reference file:line):
+  LinearProblem(A, b; u0)                        SciMLBase, src/LinearSolve.jl:21-22
+  init(prob, alg; alias_A, alias_b, ...)         src/common.jl:700-712,758-931
+  LinearCache + `cache.A =` / `cache.b =`        src/common.jl:281-306,313-360
+  solve!(cache) / solve(prob, alg)               src/common.jl:966-1017
+  reinit!(cache; A, b)                           src/common.jl:933-964
+  ReturnCode.Success / Failure                   src/factorization.jl:714-722
+  B200LUFactorization <: AbstractFactorization   (new; shaped like CudaOffloadLUFactorization,
+                                                  src/extension_algs.jl:344-354, and the solve!
+                                                  protocol of OpenBLASLUFactorization,
+                                                  src/openblas.jl:362-459)
+  B200LU32MixedLUFactorization                   (like OpenBLAS32MixedLUFactorization,
+                                                  src/openblas.jl:470-543, plus FP64 refinement)
+  BlockDiagonal + blockwise LU                   ext/LinearSolveBlockDiagonalsExt.jl:49-205
+  defaultalg(A, b, assumptions)                  src/default.jl:411-520
+"""
+from __future__ import annotations
+
+import enum
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi
+
+
+class ReturnCode(enum.Enum):
+    Default = 0
+    Success = 1
+    Failure = 2
+
+
+def successful_retcode(sol) -> bool:
+    return sol.retcode == ReturnCode.Success
+
+
+@dataclass
+class OperatorAssumptions:
+    """src/common.jl:184-201"""
+    issq: bool = True
+    condition: str = "IllConditioned"
+
+
+class LinearProblem:
+    def __init__(self, A, b, u0=None, p=None):
+        self.A, self.b, self.u0, self.p = A, b, u0, p
+
+
+@dataclass
+class LinearSolution:
+    u: np.ndarray
+    retcode: ReturnCode
+    alg: object
+    resid: object = None
+    iters: int = 0
+
+
+# ------------------------------------------------------------- algorithms ----
+class AbstractFactorization:
+    """needs_concrete_A = true, needs_square_A = true (src/LinearSolve.jl:299,720-731)"""
+    needs_concrete_A = True
+    needs_square_A = True
+
+
+class B200LUFactorization(AbstractFactorization):
+    """Dense partially pivoted LU on one B200 through libb200lu.so.
+
+    `throwerror=False` lets the default solver build the algorithm speculatively
+    on machines without the library (src/extension_algs.jl:346-353).
+    `residualsafety` enables the a-posteriori residual check of
+    src/factorization.jl:127-156 after a fresh factorization.
+    """
+    _dtype_code = {np.dtype(np.float64): _capi.F64, np.dtype(np.float32): _capi.F32}
+
+    def __init__(self, throwerror: bool = True, residualsafety: bool = False, device: int = 0,
+                 nb: int | None = None, lookahead: bool | None = None):
+        if throwerror and not useb200():
+            raise RuntimeError("B200LUFactorization requires libb200lu.so and a B200 (sm_100) GPU; "
+                               "there is no CPU fallback")
+        self.residualsafety = residualsafety
+        self.device = device
+        self.nb = nb
+        self.lookahead = lookahead
+
+    def handle_dtype(self, eltype):
+        try:
+            return self._dtype_code[np.dtype(eltype)]
+        except KeyError:
+            raise TypeError(f"B200LUFactorization supports Float32/Float64, got {eltype}") from None
+
+
+class B200LU32MixedLUFactorization(B200LUFactorization):
+    """FP64 interface, FP32 factorization on the GPU, FP64 iterative refinement.
+    With `refine=False` it is exactly the reference's *32Mixed behaviour
+    (cast, sgetrf, sgetrs, cast back; src/openblas.jl:487-543)."""
+
+    def __init__(self, refine: bool = True, maxiters: int = 10, **kw):
+        super().__init__(**kw)
+        self.refine = refine
+        self.maxiters = maxiters
+
+    def handle_dtype(self, eltype):
+        if np.dtype(eltype) != np.float64:
+            raise TypeError("B200LU32MixedLUFactorization expects a Float64 problem")
+        return _capi.MIXED
+
+
+def useb200() -> bool:
+    """availability hook, overridden when the library loads
+    (pattern: src/LinearSolve.jl:741-743, ext/LinearSolveCUDAExt.jl:16)"""
+    return _capi.is_available()
+
+
+# -------------------------------------------------------- block diagonal ----
+class BlockDiagonal:
+    """Minimal stand-in for BlockDiagonals.BlockDiagonal (square blocks)."""
+
+    def __init__(self, blocks):
+        self.blocks = [np.asarray(B) for B in blocks]
+        for B in self.blocks:
+            if B.ndim != 2:
+                raise ValueError("blocks must be matrices")
+        self.offsets = np.concatenate([[0], np.cumsum([B.shape[0] for B in self.blocks])])
+
+    @property
+    def shape(self):
+        return (int(self.offsets[-1]), int(sum(B.shape[1] for B in self.blocks)))
+
+    @property
+    def dtype(self):
+        return self.blocks[0].dtype
+
+    def all_square(self):
+        return all(B.shape[0] == B.shape[1] for B in self.blocks)
+
+    def to_dense(self):
+        n = self.shape[0]
+        M = np.zeros((n, n), dtype=self.dtype)
+        for B, o in zip(self.blocks, self.offsets[:-1]):
+            M[o:o + B.shape[0], o:o + B.shape[1]] = B
+        return M
+
+    def copy(self):
+        return BlockDiagonal([B.copy() for B in self.blocks])
+
+
+# ------------------------------------------------------------------ cache ----
+class _B200LUCache:
+    """cacheval: (handle, ipiv, info) — the analogue of OpenBLASLUCache
+    (src/openblas.jl:312-316).  The factors stay on the device."""
+
+    def __init__(self):
+        self.handle = None
+        self.ipiv = None
+        self.info = 0
+        self.groups = None  # BlockDiagonal: list of (handle, block indices, n)
+
+
+class LinearCache:
+    """src/common.jl:281-306.  Assigning `cache.A` marks the cache fresh
+    (refactor on the next solve!); assigning `cache.b` does not."""
+
+    def __init__(self, A, b, u, alg, cacheval, assumptions, abstol, reltol, verbose):
+        object.__setattr__(self, "_A", A)
+        object.__setattr__(self, "_b", b)
+        self.u = u
+        self.alg = alg
+        self.cacheval = cacheval
+        self.isfresh = True
+        self.assumptions = assumptions
+        self.abstol, self.reltol = abstol, reltol
+        self.verbose = verbose
+        self.fell_back_to_qr = False
+
+    @property
+    def A(self):
+        return self._A
+
+    @A.setter
+    def A(self, val):
+        object.__setattr__(self, "_A", val)
+        self.isfresh = True            # src/common.jl:330-348
+        self.fell_back_to_qr = False
+
+    @property
+    def b(self):
+        return self._b
+
+    @b.setter
+    def b(self, val):
+        object.__setattr__(self, "_b", val)
+
+
+def _promote(x):
+    """int arrays are promoted to float like __promote_int_arrays (src/common.jl:448-502)"""
+    x = np.asarray(x) if not isinstance(x, BlockDiagonal) else x
+    if isinstance(x, np.ndarray) and x.dtype.kind in "iub":
+        return x.astype(np.float64)
+    return x
+
+
+def init(prob: LinearProblem, alg=None, alias_A: bool = False, alias_b: bool = False,
+         abstol=None, reltol=None, verbose: bool = False, assumptions: OperatorAssumptions | None = None):
+    A, b = _promote(prob.A), _promote(prob.b)
+    assumptions = assumptions or OperatorAssumptions(issq=(A.shape[0] == A.shape[1]))
+    if alg is None:
+        alg = defaultalg(A, b, assumptions)
+    if isinstance(alg, DefaultLinearSolver):
+        alg = alg.to_alg()
+    if not isinstance(alg, B200LUFactorization):
+        raise NotImplementedError(
+            f"{type(alg).__name__} is a reference (CPU) algorithm outside this library's hot path")
+    if A.shape[0] != A.shape[1]:
+        raise ValueError("B200LUFactorization needs a square A (needs_square_A)")
+    if b.shape[0] != A.shape[0]:
+        raise ValueError(f"b has leading dimension {b.shape[0]}, but needs {A.shape[0]}")
+    # dense factorizations default to alias_A = false: the cache owns a private copy
+    if not alias_A:
+        A = A.copy() if isinstance(A, BlockDiagonal) else np.array(A, order="F", copy=True)
+    if not alias_b:
+        b = np.array(b, copy=True)
+    u = np.zeros_like(b) if prob.u0 is None else np.array(prob.u0, copy=True)
+    eps = np.finfo(b.dtype).eps if b.dtype.kind == "f" else np.finfo(np.float64).eps
+    abstol = np.sqrt(eps) if abstol is None else abstol
+    reltol = np.sqrt(eps) if reltol is None else reltol
+    return LinearCache(A, b, u, alg, _B200LUCache(), assumptions, abstol, reltol, verbose)
+
+
+def reinit(cache: LinearCache, A=None, b=None, u=None):
+    """reinit!(cache; A, b, u) — src/common.jl:933-964"""
+    if A is not None:
+        cache.A = A
+    if b is not None:
+        cache.b = b
+    if u is not None:
+        cache.u = u
+    return cache
+
+
+def _configure(handle, alg):
+    if alg.nb is not None:
+        handle.set_option(_capi.OPT_NB, alg.nb)
+    if alg.lookahead is not None:
+        handle.set_option(_capi.OPT_LOOKAHEAD, int(alg.lookahead))
+    if isinstance(alg, B200LU32MixedLUFactorization):
+        handle.set_option(_capi.OPT_REFINE_MAXIT, alg.maxiters if alg.refine else 0)
+
+
+def _factor_blockdiag(cache, alg):
+    """Blockwise LU (ext/LinearSolveBlockDiagonalsExt.jl:119-125): blocks of equal
+    size <= 64 go through ONE batched launch; larger blocks one by one.
+    success = all(issuccess) (:121-124)."""
+    A = cache.A
+    cv = cache.cacheval
+    by_size = {}
+    for i, B in enumerate(A.blocks):
+        by_size.setdefault(B.shape[0], []).append(i)
+    sig = [(n, len(by_size[n])) for n in sorted(by_size)]
+    if cv.groups is None or [(g[2], len(g[1])) for g in cv.groups] != sig:
+        cv.groups = []
+        for n in sorted(by_size):
+            # n <= 64: one handle caches the whole batch; larger blocks: one handle each
+            cnt = 1 if n <= 64 else len(by_size[n])
+            hs = []
+            for _ in range(cnt):
+                h = _capi.Handle(alg.handle_dtype(A.dtype), alg.device)
+                _configure(h, alg)
+                hs.append(h)
+            cv.groups.append([hs, by_size[n], n])
+    ok = True
+    for hs, idx, n in cv.groups:
+        if n <= 64:
+            stack = np.stack([np.asfortranarray(A.blocks[i]).T for i in idx])  # [s, col, row]
+            _, info = hs[0].factor_batched(np.ascontiguousarray(stack))
+            ok = ok and not np.any(info != 0)
+        else:
+            for hh, i in zip(hs, idx):
+                _, info = hh.factor(np.asfortranarray(A.blocks[i]), want_ipiv=False)
+                ok = ok and info == 0
+    cv.info = 0 if ok else 1
+    return cv.info
+
+
+def _solve_blockdiag(cache):
+    A, cv = cache.A, cache.cacheval
+    b = np.asarray(cache.b)
+    vec = b.ndim == 1
+    Bm = b.reshape(b.shape[0], -1)
+    X = np.empty_like(Bm)
+    for hs, idx, n in cv.groups:
+        if n <= 64:
+            # (batch, nrhs, n): each right-hand side contiguous
+            rhs = np.stack([Bm[A.offsets[i]:A.offsets[i] + n, :].T for i in idx])
+            sol = hs[0].solve_batched(np.ascontiguousarray(rhs))
+            for s, i in enumerate(idx):
+                X[A.offsets[i]:A.offsets[i] + n, :] = sol[s].T
+        else:
+            for hh, i in zip(hs, idx):
+                X[A.offsets[i]:A.offsets[i] + n, :] = hh.solve(np.asfortranarray(Bm[A.offsets[i]:A.offsets[i] + n, :]))
+    return X[:, 0] if vec else X
+
+
+def _check_residual_safety(cache, A_original, u):
+    """a-posteriori check ‖A u − b‖ <= abstol + reltol‖b‖ (src/factorization.jl:127-156)"""
+    Ad = A_original.to_dense() if isinstance(A_original, BlockDiagonal) else A_original
+    r = Ad @ u - cache.b
+    return np.linalg.norm(r) <= cache.abstol + cache.reltol * np.linalg.norm(cache.b)
+
+
+def solve_(cache: LinearCache, alg=None) -> LinearSolution:
+    """`solve!(cache)` — protocol of src/openblas.jl:362-459: factor only when
+    `cache.isfresh`; on info != 0 return ReturnCode.Failure and LEAVE isfresh
+    set; otherwise getrs from cache.b into cache.u."""
+    alg = alg or cache.alg
+    cv = cache.cacheval
+    A = cache.A
+    check_safety = alg.residualsafety and cache.isfresh
+    if cache.isfresh:
+        if isinstance(A, BlockDiagonal):
+            info = _factor_blockdiag(cache, alg)
+        else:
+            A = np.asarray(A)
+            if cv.handle is None or cv.handle.dtype != alg.handle_dtype(A.dtype):
+                cv.handle = _capi.Handle(alg.handle_dtype(A.dtype), alg.device)
+                _configure(cv.handle, alg)
+            cv.ipiv, info = cv.handle.factor(A)
+            cv.info = info
+        if info != 0:
+            if cache.verbose:
+                print("Solver failed")          # @SciMLMessage("Solver failed", ..., :solver_failure)
+            return LinearSolution(cache.u, ReturnCode.Failure, alg)
+        cache.isfresh = False
+    if isinstance(A, BlockDiagonal):
+        x = _solve_blockdiag(cache)
+    else:
+        x = cv.handle.solve(np.asarray(cache.b))
+    cache.u[...] = x
+    if check_safety and not _check_residual_safety(cache, A, cache.u):
+        return LinearSolution(cache.u, ReturnCode.Failure, alg)
+    return LinearSolution(cache.u, ReturnCode.Success, alg)
+
+
+def solve(prob: LinearProblem, alg=None, **kw) -> LinearSolution:
+    return solve_(init(prob, alg, **kw))
+
+
+# ----------------------------------------------------------- polyalgorithm ----
+class DefaultAlgorithmChoice(enum.Enum):
+    """the members of src/LinearSolve.jl:330-357 that the dense arm can return,
+    plus the new slot"""
+    GenericLUFactorization = 1
+    RFLUFactorization = 2
+    LUFactorization = 3
+    MKLLUFactorization = 4
+    QRFactorization = 5
+    SVDFactorization = 6
+    B200LUFactorization = 100
+
+
+@dataclass
+class DefaultLinearSolver:
+    alg: DefaultAlgorithmChoice
+    safetyfallback: bool = True
+
+    def to_alg(self):
+        """algchoice_to_alg (src/default.jl:522-581) for the slot this library owns"""
+        if self.alg == DefaultAlgorithmChoice.B200LUFactorization:
+            return B200LUFactorization(throwerror=False)
+        return _ReferenceCPUAlgorithm(self.alg)
+
+
+@dataclass
+class _ReferenceCPUAlgorithm:
+    choice: DefaultAlgorithmChoice
+
+
+# Break-even n above which the GPU path is selected when available.  The
+# reference documents "around 1,000 x 1,000" for CUDA offload
+# (docs/src/tutorials/gpu.md:19-22); must stay above n = 600 so the reference's
+# selection tests (test/Core/default_algs.jl:4-66) are unchanged.
+B200_DEFAULT_MIN_N = 1024
+
+
+def defaultalg(A, b, assump: OperatorAssumptions | None = None, *, isopenblas: bool = True,
+               usemkl: bool = False, userecursivefactorization: bool = True,
+               b200_available: bool | None = None) -> DefaultLinearSolver:
+    """Dense square BLAS-eltype arm of src/default.jl:411-520 with the new
+    availability-gated B200 arm inserted above n = 600."""
+    assump = assump or OperatorAssumptions()
+    n = b.shape[0]
+    C = DefaultAlgorithmChoice
+    if isinstance(A, BlockDiagonal):
+        # ext/LinearSolveBlockDiagonalsExt.jl:205-217 -> LU; the GPU arm takes it when available
+        avail = useb200() if b200_available is None else b200_available
+        return DefaultLinearSolver(C.B200LUFactorization if avail else C.LUFactorization)
+    if assump.condition == "VeryIllConditioned":
+        return DefaultLinearSolver(C.QRFactorization)
+    if assump.condition == "SuperIllConditioned":
+        return DefaultLinearSolver(C.SVDFactorization)
+    real_float = np.dtype(A.dtype) in (np.dtype(np.float32), np.dtype(np.float64))
+    if n <= 10:
+        return DefaultLinearSolver(C.GenericLUFactorization)
+    if real_float and n >= B200_DEFAULT_MIN_N:
+        avail = useb200() if b200_available is None else b200_available
+        if avail:
+            return DefaultLinearSolver(C.B200LUFactorization)
+    if (n <= 100 or (isopenblas and n <= 500) or (usemkl and n <= 200)) and real_float \
+            and userecursivefactorization:
+        return DefaultLinearSolver(C.RFLUFactorization)
+    if (n <= 32 or (isopenblas and n <= 256)) and real_float:
+        return DefaultLinearSolver(C.GenericLUFactorization)
+    if usemkl:
+        return DefaultLinearSolver(C.MKLLUFactorization)
+    return DefaultLinearSolver(C.LUFactorization)

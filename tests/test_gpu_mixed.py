@@ -1,0 +1,49 @@
+"""FP32-factor modes (reference test/Core/test_mixed_precision.jl:9-31: 100x100
+rand+5I, rel. error and residual < 1e-5) and the FP64 refinement superset
+(north star: backward error <= 10 n eps64)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_mixed_reference_behaviour_no_refine(gpu_required, ls):
+    rng = np.random.default_rng(123)
+    n = 100
+    A = rng.random((n, n)) + 5 * np.eye(n)
+    b = rng.random(n)
+    sol = ls.solve(ls.LinearProblem(A, b), ls.B200LU32MixedLUFactorization(refine=False))
+    assert sol.retcode == ls.ReturnCode.Success
+    x_ref = np.linalg.solve(A, b)
+    assert np.linalg.norm(sol.u - x_ref) / np.linalg.norm(x_ref) < 1e-5
+    assert np.linalg.norm(A @ sol.u - b) / np.linalg.norm(b) < 1e-5
+
+
+@pytest.mark.parametrize("n,shift", [(100, 5.0), (1000, 5.0), (2048, 0.0), (3000, 5.0)])
+def test_mixed_refinement_reaches_fp64(gpu_required, ls, oracle, n, shift):
+    rng = np.random.default_rng(n)
+    A = rng.random((n, n)) + shift * np.eye(n)
+    b = rng.random(n)
+    B = rng.random((n, 3))
+    alg = ls.B200LU32MixedLUFactorization()
+    cache = ls.init(ls.LinearProblem(A, b), alg)
+    sol = ls.solve_(cache)
+    assert sol.retcode == ls.ReturnCode.Success
+    eps = np.finfo(np.float64).eps
+    assert oracle.backward_error(A, sol.u, b) <= 10 * n * eps
+    # tighter than the bar: refinement should get to a few eps
+    assert oracle.backward_error(A, sol.u, b) <= 50 * eps
+    cache.b = B
+    cache.u = np.zeros_like(B)
+    sol = ls.solve_(cache)
+    assert oracle.backward_error(A, sol.u, B) <= 10 * n * eps
+    # FP32 factor pivots == sgetrf pivots (up to ties)
+    ipiv = cache.cacheval.handle.get_ipiv()
+    _, ipiv_ref, _ = oracle.lapack_getrf(A.astype(np.float32))
+    assert oracle.compare_ipiv(A.astype(np.float32), ipiv, ipiv_ref)[1] in ("exact", "tie")
+
+
+def test_mixed_singular(gpu_required, ls):
+    A = np.ones((50, 50))
+    sol = ls.solve(ls.LinearProblem(A, np.ones(50)), ls.B200LU32MixedLUFactorization())
+    assert sol.retcode == ls.ReturnCode.Failure
