@@ -1,0 +1,142 @@
+"""CPU-side checks (no GPU, no compute calls): the C-ABI library loads and exports
+every symbol include/b200lu.h declares; the product path fails loudly without a
+GPU (no CPU fallback); the default-algorithm bands of the reference are unchanged
+(test/Core/default_algs.jl:4-66); the LinearCache isfresh protocol."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _no_gpu(ls):
+    return not ls.useb200()
+
+
+def test_header_symbols_are_exported(ls):
+    hdr = open(os.path.join(ROOT, "include", "b200lu.h")).read()
+    declared = sorted(set(re.findall(r"\b(b200lu_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no prototypes found"
+    lib = ls._capi.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/b200lu.h but not exported"
+    assert sorted(ls._capi.SYMBOLS) == declared
+    assert lib.b200lu_version() >= 100
+
+
+def test_no_torch_types_in_abi():
+    hdr = open(os.path.join(ROOT, "include", "b200lu.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)          # prototypes only, comments stripped
+    assert "torch" not in code.lower() and "at::" not in code and "Tensor" not in code
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "linearsolve.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "lu_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+                assert "scipy" not in src and "numpy.linalg.solve" not in src, f
+
+
+def test_fails_loudly_without_gpu(ls):
+    if not _no_gpu(ls):
+        pytest.skip("a GPU is present")
+    with pytest.raises(ls.B200LUError):
+        ls.Handle(ls._capi.F64)
+    with pytest.raises(RuntimeError):
+        ls.B200LUFactorization()                       # throwerror=True
+    alg = ls.B200LUFactorization(throwerror=False)     # speculative construction is allowed
+    with pytest.raises(ls.B200LUError):
+        ls.solve(ls.LinearProblem(np.eye(4), np.ones(4)), alg)   # ... but solving is not
+
+
+def test_bad_arguments_do_not_need_a_device(ls):
+    lib = ls._capi.load()
+    h = ctypes.c_void_p()
+    assert lib.b200lu_create(ctypes.byref(h), 7, 1, None) == -2       # bad dtype
+    assert lib.b200lu_create(ctypes.byref(h), 0, 3, None) == -3       # ngpus != 1 per process
+    assert lib.b200lu_create(None, 0, 1, None) == -1
+    assert lib.b200lu_last_timing(None, 0) == -1.0
+    assert lib.b200lu_set_option(None, 0, 64) == -1
+
+
+def test_default_algorithm_bands_unchanged(ls):
+    """reference test/Core/default_algs.jl:4-66 with and without the new arm"""
+    C = ls.DefaultAlgorithmChoice
+    pick = lambda n, **kw: ls.defaultalg(np.zeros((n, n)), np.zeros(n), b200_available=kw.pop("gpu", False), **kw).alg
+    assert pick(3) == C.GenericLUFactorization
+    assert pick(10) == C.GenericLUFactorization
+    assert pick(50) == C.RFLUFactorization
+    assert pick(400) == C.RFLUFactorization                 # OpenBLAS band <= 500
+    assert pick(600) == C.LUFactorization
+    assert pick(600, usemkl=True) == C.MKLLUFactorization
+    assert pick(150, isopenblas=False, usemkl=True) == C.RFLUFactorization
+    assert pick(300, isopenblas=False, usemkl=True) == C.MKLLUFactorization
+    assert pick(200, userecursivefactorization=False) == C.GenericLUFactorization   # OpenBLAS <= 256
+    # the new arm: only when available, only above the break-even, never at n = 600
+    for n in (3, 50, 400, 600, 1000):
+        assert pick(n, gpu=True) == pick(n, gpu=False)
+    assert pick(1024, gpu=True) == C.B200LUFactorization
+    assert pick(8192, gpu=True) == C.B200LUFactorization
+    assert pick(8192, gpu=False) == C.LUFactorization
+    assert ls.defaultalg(np.zeros((2000, 2000), dtype=np.complex128), np.zeros(2000), b200_available=True).alg \
+        == C.LUFactorization
+    ill = ls.OperatorAssumptions(condition="VeryIllConditioned")
+    assert ls.defaultalg(np.zeros((2000, 2000)), np.zeros(2000), ill, b200_available=True).alg == C.QRFactorization
+    bd = ls.BlockDiagonal([np.eye(3)] * 4)
+    assert ls.defaultalg(bd, np.zeros(12), b200_available=False).alg == C.LUFactorization
+    assert ls.defaultalg(bd, np.zeros(12), b200_available=True).alg == C.B200LUFactorization
+
+
+def test_cache_protocol_without_compute(ls):
+    """src/common.jl:313-360: cache.A= sets isfresh, cache.b= does not; init copies A and b
+    (alias_A = false default for dense factorizations, src/common.jl:525,830-842)"""
+    A = np.arange(16.0).reshape(4, 4) + 10 * np.eye(4)
+    b = np.ones(4)
+    alg = ls.B200LUFactorization(throwerror=False)
+    cache = ls.init(ls.LinearProblem(A, b), alg)
+    assert cache.isfresh
+    assert cache.A is not A and np.array_equal(cache.A, A) and cache.A.flags.f_contiguous
+    assert cache.b is not b
+    assert np.array_equal(cache.u, np.zeros(4))
+    cache.isfresh = False
+    cache.b = np.zeros(4)
+    assert not cache.isfresh
+    cache.A = A
+    assert cache.isfresh
+    aliased = ls.init(ls.LinearProblem(A, b), alg, alias_A=True, alias_b=True)
+    assert aliased.A is A and aliased.b is b
+    with pytest.raises(ValueError):
+        ls.init(ls.LinearProblem(np.zeros((3, 4)), np.zeros(3)), alg)      # needs_square_A
+    with pytest.raises(ValueError):
+        ls.init(ls.LinearProblem(np.eye(3), np.zeros(4)), alg)
+    # integer promotion (src/common.jl:448-502)
+    ci = ls.init(ls.LinearProblem(np.eye(3, dtype=np.int64), np.ones(3, dtype=np.int32)), alg)
+    assert ci.A.dtype == np.float64 and ci.b.dtype == np.float64
+    with pytest.raises(NotImplementedError):
+        ls.init(ls.LinearProblem(np.eye(3), np.ones(3)))       # n = 3 -> reference CPU algorithm, out of scope
+
+
+def test_block_diagonal_container(ls):
+    bd = ls.BlockDiagonal([np.full((2, 2), 1.0), np.full((3, 3), 2.0)])
+    assert bd.shape == (5, 5) and bd.all_square()
+    D = bd.to_dense()
+    assert D[0, 0] == 1 and D[4, 4] == 2 and D[0, 4] == 0
+    assert list(bd.offsets) == [0, 2, 5]
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n", "512",
+                          "--nrhs", "4", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
