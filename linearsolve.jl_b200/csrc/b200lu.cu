@@ -1030,7 +1030,7 @@ static int batched_factor_launch(b200lu_handle* h, const T* A, int64_t lda, int6
     T* LU = (T*)h->dB_LU;
     cudaStream_t st = h->s_main;
     if (n <= 16)
-        getrf_batched_kernel<T, 16><<<(unsigned)batch, 16, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_info, n);
+        getrf_batched_kernel<T, 16><<<(unsigned)batch, 32, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_info, n);
     else if (n <= 32)
         getrf_batched_kernel<T, 32><<<(unsigned)batch, 32, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_info, n);
     else
@@ -1047,7 +1047,7 @@ static int batched_solve_launch(b200lu_handle* h, int nrhs, const T* B, int64_t 
     const T* LU = (const T*)h->dB_LU;
     cudaStream_t st = h->s_main;
     if (n <= 16)
-        getrs_batched_kernel<T, 16><<<(unsigned)batch, 16, 0, st>>>(LU, n, (int64_t)n * n, h->dB_ipiv, B, ldb, strideB, X, ldx, strideX, n, nrhs);
+        getrs_batched_kernel<T, 16><<<(unsigned)batch, 32, 0, st>>>(LU, n, (int64_t)n * n, h->dB_ipiv, B, ldb, strideB, X, ldx, strideX, n, nrhs);
     else if (n <= 32)
         getrs_batched_kernel<T, 32><<<(unsigned)batch, 32, 0, st>>>(LU, n, (int64_t)n * n, h->dB_ipiv, B, ldb, strideB, X, ldx, strideX, n, nrhs);
     else

@@ -14,11 +14,13 @@
 
 namespace b200lu {
 
+__host__ __device__ constexpr int batched_threads(int nmax) { return nmax < 32 ? 32 : nmax; }
+
 template <typename T, int NMAX>
-__global__ void __launch_bounds__(NMAX) getrf_batched_kernel(
+__global__ void __launch_bounds__(batched_threads(NMAX)) getrf_batched_kernel(
     const T* __restrict__ A, long long lda, long long strideA, T* __restrict__ LU,
     long long ldlu, long long strideLU, int* __restrict__ ipiv, int* __restrict__ info, int n) {
-    constexpr int NW = (NMAX + 31) / 32;
+    constexpr int NW = (NMAX + 31) / 32;  // blockDim.x == max(32, NMAX): lanes >= NMAX are padding rows
     __shared__ T s_row[NMAX];
     __shared__ T s_val[NW];
     __shared__ int s_pos[NW];
@@ -31,7 +33,7 @@ __global__ void __launch_bounds__(NMAX) getrf_batched_kernel(
 #pragma unroll
     for (int c = 0; c < NMAX; ++c)
         a[c] = (t < n && c < n) ? Ab[(long long)c * lda + t] : (t == c ? T(1) : T(0));
-    int pos = t;        // logical row position of this thread's row
+    int pos = t;        // logical row position of this thread's row (t >= n: never a candidate)
     bool done = false;  // row already used as a pivot row
     int myinfo = 0;
 
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(NMAX) getrf_batched_kernel(
                 // this row lands at position k; whoever sat at k takes my old position
                 done = true;
                 pos = k;
-                if (sys >= 0) ipiv[sys * n + k] = ppos;
+                ipiv[sys * n + k] = ppos;
                 if (pv == T(0) && myinfo == 0) myinfo = k + 1;
             } else if (!done && pos == k) {
                 pos = ppos;
@@ -116,12 +118,12 @@ __global__ void __launch_bounds__(NMAX) getrf_batched_kernel(
 // getrs on the cached batched factors: X = U \ (L \ (P B)), nrhs columns.
 // One CTA of NMAX threads per system; thread t holds row t of the packed LU.
 template <typename T, int NMAX>
-__global__ void __launch_bounds__(NMAX) getrs_batched_kernel(
+__global__ void __launch_bounds__(batched_threads(NMAX)) getrs_batched_kernel(
     const T* __restrict__ LU, long long ldlu, long long strideLU, const int* __restrict__ ipiv,
     const T* __restrict__ B, long long ldb, long long strideB, T* __restrict__ X, long long ldx,
     long long strideX, int n, int nrhs) {
-    __shared__ T s_b[NMAX];
-    __shared__ int s_perm[NMAX];
+    __shared__ T s_b[batched_threads(NMAX)];
+    __shared__ int s_perm[batched_threads(NMAX)];
     const int t = threadIdx.x;
     const long long sys = blockIdx.x;
     const T* Lb = LU + sys * strideLU;

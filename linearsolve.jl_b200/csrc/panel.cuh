@@ -9,12 +9,15 @@
 // B200 mapping: the (m x W) block lives in REGISTERS for the whole kernel: thread
 // t of CTA c owns RPT rows (all W columns of each).  Per column:
 //   1. warp-shuffle arg-max (lowest index on ties) -> CTA candidate;
-//   2. the candidate row and (val, idx) are published to a small L2-resident
-//      mailbox with a release flag (double-buffered by column parity);
-//   3. warp 0 of every CTA acquires all G flags, reduces the candidates, and
-//      stages the winning row + the current top row in shared memory;
+//   2. the candidate (|value|, row index, the whole candidate row) is written to an
+//      L2-resident mailbox as 64-bit {data32, flag32} packets ("LL" style: the
+//      flag travels with the data, so there is NO fence and NO separate flag);
+//   3. every CTA gathers all G candidate messages (one L2 round trip, all
+//      threads polling their own packets), warp 0 reduces them and stages the
+//      winning row + the current top row in shared memory;
 //   4. swap (pure register moves) + scale + rank-1 update.
-// One L2 round trip per column; no grid.sync, no kernel relaunch.
+// Mailboxes are double-buffered by column parity; flags are a monotone epoch, so
+// nothing is ever reset between columns or launches.
 // An extra "swapper" CTA follows the published pivots and applies each row
 // interchange eagerly to the remaining columns of the OUTER panel
 // [pc0, pc1) \ [j0, j0+wc), so the recursive panel needs no laswp kernels.
@@ -26,6 +29,15 @@ namespace b200lu {
 
 constexpr int PANEL_GMAX = 128;  // max CTAs cooperating on one base panel
 constexpr int PANEL_WMAX = 32;   // max base width
+// message words (32-bit): |val| (2) + idx (1) + row (2*W)  [float uses half of the value words]
+constexpr int PANEL_MSG_WORDS = 3 + 2 * PANEL_WMAX;  // 67
+constexpr int PANEL_TOP_WORDS = 2 * PANEL_WMAX;
+
+struct PanelMail {
+    unsigned long long msg[2][PANEL_GMAX][PANEL_MSG_WORDS + 1];
+    unsigned long long top[2][PANEL_TOP_WORDS];
+    unsigned long long piv[PANEL_WMAX];
+};
 
 template <typename T>
 struct PanelArgs {
@@ -38,23 +50,63 @@ struct PanelArgs {
     int* ipiv;           // global, 0-based row indices
     int* info;           // 0 or 1-based first zero pivot
     int G;               // panel CTAs (grid = G + has_swapper)
-    int epoch;           // flags carry epoch + j + 1 at column j
-    int* flags;          // [2][PANEL_GMAX]
-    T* cand_val;         // [2][PANEL_GMAX]
-    int* cand_idx;       // [2][PANEL_GMAX]
-    T* rowbuf;           // [2][PANEL_GMAX][PANEL_WMAX]
-    T* toprow;           // [2][PANEL_WMAX]
-    int* progress;       // last finished epoch (for the swapper)
+    unsigned epoch;      // packets carry epoch + j + 1 at column j
+    PanelMail* mail;
     int* deverr;
+};
+
+__device__ __forceinline__ void ll_store(unsigned long long* p, unsigned data, unsigned flag) {
+    const unsigned long long v = ((unsigned long long)flag << 32) | data;
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until the packet carries `want`; returns false on watchdog timeout
+__device__ __forceinline__ bool ll_wait(const unsigned long long* p, unsigned want, unsigned& data) {
+    unsigned long long v = ll_load(p);
+    if ((unsigned)(v >> 32) != want) {
+        const long long t0 = clock64();
+        do {
+            v = ll_load(p);
+            if (clock64() - t0 > kSpinTimeoutCycles) return false;
+        } while ((unsigned)(v >> 32) != want);
+    }
+    data = (unsigned)v;
+    return true;
+}
+
+template <typename T> struct Words;
+template <> struct Words<double> {
+    static constexpr int N = 2;
+    __device__ static void split(double x, unsigned* w) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+        w[0] = (unsigned)b; w[1] = (unsigned)(b >> 32);
+    }
+    __device__ static double join(const unsigned* w) {
+        return __longlong_as_double((long long)(((unsigned long long)w[1] << 32) | w[0]));
+    }
+};
+template <> struct Words<float> {
+    static constexpr int N = 1;
+    __device__ static void split(float x, unsigned* w) { w[0] = __float_as_uint(x); }
+    __device__ static float join(const unsigned* w) { return __uint_as_float(w[0]); }
 };
 
 template <typename T, int W, int RPT, int NT>
 __global__ void __launch_bounds__(NT, 1) panel_base_kernel(PanelArgs<T> p) {
     constexpr int NW = NT / 32;
+    constexpr int WN = Words<T>::N;
+    constexpr int OFF_IDX = WN;              // message layout: [val WN][idx 1][row W*WN]
+    constexpr int OFF_ROW = WN + 1;
+    constexpr int MSG = OFF_ROW + W * WN;    // words actually used
+    extern __shared__ unsigned s_tab[];      // [G*MSG + W*WN] gathered message words
     __shared__ T s_val[NW];
     __shared__ int s_idx[NW];
-    __shared__ T s_prow[PANEL_WMAX];
-    __shared__ T s_trow[PANEL_WMAX];
+    __shared__ __align__(16) T s_prow[PANEL_WMAX];
+    __shared__ __align__(16) T s_trow[PANEL_WMAX];
     __shared__ int s_piv;
     __shared__ int s_abort;
 
@@ -64,36 +116,31 @@ __global__ void __launch_bounds__(NT, 1) panel_base_kernel(PanelArgs<T> p) {
     const int cta = blockIdx.x;
     const int G = p.G;
     const int wc = p.wc;
+    PanelMail* mail = p.mail;
 
     // ------------------------------------------------------------------ swapper
     if (cta >= G) {
         const int nleft = p.j0 - p.pc0;
         const int nright = p.pc1 - (p.j0 + wc);
         const int ncols = nleft + nright;
-        if (tid == 0) s_abort = 0;
-        __syncthreads();
         for (int j = 0; j < wc; ++j) {
             if (tid == 0) {
-                const int want = p.epoch + j + 1;
-                long long t0 = clock64();
-                while (ld_acquire(p.progress) - want < 0) {
-                    if (clock64() - t0 > kSpinTimeoutCycles) {
-                        atomicExch(p.deverr, DEV_ERR_PANEL_TIMEOUT);
-                        s_abort = 1;
-                        break;
-                    }
-                }
+                unsigned d = 0;
+                const bool ok = ll_wait(&mail->piv[j], p.epoch + j + 1, d);
+                if (!ok) atomicExch(p.deverr, DEV_ERR_PANEL_TIMEOUT);
+                s_piv = ok ? (int)d : -1;
             }
             __syncthreads();
-            if (s_abort) return;
+            const int piv = s_piv;
+            __syncthreads();
+            if (piv < 0) return;
             const int k = p.j0 + j;
-            const int piv = ld_cg(p.ipiv + k);
             if (piv != k) {
                 for (int c = tid; c < ncols; c += NT) {
                     const int col = (c < nleft) ? (p.pc0 + c) : (p.j0 + wc + (c - nleft));
                     T* pk = p.A + (long long)col * p.lda + k;
                     T* pp = p.A + (long long)col * p.lda + piv;
-                    T vk = *pk, vp = *pp;
+                    const T vk = *pk, vp = *pp;
                     *pk = vp;
                     *pp = vk;
                 }
@@ -116,26 +163,27 @@ __global__ void __launch_bounds__(NT, 1) panel_base_kernel(PanelArgs<T> p) {
         }
     }
     if (tid == 0) s_abort = 0;
+    const int total_words = G * MSG + W * WN;
 
 #pragma unroll
     for (int j = 0; j < W; ++j) {
         if (j < wc) {
             const int par = j & 1;
-            const int want = p.epoch + j + 1;
+            const unsigned want = p.epoch + j + 1;
             // 1. local candidate: strict '>' from amax = 0, rows ascending
             T best = T(0);
             int bi = INT_MAX;
 #pragma unroll
             for (int q = 0; q < RPT; ++q) {
                 if (ri[q] >= j && ri[q] < p.m) {
-                    T v = tabs(a[q][j]);
+                    const T v = tabs(a[q][j]);
                     if (v > best) { best = v; bi = ri[q]; }
                 }
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
-                T ob = shfl_xor(best, off);
-                int oi = shfl_xor(bi, off);
+                const T ob = shfl_xor(best, off);
+                const int oi = shfl_xor(bi, off);
                 if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
             if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
@@ -144,63 +192,78 @@ __global__ void __launch_bounds__(NT, 1) panel_base_kernel(PanelArgs<T> p) {
             int ci = s_idx[0];
 #pragma unroll
             for (int w = 1; w < NW; ++w) {
-                T ob = s_val[w];
-                int oi = s_idx[w];
+                const T ob = s_val[w];
+                const int oi = s_idx[w];
                 if (ob > cb || (ob == cb && oi < ci)) { cb = ob; ci = oi; }
             }
-            // 2. publish candidate row (+ the current top row from its owner)
+            // 2. publish: the candidate's owner writes the whole message as LL packets
+            {
+                unsigned long long* mb = mail->msg[par][cta];
+                const bool nocand = (ci == INT_MAX);
 #pragma unroll
-            for (int q = 0; q < RPT; ++q) {
-                if (ri[q] == ci) {
-                    T* dst = p.rowbuf + ((long long)par * PANEL_GMAX + cta) * PANEL_WMAX;
+                for (int q = 0; q < RPT; ++q) {
+                    const bool writer = nocand ? (q == 0 && tid == 0) : (ri[q] == ci);
+                    if (writer) {
+                        unsigned w[WN];
+                        Words<T>::split(cb, w);
 #pragma unroll
-                    for (int c = 0; c < W; ++c) dst[c] = a[q][c];
-                    __threadfence();
+                        for (int x = 0; x < WN; ++x) ll_store(mb + x, w[x], want);
+                        ll_store(mb + OFF_IDX, (unsigned)ci, want);
+#pragma unroll
+                        for (int c = 0; c < W; ++c) {
+                            Words<T>::split(nocand ? T(0) : a[q][c], w);
+#pragma unroll
+                            for (int x = 0; x < WN; ++x) ll_store(mb + OFF_ROW + c * WN + x, w[x], want);
+                        }
+                    }
+                    if (ri[q] == j) {  // current top row (CTA 0 only)
+                        unsigned w[WN];
+#pragma unroll
+                        for (int c = 0; c < W; ++c) {
+                            Words<T>::split(a[q][c], w);
+#pragma unroll
+                            for (int x = 0; x < WN; ++x) ll_store(&mail->top[par][c * WN + x], w[x], want);
+                        }
+                    }
                 }
-                if (ri[q] == j) {
-                    T* dst = p.toprow + par * PANEL_WMAX;
-#pragma unroll
-                    for (int c = 0; c < W; ++c) dst[c] = a[q][c];
-                    __threadfence();
+            }
+            // 3. gather all messages (every thread polls its own packets)
+            {
+                bool dead = false;
+                for (int idx = tid; idx < total_words; idx += NT) {
+                    const unsigned long long* src;
+                    if (idx < G * MSG) {
+                        const int c = idx / MSG;
+                        src = &mail->msg[par][c][idx - c * MSG];
+                    } else {
+                        src = &mail->top[par][idx - G * MSG];
+                    }
+                    unsigned d = 0;
+                    if (!ll_wait(src, want, d)) dead = true;
+                    s_tab[idx] = d;
                 }
+                if (dead) { atomicExch(p.deverr, DEV_ERR_PANEL_TIMEOUT); s_abort = 1; }
             }
             __syncthreads();
-            if (tid == 0) {
-                p.cand_val[par * PANEL_GMAX + cta] = cb;
-                p.cand_idx[par * PANEL_GMAX + cta] = ci;
-                __threadfence();
-                st_release(p.flags + par * PANEL_GMAX + cta, want);
-            }
-            // 3. warp 0: acquire all candidates, pick the pivot, stage rows
             if (warp == 0) {
                 T gv = T(0);
-                int gi = INT_MAX;
-                int gc = -1;
-                bool dead = false;
+                int gi = INT_MAX, gc = -1;
                 for (int c = lane; c < G; c += 32) {
-                    long long t0 = clock64();
-                    while (ld_acquire(p.flags + par * PANEL_GMAX + c) != want) {
-                        if (clock64() - t0 > kSpinTimeoutCycles) { dead = true; break; }
-                    }
-                    T v = ld_cg(p.cand_val + par * PANEL_GMAX + c);
-                    int idx = ld_cg(p.cand_idx + par * PANEL_GMAX + c);
+                    const T v = Words<T>::join(&s_tab[c * MSG]);
+                    const int idx = (int)s_tab[c * MSG + OFF_IDX];
                     if (v > gv || (v == gv && idx < gi)) { gv = v; gi = idx; gc = c; }
-                }
-                if (__any_sync(0xffffffffu, dead)) {
-                    if (lane == 0) { atomicExch(p.deverr, DEV_ERR_PANEL_TIMEOUT); s_abort = 1; }
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
-                    T ob = shfl_xor(gv, off);
-                    int oi = shfl_xor(gi, off);
-                    int oc = shfl_xor(gc, off);
+                    const T ob = shfl_xor(gv, off);
+                    const int oi = shfl_xor(gi, off);
+                    const int oc = shfl_xor(gc, off);
                     if (ob > gv || (ob == gv && oi < gi)) { gv = ob; gi = oi; gc = oc; }
                 }
                 const bool none = !(gv > T(0));  // all-zero (or all-NaN) subcolumn: kp = k
                 if (lane < W) {
-                    T tr = ld_cg(p.toprow + par * PANEL_WMAX + lane);
-                    T pr = none ? tr
-                                : ld_cg(p.rowbuf + ((long long)par * PANEL_GMAX + gc) * PANEL_WMAX + lane);
+                    const T tr = Words<T>::join(&s_tab[G * MSG + lane * WN]);
+                    const T pr = none ? tr : Words<T>::join(&s_tab[gc * MSG + OFF_ROW + lane * WN]);
                     s_trow[lane] = tr;
                     s_prow[lane] = pr;
                 }
@@ -213,9 +276,8 @@ __global__ void __launch_bounds__(NT, 1) panel_base_kernel(PanelArgs<T> p) {
             const T pv = s_prow[j];
             if (cta == 0 && tid == 0) {
                 p.ipiv[p.j0 + j] = p.j0 + piv;
+                ll_store(&mail->piv[j], (unsigned)(p.j0 + piv), want);
                 if (pv == T(0) && *p.info == 0) *p.info = p.j0 + j + 1;
-                __threadfence();
-                st_release(p.progress, want);
             }
             const bool scale = (pv != T(0));
             const T rinv = T(1) / pv;

@@ -1,0 +1,233 @@
+# B200LUFactorization.jl — the glue a LinearSolve.jl maintainer adds to reach
+# libb200lu.so.  NOT runnable in the build environment (no Julia); it is kept
+# declarative and follows, line for line, patterns that already exist in the
+# reference (v5.12.0):
+#   * struct + `throwerror=false` constructor  : src/extension_algs.jl:344-354
+#   * direct-`ccall` getrf/getrs wrappers        : src/openblas.jl:131-154,247-278
+#   * cacheval struct + init_cacheval            : src/openblas.jl:312-360
+#   * solve! protocol (isfresh / Failure / u<-b) : src/openblas.jl:362-459
+#   * 32Mixed variant                            : src/openblas.jl:470-543
+#   * availability hook                          : src/LinearSolve.jl:741-743
+# The Python package `linearsolve.jl_b200` (interface.py/_capi.py) is the tested
+# twin of this file: same names, same control flow, ctypes instead of ccall.
+#
+# Everything below lives in `src/b200lu.jl` (included from src/LinearSolve.jl
+# next to `include("openblas.jl")`); the enum wiring is listed in INTEGRATION.md.
+
+const libb200lu = Ref{String}(get(ENV, "LINEARSOLVE_B200LU_LIB", "libb200lu.so"))
+const _b200lu_handle_ok = Ref{Union{Nothing, Bool}}(nothing)
+
+# dtype codes of include/b200lu.h
+const B200LU_F64 = Cint(0)
+const B200LU_F32 = Cint(1)
+const B200LU_MIXED = Cint(2)
+
+"""
+    useb200()
+
+`true` when libb200lu.so can be dlopen'ed and creates a handle on an sm_100
+device.  Cached after the first call.  Mirrors `usecuda`/`usemetal`
+(src/LinearSolve.jl:741-743): the default algorithm only routes here when it
+returns `true`, so machines without the library see no behaviour change.
+"""
+function useb200()
+    ok = _b200lu_handle_ok[]
+    ok === nothing || return ok
+    ok = try
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:b200lu_create, libb200lu[]), Cint,
+            (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Cint}), h, B200LU_F64, 1, C_NULL)
+        rc == 0 && ccall((:b200lu_destroy, libb200lu[]), Cvoid, (Ptr{Cvoid},), h[])
+        rc == 0
+    catch
+        false
+    end
+    _b200lu_handle_ok[] = ok
+    return ok
+end
+
+"""
+    B200LUFactorization(; throwerror = true, residualsafety = false, device = 0)
+
+Dense partially pivoted LU on one NVIDIA B200 through `libb200lu.so`
+(hand-written sm_100a kernels; no CUDA.jl, no cuSOLVER, no CPU fallback).
+Host arrays in, host arrays out; the factors stay on the device inside the
+cache, so `cache.b = b2; solve!(cache)` only runs getrs.
+"""
+struct B200LUFactorization <: AbstractFactorization
+    residualsafety::Bool
+    device::Int
+    function B200LUFactorization(; throwerror = true, residualsafety::Bool = false, device::Int = 0)
+        if throwerror && !useb200()
+            error("B200LUFactorization requires libb200lu.so and an NVIDIA B200 (sm_100) GPU")
+        end
+        return new(residualsafety, device)
+    end
+end
+
+"""
+    B200LU32MixedLUFactorization(; refine = true, maxiters = 10, throwerror = true)
+
+Float64 interface, Float32 factorization on the GPU.  With `refine = false` this
+is the behaviour of the other `*32MixedLUFactorization` algorithms (cast, sgetrf,
+sgetrs, cast back); with `refine = true` an FP64 residual/correction loop runs on
+the device until the normwise backward error reaches FP64 working accuracy.
+"""
+struct B200LU32MixedLUFactorization <: AbstractFactorization
+    refine::Bool
+    maxiters::Int
+    device::Int
+    function B200LU32MixedLUFactorization(; refine::Bool = true, maxiters::Int = 10,
+            throwerror = true, device::Int = 0)
+        if throwerror && !useb200()
+            error("B200LU32MixedLUFactorization requires libb200lu.so and an NVIDIA B200 (sm_100) GPU")
+        end
+        return new(refine, maxiters, device)
+    end
+end
+
+# traits live next to the struct, never in an extension (src/interface.jl:203-209)
+needs_concrete_A(::B200LUFactorization) = true
+needs_concrete_A(::B200LU32MixedLUFactorization) = true
+default_alias_A(::B200LUFactorization, ::Any, ::Any) = false
+default_alias_b(::B200LUFactorization, ::Any, ::Any) = false
+default_alias_A(::B200LU32MixedLUFactorization, ::Any, ::Any) = false
+default_alias_b(::B200LU32MixedLUFactorization, ::Any, ::Any) = false
+_get_residualsafety(alg::B200LUFactorization) = alg.residualsafety
+
+# ------------------------------------------------------------------ cacheval --
+mutable struct B200LUCache
+    handle::Ptr{Cvoid}          # b200lu_handle*, C_NULL until the first fresh solve
+    dtype::Cint
+    ipiv::Vector{BlasInt}       # 1-based LAPACK interchange sequence (BlasInt == Int64)
+    info::Base.RefValue{BlasInt}
+    n::Int
+end
+
+function _b200lu_finalize(c::B200LUCache)
+    if c.handle != C_NULL
+        ccall((:b200lu_destroy, libb200lu[]), Cvoid, (Ptr{Cvoid},), c.handle)
+        c.handle = C_NULL
+    end
+    return nothing
+end
+
+function _b200lu_cache(dtype::Cint)
+    c = B200LUCache(C_NULL, dtype, Vector{BlasInt}(undef, 0), Ref{BlasInt}(0), 0)
+    finalizer(_b200lu_finalize, c)      # pattern: AMGX handles, src/extension_algs.jl:1555-1556
+    return c
+end
+
+_b200lu_dtype(::B200LUFactorization, ::Type{Float64}) = B200LU_F64
+_b200lu_dtype(::B200LUFactorization, ::Type{Float32}) = B200LU_F32
+_b200lu_dtype(::B200LU32MixedLUFactorization, ::Type{Float64}) = B200LU_MIXED
+
+# init_cacheval must return the SAME concrete type solve! later stores
+# (docs/src/advanced/algorithm_interface.md:68); no device allocation here —
+# the default solver builds every slot eagerly (src/default.jl:645-694).
+function init_cacheval(
+        alg::Union{B200LUFactorization, B200LU32MixedLUFactorization}, A, b, u, Pl, Pr,
+        maxiters::Int, abstol, reltol, verbose::Union{LinearVerbosity, Bool},
+        assumptions::OperatorAssumptions
+    )
+    T = A === nothing ? Float64 : eltype(A)
+    dtype = T === Float32 && alg isa B200LUFactorization ? B200LU_F32 :
+            (alg isa B200LU32MixedLUFactorization ? B200LU_MIXED : B200LU_F64)
+    return _b200lu_cache(dtype)
+end
+
+function _b200lu_error(c::B200LUCache, rc::Cint)
+    msg = unsafe_string(ccall((:b200lu_last_error, libb200lu[]), Cstring, (Ptr{Cvoid},), c.handle))
+    return error("libb200lu status $rc: $msg")
+end
+
+function _b200lu_ensure_handle!(c::B200LUCache, alg)
+    c.handle != C_NULL && return c
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    dev = Cint[alg.device]
+    rc = ccall((:b200lu_create, libb200lu[]), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Cint}), h, c.dtype, 1, dev)
+    rc == 0 || error("b200lu_create failed with status $rc (no usable sm_100 device; there is no CPU fallback)")
+    c.handle = h[]
+    if alg isa B200LU32MixedLUFactorization
+        ccall((:b200lu_set_option, libb200lu[]), Cint, (Ptr{Cvoid}, Cint, Int64),
+            c.handle, 2, alg.refine ? alg.maxiters : 0)          # B200LU_OPT_REFINE_MAXIT
+    end
+    return c
+end
+
+# getrf: same call shape as openblas_getrf! (src/openblas.jl:131-154)
+@inline function _direct_lu_factorize!(c::B200LUCache, A::StridedMatrix{T}, alg) where {T}
+    chkstride1(A)
+    n = checksquare(A)
+    _b200lu_ensure_handle!(c, alg)
+    length(c.ipiv) == n || resize!(c.ipiv, n)
+    rc = ccall((:b200lu_factor, libb200lu[]), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{T}, Int64, Ptr{BlasInt}, Ref{BlasInt}),
+        c.handle, n, A, max(1, stride(A, 2)), c.ipiv, c.info)
+    rc == 0 || _b200lu_error(c, rc)
+    c.n = n
+    return c.info[]
+end
+
+# getrs: same call shape as openblas_getrs! (src/openblas.jl:247-278); u may alias b
+@inline function _direct_lu_solve!(c::B200LUCache, u::StridedVecOrMat{T}, b::StridedVecOrMat{T}, alg) where {T}
+    chkstride1(u, b)
+    size(b, 1) == c.n || throw(DimensionMismatch("b has leading dimension $(size(b, 1)), but needs $(c.n)"))
+    rc = ccall((:b200lu_solve, libb200lu[]), Cint,
+        (Ptr{Cvoid}, UInt8, Int64, Ptr{T}, Int64, Ptr{T}, Int64),
+        c.handle, UInt8('N'), size(b, 2), b, max(1, stride(b, 2)), u, max(1, stride(u, 2)))
+    rc == 0 || _b200lu_error(c, rc)
+    return u
+end
+
+function SciMLBase.solve!(
+        cache::LinearCache, alg::Union{B200LUFactorization, B200LU32MixedLUFactorization};
+        kwargs...
+    )
+    A_work = convert(AbstractMatrix, cache.A)
+    check_safety = alg isa B200LUFactorization && alg.residualsafety && cache.isfresh
+    # host A is never overwritten by the device path, so no A_backup copy is needed
+    # for the default solver's QR rescue (contrast src/openblas.jl:369-372)
+    cacheval = alg isa B200LUFactorization ?
+        @get_cacheval(cache, :B200LUFactorization) :
+        @get_cacheval(cache, :B200LU32MixedLUFactorization)
+    if cache.isfresh
+        info_value = _direct_lu_factorize!(cacheval, A_work, alg)
+        if info_value != 0
+            @SciMLMessage("Solver failed", cache.verbose, :solver_failure)
+            return SciMLBase.build_linear_solution(
+                alg, cache.u, nothing, nothing; retcode = ReturnCode.Failure
+            )                                   # isfresh stays true (src/factorization.jl:714-722)
+        end
+        cache.isfresh = false
+    end
+    require_one_based_indexing(cache.u, cache.b)
+    _direct_lu_solve!(cacheval, cache.u, cache.b, alg)
+    if check_safety
+        failed = _check_residual_safety(cache, alg, A_work, cache.u)
+        failed !== nothing && return failed
+    end
+    return SciMLBase.build_linear_solution(
+        alg, cache.u, nothing, nothing; retcode = ReturnCode.Success
+    )
+end
+
+# BlockDiagonal surface (ext/LinearSolveBlockDiagonalsExt.jl:119-125,183-205): equal
+# square blocks of size <= 64 go through ONE batched call.
+function _b200lu_factor_blocks!(c::B200LUCache, blocks::Vector{Matrix{T}}, alg) where {T}
+    n = size(first(blocks), 1)
+    batch = length(blocks)
+    _b200lu_ensure_handle!(c, alg)
+    packed = Array{T, 3}(undef, n, n, batch)          # column-major blocks back to back
+    for (s, B) in enumerate(blocks)
+        copyto!(view(packed, :, :, s), B)
+    end
+    ipiv = Vector{BlasInt}(undef, n * batch)
+    info = Vector{BlasInt}(undef, batch)
+    rc = ccall((:b200lu_factor_batched, libb200lu[]), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{T}, Int64, Int64, Ptr{BlasInt}, Ptr{BlasInt}),
+        c.handle, batch, n, packed, n, n * n, ipiv, info)
+    rc == 0 || _b200lu_error(c, rc)
+    return all(iszero, info)                           # success = all(issuccess), :121-124
+end

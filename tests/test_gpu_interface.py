@@ -117,10 +117,10 @@ def test_matrix_rhs(gpu_required, ls, oracle, nrhs):
     cache = ls.init(ls.LinearProblem(A, B), ls.B200LUFactorization())
     sol = ls.solve_(cache)
     assert sol.retcode == ls.ReturnCode.Success
-    np.testing.assert_allclose(sol.u, np.linalg.solve(A, B), rtol=1e-10)
+    np.testing.assert_allclose(sol.u, np.linalg.solve(A, B), rtol=1e-10, atol=1e-14)
     B2 = rng.random((n, nrhs))
     cache.b = B2
-    np.testing.assert_allclose(ls.solve_(cache).u, np.linalg.solve(A, B2), rtol=1e-10)
+    np.testing.assert_allclose(ls.solve_(cache).u, np.linalg.solve(A, B2), rtol=1e-10, atol=1e-14)
     # singular => failure retcode (batch.jl:135-147)
     cache.A = np.zeros((n, n))
     assert ls.solve_(cache).retcode == ls.ReturnCode.Failure
