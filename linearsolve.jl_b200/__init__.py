@@ -26,9 +26,12 @@ from .interface import (
     LinearSolution,
     OperatorAssumptions,
     ReturnCode,
+    block_cyclic_columns,
     defaultalg,
     init,
+    reduce_info,
     reinit,
+    shard_batch,
     solve,
     solve_,
     successful_retcode,

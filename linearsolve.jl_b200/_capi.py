@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libb200lu.so")
 
 F64, F32, MIXED = 0, 1, 2
 T_H2D, T_FACTOR, T_SOLVE, T_D2H, T_GEMM = range(5)
-OPT_NB, OPT_LOOKAHEAD, OPT_REFINE_MAXIT, OPT_PANEL_CTAS, OPT_SOLVE_NRHS_TILE, OPT_PROFILE = range(6)
+OPT_NB, OPT_LOOKAHEAD, OPT_REFINE_MAXIT, OPT_PANEL_CTAS, OPT_SOLVE_NRHS_TILE, OPT_PROFILE, OPT_PANEL_RPT = range(7)
 C_GEMM_FLOPS, C_GEMM_LAUNCHES, C_REFINE_ITERS = range(3)
 PEAK_FP64_DMMA, PEAK_FP64_DFMA, PEAK_HBM_COPY = range(3)
 
@@ -225,6 +225,35 @@ class Handle:
         cs = cb if col_block_stride is None else col_block_stride
         self._check(self.lib.b200lu_fill_uniform_device(self._h, ctypes.c_void_p(ptr), lda, n, ncols,
                                                         first_global_col, cb, cs, seed, diag_shift))
+
+    # ---- one-process-per-GPU distributed mode (1D block-cyclic columns) --------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        rc = load().b200lu_comm_unique_id(buf)
+        if rc != 0:
+            raise B200LUError(rc, "b200lu_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, id_bytes: bytes, rank: int, nranks: int):
+        buf = ctypes.create_string_buffer(id_bytes, 128)
+        self._check(self.lib.b200lu_comm_init(self._h, buf, rank, nranks))
+        self.rank, self.nranks = rank, nranks
+
+    def dist_local_cols(self, n: int) -> int:
+        out = ctypes.c_int64(0)
+        self._check(self.lib.b200lu_dist_local_cols(self._h, n, ctypes.byref(out)))
+        return int(out.value)
+
+    def factor_dist(self, ptr, n, lda):
+        info = ctypes.c_int64(0)
+        self._check(self.lib.b200lu_factor_dist(self._h, n, ctypes.c_void_p(ptr), lda, ctypes.byref(info)))
+        self.n = n
+        return int(info.value)
+
+    def solve_dist(self, b_ptr, ldb, x_ptr, ldx, nrhs=1):
+        self._check(self.lib.b200lu_solve_dist(self._h, nrhs, ctypes.c_void_p(b_ptr), ldb,
+                                               ctypes.c_void_p(x_ptr), ldx))
 
     # ---- batched -------------------------------------------------------------
     def factor_batched(self, A):

@@ -44,7 +44,7 @@ struct b200lu_handle {
     int64_t opt[B200LU_OPT_COUNT];
 
     // single large system
-    int64_t n = 0, ldd = 0, cap_n = 0;
+    int64_t n = 0, ldd = 0, cap_n = 0, cap_meta = 0;
     void* dA = nullptr;        // factors (double for F64, float for F32/MIXED)
     double* dA64 = nullptr;    // MIXED: FP64 copy of A for residuals
     int* d_ipiv = nullptr;
@@ -54,17 +54,20 @@ struct b200lu_handle {
     LaswpPlan* d_plans = nullptr;
     int cap_plans = 0;
     void* d_panelsync = nullptr;
-    int panel_epoch = 0;
+    unsigned panel_epoch = 0;
     bool factored = false;
     int64_t info = 0;
     // solve state
     bool solve_ready = false;
     void* d_dinvL = nullptr;
     void* d_dinvU = nullptr;
+    void* d_wL = nullptr;   // coupling blocks dinv_r * A[r, r-1]
+    void* d_wU = nullptr;   // coupling blocks dinv_r * A[r, r+1]
     int* d_tflags = nullptr;
     int* d_tticket = nullptr;
     int cap_tgroups = 0;
-    int trsv_epoch = 0;
+    size_t cap_tflag_bytes = 0;
+    unsigned trsv_epoch = 0;
     void* d_B = nullptr;       // staging for host solves / permuted rhs
     void* d_X = nullptr;
     int64_t cap_rhs = 0;
@@ -102,8 +105,9 @@ struct b200lu_handle {
     double counters[B200LU_C_COUNT] = {0};
 
     // distributed (filled by dist.cuh)
-    void* comm = nullptr;
+    void* comm = nullptr;  // DistState*
     int rank = 0, nranks = 1;
+    bool factored_dist = false;
 };
 
 static int set_err(b200lu_handle* h, int status, const char* fmt, ...) {
@@ -142,34 +146,13 @@ static void free_dev(P*& p) {
     p = nullptr;
 }
 
-// --------------------------------------------------------- panel sync blob --
-struct PanelSyncLayout {
-    size_t off_flags, off_cval, off_cidx, off_rowbuf, off_toprow, off_progress, total;
-};
-static PanelSyncLayout panel_sync_layout() {
-    PanelSyncLayout L;
-    size_t o = 0;
-    L.off_flags = o;   o += sizeof(int) * 2 * PANEL_GMAX;
-    L.off_cidx = o;    o += sizeof(int) * 2 * PANEL_GMAX;
-    L.off_progress = o; o += 64;
-    o = (o + 255) & ~(size_t)255;
-    L.off_cval = o;    o += sizeof(double) * 2 * PANEL_GMAX;
-    L.off_toprow = o;  o += sizeof(double) * 2 * PANEL_WMAX;
-    L.off_rowbuf = o;  o += sizeof(double) * 2 * PANEL_GMAX * PANEL_WMAX;
-    L.total = o;
-    return L;
-}
-
 // ------------------------------------------------------------ kernel launch --
-constexpr int BASE_W = 16;    // base panel width (columns held in registers)
-constexpr int BASE_RPT = 2;   // rows per thread
+constexpr int BASE_W = 32;    // base panel width (columns held in registers)
 constexpr int BASE_NT = 256;  // threads per panel CTA
 
 template <typename T>
 static int launch_panel_base(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda, int nrows,
                              int j0, int wc, int pc0, int pc1) {
-    const PanelSyncLayout L = panel_sync_layout();
-    char* blob = (char*)h->d_panelsync;
     PanelArgs<T> p;
     p.A = A;
     p.lda = lda;
@@ -180,27 +163,29 @@ static int launch_panel_base(b200lu_handle* h, cudaStream_t st, T* A, int64_t ld
     p.pc1 = pc1;
     p.ipiv = h->d_ipiv;
     p.info = h->d_info;
-    const int rows_per_cta = BASE_NT * BASE_RPT;
-    int G = cdiv(p.m, rows_per_cta);
+    // rows per thread: 1 keeps the block spill-free and halves the per-column work of a
+    // thread; 2 halves the number of cooperating CTAs (and mailbox traffic) for tall panels
+    int rpt = (int)h->opt[B200LU_OPT_PANEL_RPT];
+    if (rpt == 0) rpt = (p.m <= 16384) ? 1 : 2;
     const int gmax = (int)std::min<int64_t>(PANEL_GMAX, h->opt[B200LU_OPT_PANEL_CTAS]);
+    if (rpt == 1 && cdiv(p.m, BASE_NT) > gmax) rpt = 2;
+    const int G = cdiv(p.m, BASE_NT * rpt);
     if (G > gmax)
         return set_err(h, 2, "panel of %d rows needs %d CTAs > limit %d", p.m, G, gmax);
     p.G = G;
-    if (h->panel_epoch > (1 << 30)) {
-        CU_TRY(h, cudaMemsetAsync(blob, 0, L.off_cval, st));
+    if (h->panel_epoch > (1u << 30)) {
+        CU_TRY(h, cudaMemsetAsync(h->d_panelsync, 0, sizeof(PanelMail), st));
         h->panel_epoch = 0;
     }
     p.epoch = h->panel_epoch;
     h->panel_epoch += BASE_W;
-    p.flags = (int*)(blob + L.off_flags);
-    p.cand_idx = (int*)(blob + L.off_cidx);
-    p.progress = (int*)(blob + L.off_progress);
-    p.cand_val = (T*)(blob + L.off_cval);
-    p.toprow = (T*)(blob + L.off_toprow);
-    p.rowbuf = (T*)(blob + L.off_rowbuf);
+    p.mail = (PanelMail*)h->d_panelsync;
     p.deverr = h->d_deverr;
     const int has_swapper = (pc1 - pc0) > wc ? 1 : 0;
-    panel_base_kernel<T, BASE_W, BASE_RPT, BASE_NT><<<G + has_swapper, BASE_NT, 0, st>>>(p);
+    if (rpt == 1)
+        panel_base_kernel<T, BASE_W, 1, BASE_NT><<<G + has_swapper, BASE_NT, 0, st>>>(p);
+    else
+        panel_base_kernel<T, BASE_W, 2, BASE_NT><<<G + has_swapper, BASE_NT, 0, st>>>(p);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -349,7 +334,7 @@ static int getrf_device(b200lu_handle* h, T* A, int64_t lda, int n) {
         const int jb = std::min(nb, n);
         rc = panel_recursive<T>(h, sp, A, lda, n, 0, jb, 0, jb);
         if (rc) return rc;
-        laswp_plan_kernel<<<1, 32, 0, sp>>>(h->d_ipiv, 0, jb, h->d_plans + 0);
+        laswp_plan_kernel<<<1, 2 * LASWP_MAXSW, 0, sp>>>(h->d_ipiv, 0, jb, h->d_plans + 0);
         LAUNCH_CHECK(h);
         if (la) CU_TRY(h, cudaEventRecord(h->ev_panel[0], sp));
     }
@@ -381,7 +366,7 @@ static int getrf_device(b200lu_handle* h, T* A, int64_t lda, int n) {
         }
         rc = panel_recursive<T>(h, sp, A, lda, n, j1, jb2, j1, j1 + jb2);
         if (rc) return rc;
-        laswp_plan_kernel<<<1, 32, 0, sp>>>(h->d_ipiv, j1, jb2, h->d_plans + (k + 1));
+        laswp_plan_kernel<<<1, 2 * LASWP_MAXSW, 0, sp>>>(h->d_ipiv, j1, jb2, h->d_plans + (k + 1));
         LAUNCH_CHECK(h);
         if (la) CU_TRY(h, cudaEventRecord(h->ev_panel[k + 1], sp));
         // rest of the trailing matrix
@@ -398,9 +383,39 @@ static int getrf_device(b200lu_handle* h, T* A, int64_t lda, int n) {
 }
 
 // ----------------------------------------------------------------- capacity --
+// pivots / permutation / laswp plans / pinned staging: needed by every mode
+static int ensure_meta(b200lu_handle* h, int64_t n) {
+    if (n <= h->cap_meta) return 0;
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    int* old_ipiv = h->d_ipiv;
+    int* old_perm = h->d_perm;
+    h->d_ipiv = nullptr;
+    h->d_perm = nullptr;
+    free_dev(h->d_plans);
+    CU_TRY(h, cudaMalloc((void**)&h->d_ipiv, (size_t)n * sizeof(int)));
+    CU_TRY(h, cudaMalloc((void**)&h->d_perm, (size_t)n * sizeof(int)));
+    if (old_ipiv && h->cap_meta > 0) {  // keep a cached factorization's pivots alive
+        CU_TRY(h, cudaMemcpy(h->d_ipiv, old_ipiv, (size_t)h->cap_meta * sizeof(int), cudaMemcpyDeviceToDevice));
+        CU_TRY(h, cudaMemcpy(h->d_perm, old_perm, (size_t)h->cap_meta * sizeof(int), cudaMemcpyDeviceToDevice));
+    }
+    free_dev(old_ipiv);
+    free_dev(old_perm);
+    h->cap_plans = cdiv(n, 16) + 1;
+    CU_TRY(h, cudaMalloc((void**)&h->d_plans, (size_t)h->cap_plans * sizeof(LaswpPlan)));
+    if (n > h->cap_hipiv) {
+        if (h->h_ipiv) cudaFreeHost(h->h_ipiv);
+        CU_TRY(h, cudaMallocHost((void**)&h->h_ipiv, (size_t)n * sizeof(long long)));
+        h->cap_hipiv = n;
+    }
+    h->cap_meta = n;
+    return 0;
+}
+
 static int ensure_capacity(b200lu_handle* h, int64_t n) {
+    int rc = ensure_meta(h, n);
+    if (rc) return rc;
     if (n <= h->cap_n) {
-        if (n != h->n) {
+        if (n != h->n || h->ldd != ((n + 15) / 16) * 16) {
             h->n = n;
             h->ldd = ((n + 15) / 16) * 16;
             // keep padding rows finite for the 16-byte chunk loads
@@ -411,11 +426,10 @@ static int ensure_capacity(b200lu_handle* h, int64_t n) {
     CU_TRY(h, cudaStreamSynchronize(h->s_main));
     free_dev(h->dA);
     free_dev(h->dA64);
-    free_dev(h->d_ipiv);
-    free_dev(h->d_perm);
-    free_dev(h->d_plans);
     free_dev(h->d_dinvL);
     free_dev(h->d_dinvU);
+    free_dev(h->d_wL);
+    free_dev(h->d_wU);
     free_dev(h->d_r);
     free_dev(h->d_r32);
     h->n = n;
@@ -429,20 +443,15 @@ static int ensure_capacity(b200lu_handle* h, int64_t n) {
         CU_TRY(h, cudaMalloc((void**)&h->d_r, (size_t)n * 8));
         CU_TRY(h, cudaMalloc((void**)&h->d_r32, (size_t)n * 4));
     }
-    CU_TRY(h, cudaMalloc((void**)&h->d_ipiv, (size_t)n * sizeof(int)));
-    CU_TRY(h, cudaMalloc((void**)&h->d_perm, (size_t)n * sizeof(int)));
-    h->cap_plans = cdiv(n, 16) + 1;
-    CU_TRY(h, cudaMalloc((void**)&h->d_plans, (size_t)h->cap_plans * sizeof(LaswpPlan)));
     const int nblk = cdiv(n, TRSV_TB);
     CU_TRY(h, cudaMalloc(&h->d_dinvL, (size_t)nblk * TRSV_TB * TRSV_TB * es));
     CU_TRY(h, cudaMalloc(&h->d_dinvU, (size_t)nblk * TRSV_TB * TRSV_TB * es));
+    CU_TRY(h, cudaMalloc(&h->d_wL, (size_t)nblk * TRSV_TB * TRSV_TB * es));
+    CU_TRY(h, cudaMalloc(&h->d_wU, (size_t)nblk * TRSV_TB * TRSV_TB * es));
     free_dev(h->d_tflags);
+    free_dev(h->d_tticket);
     h->cap_tgroups = 0;
-    if (n > h->cap_hipiv) {
-        if (h->h_ipiv) cudaFreeHost(h->h_ipiv);
-        CU_TRY(h, cudaMallocHost((void**)&h->h_ipiv, (size_t)n * sizeof(long long)));
-        h->cap_hipiv = n;
-    }
+    h->cap_tflag_bytes = 0;
     h->cap_rhs = 0;
     free_dev(h->d_B);
     free_dev(h->d_X);
@@ -460,24 +469,32 @@ static int ensure_rhs(b200lu_handle* h, int64_t nrhs) {
     return 0;
 }
 
-static int ensure_trsv_groups(b200lu_handle* h, int groups) {
-    if (groups <= h->cap_tgroups) return 0;
+static int ensure_trsv_groups(b200lu_handle* h, int groups, int NR) {
+    // LL packet buffer: [groups][nblk*64 rows][NR][2 words] x 8 bytes (sized for FP64)
+    const int nblk = cdiv(h->cap_n, TRSV_TB);
+    const size_t need = (size_t)groups * nblk * TRSV_TB * NR * 2 * sizeof(unsigned long long);
+    if (need <= h->cap_tflag_bytes && groups <= h->cap_tgroups) return 0;
     CU_TRY(h, cudaStreamSynchronize(h->s_main));
     free_dev(h->d_tflags);
     free_dev(h->d_tticket);
-    const int nblk = cdiv(h->cap_n, TRSV_TB);
-    CU_TRY(h, cudaMalloc((void**)&h->d_tflags, (size_t)groups * nblk * sizeof(int)));
-    CU_TRY(h, cudaMemset(h->d_tflags, 0, (size_t)groups * nblk * sizeof(int)));
-    CU_TRY(h, cudaMalloc((void**)&h->d_tticket, (size_t)groups * sizeof(int)));
-    h->cap_tgroups = groups;
+    const size_t bytes = std::max(need, h->cap_tflag_bytes);
+    const int g = std::max(groups, h->cap_tgroups);
+    CU_TRY(h, cudaMalloc((void**)&h->d_tflags, bytes));
+    CU_TRY(h, cudaMemset(h->d_tflags, 0, bytes));
+    CU_TRY(h, cudaMalloc((void**)&h->d_tticket, (size_t)g * sizeof(int)));
+    CU_TRY(h, cudaMemset(h->d_tticket, 0, (size_t)g * sizeof(int)));
+    h->cap_tflag_bytes = bytes;
+    h->cap_tgroups = g;
     h->trsv_epoch = 0;
     return 0;
 }
 
 // ------------------------------------------------------------------- getrs --
+// X = U \ (L \ (P B)).  B must not alias X here (the lower sweep gathers B rows
+// through the permutation); getrs_device stages an aliased right-hand side.
 template <typename T>
-static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, T* X, int64_t ldx,
-                       int nrhs) {
+static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T* B, int64_t ldb,
+                       T* X, int64_t ldx, int nrhs) {
     cudaStream_t st = h->s_main;
     const int nblk = cdiv(n, TRSV_TB);
     if (!h->solve_ready) {
@@ -492,30 +509,34 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, T* X, i
         LAUNCH_CHECK(h);
         trtri_diag_kernel<T><<<nblk, TRSV_TB, tsm, st>>>(A, lda, n, (T*)h->d_dinvU, 1);
         LAUNCH_CHECK(h);
+        trsv_coupling_kernel<T><<<nblk, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvL, (T*)h->d_wL, 0, nblk);
+        LAUNCH_CHECK(h);
+        trsv_coupling_kernel<T><<<nblk, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvU, (T*)h->d_wU, 1, nblk);
+        LAUNCH_CHECK(h);
         h->solve_ready = true;
     }
     const int tile = (int)h->opt[B200LU_OPT_SOLVE_NRHS_TILE];
     const int NR = nrhs == 1 ? 1 : (tile >= 8 ? 8 : (tile >= 4 ? 4 : 1));
     const int groups = cdiv(nrhs, NR);
-    int rc = ensure_trsv_groups(h, groups);
+    int rc = ensure_trsv_groups(h, groups, NR);
     if (rc) return rc;
-    TrsvSync sy{h->d_tflags, h->d_tticket, h->d_deverr};
+    TrsvSync sy{(unsigned long long*)h->d_tflags, h->d_tticket, h->d_deverr};
     dim3 grid(nblk, groups);
     for (int upper = 0; upper < 2; ++upper) {
-        if (h->trsv_epoch > (1 << 30)) {
-            CU_TRY(h, cudaMemsetAsync(h->d_tflags, 0, (size_t)h->cap_tgroups * cdiv(h->cap_n, TRSV_TB) * sizeof(int), st));
+        if (h->trsv_epoch > (1u << 30)) {
+            CU_TRY(h, cudaMemsetAsync(h->d_tflags, 0, h->cap_tflag_bytes, st));
             h->trsv_epoch = 0;
         }
-        const int epoch = ++h->trsv_epoch;
-        CU_TRY(h, cudaMemsetAsync(h->d_tticket, 0, (size_t)groups * sizeof(int), st));
+        const unsigned epoch = ++h->trsv_epoch;
         const T* dinv = (const T*)(upper ? h->d_dinvU : h->d_dinvL);
-#define TRSV_LAUNCH(NRV)                                                                      \
-    if (upper)                                                                                \
-        trsv_block_kernel<T, NRV, true><<<grid, 256, 0, st>>>(A, lda, n, dinv, X, ldx, nrhs, sy, \
-                                                              epoch, 0, nblk);               \
-    else                                                                                      \
-        trsv_block_kernel<T, NRV, false><<<grid, 256, 0, st>>>(A, lda, n, dinv, X, ldx, nrhs, sy, \
-                                                               epoch, 0, nblk);
+        const T* wmat = (const T*)(upper ? h->d_wU : h->d_wL);
+#define TRSV_LAUNCH(NRV)                                                                          \
+    if (upper)                                                                                    \
+        trsv_block_kernel<T, NRV, true><<<grid, 256, 0, st>>>(A, lda, n, dinv, wmat, nullptr, 0, nullptr, \
+                                                              X, ldx, nrhs, sy, epoch, nblk);     \
+    else                                                                                          \
+        trsv_block_kernel<T, NRV, false><<<grid, 256, 0, st>>>(A, lda, n, dinv, wmat, B, ldb, h->d_perm, \
+                                                               X, ldx, nrhs, sy, epoch, nblk);
         if (NR == 1) { TRSV_LAUNCH(1) }
         else if (NR == 4) { TRSV_LAUNCH(4) }
         else { TRSV_LAUNCH(8) }
@@ -534,7 +555,7 @@ static int getrs_device(b200lu_handle* h, const T* B, int64_t ldb, T* X, int64_t
     const T* src = B;
     int64_t lds = ldb;
     if ((const void*)B == (const void*)X) {
-        // in-place permutation is not a gather: stage through d_B
+        // the row gather through the permutation is not an in-place operation: stage B
         int rc = ensure_rhs(h, nrhs);
         if (rc) return rc;
         CU_TRY(h, cudaMemcpy2DAsync(h->d_B, (size_t)n * sizeof(T), B, (size_t)ldb * sizeof(T),
@@ -542,10 +563,7 @@ static int getrs_device(b200lu_handle* h, const T* B, int64_t ldb, T* X, int64_t
         src = (const T*)h->d_B;
         lds = n;
     }
-    dim3 pg(cdiv(n, 256), nrhs);
-    permute_rows_kernel<T><<<pg, 256, 0, st>>>(src, lds, X, ldx, h->d_perm, n, nrhs, 0);
-    LAUNCH_CHECK(h);
-    return trsv_sweeps<T>(h, (const T*)h->dA, h->ldd, n, X, ldx, nrhs);
+    return trsv_sweeps<T>(h, (const T*)h->dA, h->ldd, n, src, lds, X, ldx, nrhs);
 }
 
 // MIXED: FP32 factors + FP64 residual refinement, one right-hand side at a time.
@@ -637,6 +655,7 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     h->opt[B200LU_OPT_PANEL_CTAS] = PANEL_GMAX;
     h->opt[B200LU_OPT_SOLVE_NRHS_TILE] = 8;
     h->opt[B200LU_OPT_PROFILE] = 0;
+    h->opt[B200LU_OPT_PANEL_RPT] = 0;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) == cudaSuccess;
@@ -645,9 +664,8 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     ok = ok && cudaEventCreate(&h->ev_c) == cudaSuccess && cudaEventCreate(&h->ev_d) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_next, cudaEventDisableTiming) == cudaSuccess;
-    const PanelSyncLayout L = panel_sync_layout();
-    ok = ok && cudaMalloc(&h->d_panelsync, L.total) == cudaSuccess;
-    ok = ok && cudaMemset(h->d_panelsync, 0, L.total) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_panelsync, sizeof(PanelMail)) == cudaSuccess;
+    ok = ok && cudaMemset(h->d_panelsync, 0, sizeof(PanelMail)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_info, 64) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&h->d_deverr, 64) == cudaSuccess;
     ok = ok && cudaMemset(h->d_deverr, 0, 64) == cudaSuccess;
@@ -669,7 +687,7 @@ void b200lu_destroy(b200lu_handle* h) {
     if (h->s_panel) cudaStreamSynchronize(h->s_panel);
     free_dev(h->dA); free_dev(h->dA64); free_dev(h->d_ipiv); free_dev(h->d_perm);
     free_dev(h->d_info); free_dev(h->d_deverr); free_dev(h->d_plans); free_dev(h->d_panelsync);
-    free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_tflags); free_dev(h->d_tticket);
+    free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_wL); free_dev(h->d_wU); free_dev(h->d_tflags); free_dev(h->d_tticket);
     free_dev(h->d_B); free_dev(h->d_X); free_dev(h->d_r); free_dev(h->d_r32); free_dev(h->d_scal);
     free_dev(h->dB_LU); free_dev(h->dB_ipiv); free_dev(h->dB_info); free_dev(h->dB_in);
     free_dev(h->dB_rhs); free_dev(h->dB_x);
@@ -759,6 +777,7 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     }
     if (option == B200LU_OPT_PANEL_CTAS && (value < 1 || value > PANEL_GMAX)) return -3;
     if (option == B200LU_OPT_REFINE_MAXIT && value < 0) return -3;
+    if (option == B200LU_OPT_PANEL_RPT && (value < 0 || value > 2)) return -3;
     h->opt[option] = value;
     return 0;
 }
@@ -1264,24 +1283,7 @@ int b200lu_fill_uniform_device(b200lu_handle* h, void* A_dev, int64_t lda, int64
     return 0;
 }
 
-// ------------------------------------------------------------- distributed --
-// (implemented in a later milestone; the symbols exist so the ABI is stable)
-int b200lu_comm_unique_id(void* id128) { (void)id128; return 5; }
-int b200lu_comm_init(b200lu_handle* h, const void* id128, int rank, int nranks) {
-    (void)id128; (void)rank; (void)nranks;
-    return set_err(h, 5, "distributed mode not built");
-}
-int b200lu_dist_local_cols(const b200lu_handle* h, int64_t n, int64_t* ncols_local) {
-    (void)h; (void)n; (void)ncols_local;
-    return 5;
-}
-int b200lu_factor_dist(b200lu_handle* h, int64_t n, const void* Aloc_dev, int64_t lda, int64_t* info) {
-    (void)n; (void)Aloc_dev; (void)lda; (void)info;
-    return set_err(h, 5, "distributed mode not built");
-}
-int b200lu_solve_dist(b200lu_handle* h, int64_t nrhs, const void* B_dev, int64_t ldb, void* X_dev, int64_t ldx) {
-    (void)nrhs; (void)B_dev; (void)ldb; (void)X_dev; (void)ldx;
-    return set_err(h, 5, "distributed mode not built");
-}
-
 }  // extern "C"
+
+#include "dist.inc"
+

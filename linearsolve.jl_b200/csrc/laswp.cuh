@@ -19,67 +19,49 @@ struct LaswpPlan {
     int src[2 * LASWP_MAXSW];      // original row whose content lands there
 };
 
-// One warp. ipiv: global 0-based rows; interchanges k0 .. k0+nsw-1.
-__global__ void laswp_plan_kernel(const int* __restrict__ ipiv, int k0, int nsw,
-                                  LaswpPlan* __restrict__ plan) {
-    __shared__ int top[LASWP_MAXSW];
-    __shared__ int ext_row[LASWP_MAXSW];
-    __shared__ int ext_cont[LASWP_MAXSW];
+// ipiv: global 0-based rows; interchanges k0 .. k0+nsw-1 (nsw <= LASWP_MAXSW).
+// One CTA of 2*LASWP_MAXSW threads.  Thread t < nsw owns top position k0+t;
+// thread LASWP_MAXSW+t owns the outside pivot row ipiv[k0+t] (first occurrence
+// only).  Each thread finds where the content that ends up at ITS position
+// came from by walking the interchange sequence backwards — positions are
+// independent, so the jb sequential swaps cost O(jb) steps in parallel instead
+// of a serial simulation.
+__global__ void __launch_bounds__(2 * LASWP_MAXSW)
+    laswp_plan_kernel(const int* __restrict__ ipiv, int k0, int nsw, LaswpPlan* __restrict__ plan) {
     __shared__ int s_piv[LASWP_MAXSW];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < nsw; i += 32) {
-        top[i] = k0 + i;
-        s_piv[i] = ipiv[k0 + i];
-    }
-    __syncwarp();
-    int ne = 0;
-    for (int k = 0; k < nsw; ++k) {
-        const int pv = s_piv[k];
-        if (pv == k0 + k) continue;
-        if (pv < k0 + nsw) {
-            if (lane == 0) {
-                int t = top[k];
-                top[k] = top[pv - k0];
-                top[pv - k0] = t;
-            }
-        } else {
-            int found = -1;
-            for (int e = lane; e < ne; e += 32)
-                if (ext_row[e] == pv) found = e;
-            unsigned msk = __ballot_sync(0xffffffffu, found >= 0);
-            int e;
-            if (msk) {
-                e = __shfl_sync(0xffffffffu, found, __ffs(msk) - 1);
-            } else {
-                e = ne++;
-                if (lane == 0) { ext_row[e] = pv; ext_cont[e] = pv; }
-            }
-            __syncwarp();
-            if (lane == 0) {
-                int t = top[k];
-                top[k] = ext_cont[e];
-                ext_cont[e] = t;
+    __shared__ int s_cnt;
+    const int t = threadIdx.x;
+    if (t < nsw) s_piv[t] = ipiv[k0 + t];
+    if (t == 0) s_cnt = 0;
+    __syncthreads();
+    int pos = -1;
+    if (t < LASWP_MAXSW) {
+        if (t < nsw) pos = k0 + t;
+    } else {
+        const int k = t - LASWP_MAXSW;
+        if (k < nsw) {
+            const int pv = s_piv[k];
+            if (pv >= k0 + nsw) {
+                pos = pv;
+                for (int kk = 0; kk < k; ++kk)
+                    if (s_piv[kk] == pv) { pos = -1; break; }  // an earlier swap already lists this row
             }
         }
-        __syncwarp();
     }
-    // compact: only entries that actually move
-    int cnt = 0;
-    for (int base = 0; base < nsw + ne; base += 32) {
-        const int i = base + lane;
-        int d = -1, s = -1;
-        if (i < nsw) { d = k0 + i; s = top[i]; }
-        else if (i < nsw + ne) { d = ext_row[i - nsw]; s = ext_cont[i - nsw]; }
-        const bool mv = (i < nsw + ne) && (d != s);
-        unsigned msk = __ballot_sync(0xffffffffu, mv);
-        if (mv) {
-            int pos = cnt + __popc(msk & ((1u << lane) - 1));
-            plan->dst[pos] = d;
-            plan->src[pos] = s;
+    if (pos >= 0) {
+        int y = pos;
+        for (int k = nsw - 1; k >= 0; --k) {
+            const int a = k0 + k, b = s_piv[k];
+            y = (y == a) ? b : ((y == b) ? a : y);
         }
-        cnt += __popc(msk);
+        if (y != pos) {
+            const int slot = atomicAdd(&s_cnt, 1);
+            plan->dst[slot] = pos;
+            plan->src[slot] = y;
+        }
     }
-    if (lane == 0) plan->n_tot = cnt;
+    __syncthreads();
+    if (t == 0) plan->n_tot = s_cnt;
 }
 
 // Columns [c0, c1) of A get the planned row gather. Each CTA walks column

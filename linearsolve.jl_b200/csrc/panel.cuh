@@ -8,14 +8,15 @@
 //
 // B200 mapping: the (m x W) block lives in REGISTERS for the whole kernel: thread
 // t of CTA c owns RPT rows (all W columns of each).  Per column:
-//   1. warp-shuffle arg-max (lowest index on ties) -> CTA candidate;
+//   1. redux.sync arg-max (lowest index on ties) -> CTA candidate;
 //   2. the candidate (|value|, row index, the whole candidate row) is written to an
 //      L2-resident mailbox as 64-bit {data32, flag32} packets ("LL" style: the
 //      flag travels with the data, so there is NO fence and NO separate flag);
-//   3. every CTA gathers all G candidate messages (one L2 round trip, all
-//      threads polling their own packets), warp 0 reduces them and stages the
-//      winning row + the current top row in shared memory;
-//   4. swap (pure register moves) + scale + rank-1 update.
+//   3. every warp of every CTA reads the G candidate headers and reduces them on
+//      its own (no barrier), then one thread per packet fetches the winning row
+//      and the current top row into shared memory;
+//   4. swap (pure register moves) + scale + rank-1 update, fused with a register
+//      rotation that keeps the column loop compact (not unrolled).
 // Mailboxes are double-buffered by column parity; flags are a monotone epoch, so
 // nothing is ever reset between columns or launches.
 // An extra "swapper" CTA follows the published pivots and applies each row
@@ -29,13 +30,15 @@ namespace b200lu {
 
 constexpr int PANEL_GMAX = 128;  // max CTAs cooperating on one base panel
 constexpr int PANEL_WMAX = 32;   // max base width
-// message words (32-bit): |val| (2) + idx (1) + row (2*W)  [float uses half of the value words]
-constexpr int PANEL_MSG_WORDS = 3 + 2 * PANEL_WMAX;  // 67
-constexpr int PANEL_TOP_WORDS = 2 * PANEL_WMAX;
-
+// Mailbox (all 64-bit {data32, flag32} packets, double-buffered by column parity):
+//   hdr[par][cta][0..3] : candidate |value| (1 or 2 words) and row index
+//   row[par][cta][..]   : the candidate row (W values)
+//   top[par][..]        : the current top row (from CTA 0)
+//   piv[j]              : the chosen pivot row of column j (for the swapper CTA)
 struct PanelMail {
-    unsigned long long msg[2][PANEL_GMAX][PANEL_MSG_WORDS + 1];
-    unsigned long long top[2][PANEL_TOP_WORDS];
+    unsigned long long hdr[2][PANEL_GMAX][4];
+    unsigned long long row[2][PANEL_GMAX][2 * PANEL_WMAX];
+    unsigned long long top[2][2 * PANEL_WMAX];
     unsigned long long piv[PANEL_WMAX];
 };
 
@@ -57,11 +60,11 @@ struct PanelArgs {
 
 __device__ __forceinline__ void ll_store(unsigned long long* p, unsigned data, unsigned flag) {
     const unsigned long long v = ((unsigned long long)flag << 32) | data;
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ll_load(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 // spin until the packet carries `want`; returns false on watchdog timeout
@@ -95,18 +98,41 @@ template <> struct Words<float> {
     __device__ static float join(const unsigned* w) { return __uint_as_float(w[0]); }
 };
 
+// Warp arg-max of non-negative values with lowest-index tie-break, on the redux unit
+// (3 REDUX for double, 2 for float, instead of 5 dependent shuffle rounds).
+// Lanes without a candidate pass v = 0, idx = INT_MAX.  Returns the winning
+// (v, idx) in every lane and the winning lane in `wl` (undefined value if none).
+__device__ __forceinline__ void warp_argmax(double& v, int& idx, int& wl) {
+    const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    const bool ismax = (hi == mhi) && (lo == mlo);
+    const int midx = __reduce_min_sync(0xffffffffu, ismax ? idx : INT_MAX);
+    wl = __ffs(__ballot_sync(0xffffffffu, ismax && idx == midx)) - 1;
+    v = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+    idx = midx;
+}
+__device__ __forceinline__ void warp_argmax(float& v, int& idx, int& wl) {
+    const unsigned key = __float_as_uint(v);
+    const unsigned mk = __reduce_max_sync(0xffffffffu, key);
+    const bool ismax = key == mk;
+    const int midx = __reduce_min_sync(0xffffffffu, ismax ? idx : INT_MAX);
+    wl = __ffs(__ballot_sync(0xffffffffu, ismax && idx == midx)) - 1;
+    v = __uint_as_float(mk);
+    idx = midx;
+}
+
 template <typename T, int W, int RPT, int NT>
 __global__ void __launch_bounds__(NT, 1) panel_base_kernel(PanelArgs<T> p) {
     constexpr int NW = NT / 32;
     constexpr int WN = Words<T>::N;
-    constexpr int OFF_IDX = WN;              // message layout: [val WN][idx 1][row W*WN]
-    constexpr int OFF_ROW = WN + 1;
-    constexpr int MSG = OFF_ROW + W * WN;    // words actually used
-    extern __shared__ unsigned s_tab[];      // [G*MSG + W*WN] gathered message words
+    constexpr int ROWW = W * WN;               // 32-bit words of one row
+    static_assert(2 * ROWW <= NT && 32 + ROWW <= NT, "one publishing / fetching thread per packet");
     __shared__ T s_val[NW];
     __shared__ int s_idx[NW];
-    __shared__ __align__(16) T s_prow[PANEL_WMAX];
-    __shared__ __align__(16) T s_trow[PANEL_WMAX];
+    __shared__ __align__(16) unsigned s_stage[4 + 2 * ROWW];  // [hdr 4][row ROWW][top ROWW]
+    __shared__ __align__(16) unsigned s_rows[2 * ROWW];       // fetched [pivot row][top row]
     __shared__ int s_piv;
     __shared__ int s_abort;
 
@@ -163,141 +189,147 @@ __global__ void __launch_bounds__(NT, 1) panel_base_kernel(PanelArgs<T> p) {
         }
     }
     if (tid == 0) s_abort = 0;
-    const int total_words = G * MSG + W * WN;
+    T* stage_row = reinterpret_cast<T*>(&s_stage[4]);
+    T* stage_top = reinterpret_cast<T*>(&s_stage[4 + ROWW]);
+    const T* prow = reinterpret_cast<const T*>(&s_rows[0]);
+    const T* trow = reinterpret_cast<const T*>(&s_rows[ROWW]);
 
+    // The column loop is NOT unrolled (an unrolled body is ~400 KB of SASS and every
+    // column then runs from a cold instruction cache).  To keep all register indices
+    // static, the row registers are ROTATED left by one each column: the current
+    // column always sits at index 0, the finished multiplier re-enters at index W-1,
+    // and after W steps the row is back in natural order.  Every CTA rotates in
+    // lock-step, so staged rows line up across CTAs.
+#pragma unroll 1
+    for (int j = 0; j < wc; ++j) {
+        const int par = j & 1;
+        const unsigned want = p.epoch + j + 1;
+        const int nact = W - j;  // rotated indices [0, nact) are not yet factored columns
+        // 1. local candidate: strict '>' from amax = 0 (NaN never wins), lowest row on ties
+        T best = T(0);
+        int bi = INT_MAX;
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-        if (j < wc) {
-            const int par = j & 1;
-            const unsigned want = p.epoch + j + 1;
-            // 1. local candidate: strict '>' from amax = 0, rows ascending
-            T best = T(0);
-            int bi = INT_MAX;
-#pragma unroll
-            for (int q = 0; q < RPT; ++q) {
-                if (ri[q] >= j && ri[q] < p.m) {
-                    const T v = tabs(a[q][j]);
-                    if (v > best) { best = v; bi = ri[q]; }
-                }
+        for (int q = 0; q < RPT; ++q) {
+            if (ri[q] >= j && ri[q] < p.m) {
+                const T v = tabs(a[q][0]);
+                if (v > best) { best = v; bi = ri[q]; }
             }
+        }
+        int wl;
+        warp_argmax(best, bi, wl);
+        if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+        __syncthreads();
+        T cb = s_val[0];
+        int ci = s_idx[0];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const T ob = shfl_xor(best, off);
-                const int oi = shfl_xor(bi, off);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        for (int w = 1; w < NW; ++w) {
+            const T ob = s_val[w];
+            const int oi = s_idx[w];
+            if (ob > cb || (ob == cb && oi < ci)) { cb = ob; ci = oi; }
+        }
+        // 2. stage the candidate message in shared memory, then one thread per packet
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+            if (ri[q] == ci) {
+#pragma unroll
+                for (int c = 0; c < W; ++c) stage_row[c] = a[q][c];
             }
-            if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
-            __syncthreads();
-            T cb = s_val[0];
-            int ci = s_idx[0];
+            if (ri[q] == j) {  // current top row (CTA 0 only)
 #pragma unroll
-            for (int w = 1; w < NW; ++w) {
-                const T ob = s_val[w];
-                const int oi = s_idx[w];
-                if (ob > cb || (ob == cb && oi < ci)) { cb = ob; ci = oi; }
+                for (int c = 0; c < W; ++c) stage_top[c] = a[q][c];
             }
-            // 2. publish: the candidate's owner writes the whole message as LL packets
-            {
-                unsigned long long* mb = mail->msg[par][cta];
-                const bool nocand = (ci == INT_MAX);
+        }
+        if (tid == 0) {
+            *reinterpret_cast<T*>(&s_stage[0]) = cb;
+            s_stage[WN] = (unsigned)ci;
+        }
+        __syncthreads();
+        if (tid <= WN) ll_store(&mail->hdr[par][cta][tid], s_stage[tid], want);
+        else if (tid >= 32 && tid < 32 + ROWW) ll_store(&mail->row[par][cta][tid - 32], s_stage[4 + tid - 32], want);
+        if (cta == 0 && tid >= NT - ROWW) ll_store(&mail->top[par][tid - (NT - ROWW)], s_stage[4 + ROWW + tid - (NT - ROWW)], want);
+        // 3a. every warp reads all G candidate headers on its own and picks the winner
+        T gv = T(0);
+        int gi = INT_MAX, gc = 0;
+        bool dead = false;
+        for (int c = lane; c < G; c += 32) {
+            unsigned w[WN + 1];
+            unsigned long long v[WN + 1];
 #pragma unroll
-                for (int q = 0; q < RPT; ++q) {
-                    const bool writer = nocand ? (q == 0 && tid == 0) : (ri[q] == ci);
-                    if (writer) {
-                        unsigned w[WN];
-                        Words<T>::split(cb, w);
+            for (int x = 0; x <= WN; ++x) v[x] = ll_load(&mail->hdr[par][c][x]);
 #pragma unroll
-                        for (int x = 0; x < WN; ++x) ll_store(mb + x, w[x], want);
-                        ll_store(mb + OFF_IDX, (unsigned)ci, want);
-#pragma unroll
-                        for (int c = 0; c < W; ++c) {
-                            Words<T>::split(nocand ? T(0) : a[q][c], w);
-#pragma unroll
-                            for (int x = 0; x < WN; ++x) ll_store(mb + OFF_ROW + c * WN + x, w[x], want);
-                        }
-                    }
-                    if (ri[q] == j) {  // current top row (CTA 0 only)
-                        unsigned w[WN];
-#pragma unroll
-                        for (int c = 0; c < W; ++c) {
-                            Words<T>::split(a[q][c], w);
-#pragma unroll
-                            for (int x = 0; x < WN; ++x) ll_store(&mail->top[par][c * WN + x], w[x], want);
-                        }
-                    }
+            for (int x = 0; x <= WN; ++x) {
+                if ((unsigned)(v[x] >> 32) != want) {
+                    const long long t0 = clock64();
+                    do {
+                        v[x] = ll_load(&mail->hdr[par][c][x]);
+                        if (clock64() - t0 > kSpinTimeoutCycles) { dead = true; break; }
+                    } while ((unsigned)(v[x] >> 32) != want);
                 }
+                w[x] = (unsigned)v[x];
             }
-            // 3. gather all messages (every thread polls its own packets)
-            {
-                bool dead = false;
-                for (int idx = tid; idx < total_words; idx += NT) {
-                    const unsigned long long* src;
-                    if (idx < G * MSG) {
-                        const int c = idx / MSG;
-                        src = &mail->msg[par][c][idx - c * MSG];
-                    } else {
-                        src = &mail->top[par][idx - G * MSG];
-                    }
-                    unsigned d = 0;
-                    if (!ll_wait(src, want, d)) dead = true;
-                    s_tab[idx] = d;
-                }
-                if (dead) { atomicExch(p.deverr, DEV_ERR_PANEL_TIMEOUT); s_abort = 1; }
+            const T cv = Words<T>::join(w);
+            const int cidx = (int)w[WN];
+            if (cv > gv || (cv == gv && cidx < gi)) { gv = cv; gi = cidx; gc = c; }
+        }
+        {
+            int gl;
+            if (!(gv > T(0))) gi = INT_MAX;
+            warp_argmax(gv, gi, gl);
+            gc = __shfl_sync(0xffffffffu, gc, gl < 0 ? 0 : gl);
+        }
+        const bool none = !(gv > T(0));  // all-zero (or all-NaN) subcolumn: kp = k
+        const int piv = none ? j : gi;
+        // 3b. fetch the winning row and the top row: one packet per thread
+        if (tid < 2 * ROWW) {
+            const unsigned long long* src = (tid < ROWW)
+                ? (none ? &mail->top[par][tid] : &mail->row[par][gc][tid])
+                : &mail->top[par][tid - ROWW];
+            unsigned d = 0;
+            if (!ll_wait(src, want, d)) dead = true;
+            s_rows[tid] = d;
+        }
+        if (dead) { atomicExch(p.deverr, DEV_ERR_PANEL_TIMEOUT); s_abort = 1; }
+        __syncthreads();
+        if (s_abort) return;
+        // 4. swap + scale + rank-1 update fused with the rotation, all in registers
+        const T pv = prow[0];
+        if (cta == 0 && tid == 0) {
+            p.ipiv[p.j0 + j] = p.j0 + piv;
+            ll_store(&mail->piv[j], (unsigned)(p.j0 + piv), want);
+            if (pv == T(0) && *p.info == 0) *p.info = p.j0 + j + 1;
+        }
+        const bool scale = (pv != T(0));
+        const T rinv = T(1) / pv;
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+            if (ri[q] == j) {
+#pragma unroll
+                for (int c = 0; c < W; ++c) a[q][c] = prow[c];
+            } else if (ri[q] == piv) {  // piv != j here
+#pragma unroll
+                for (int c = 0; c < W; ++c) a[q][c] = trow[c];
             }
-            __syncthreads();
-            if (warp == 0) {
-                T gv = T(0);
-                int gi = INT_MAX, gc = -1;
-                for (int c = lane; c < G; c += 32) {
-                    const T v = Words<T>::join(&s_tab[c * MSG]);
-                    const int idx = (int)s_tab[c * MSG + OFF_IDX];
-                    if (v > gv || (v == gv && idx < gi)) { gv = v; gi = idx; gc = c; }
-                }
+            const bool upd = ri[q] > j && ri[q] < p.m;
+            T l = a[q][0];
+            if (upd && scale) l *= rinv;
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const T ob = shfl_xor(gv, off);
-                    const int oi = shfl_xor(gi, off);
-                    const int oc = shfl_xor(gc, off);
-                    if (ob > gv || (ob == gv && oi < gi)) { gv = ob; gi = oi; gc = oc; }
-                }
-                const bool none = !(gv > T(0));  // all-zero (or all-NaN) subcolumn: kp = k
-                if (lane < W) {
-                    const T tr = Words<T>::join(&s_tab[G * MSG + lane * WN]);
-                    const T pr = none ? tr : Words<T>::join(&s_tab[gc * MSG + OFF_ROW + lane * WN]);
-                    s_trow[lane] = tr;
-                    s_prow[lane] = pr;
-                }
-                if (lane == 0) s_piv = none ? j : gi;
+            for (int c = 1; c < W; ++c) {
+                T nv = a[q][c];
+                if (upd && c < nact) nv = tfma(-l, prow[c], nv);
+                a[q][c - 1] = nv;
             }
-            __syncthreads();
-            if (s_abort) return;
-            // 4. swap + scale + rank-1 update, all in registers
-            const int piv = s_piv;
-            const T pv = s_prow[j];
-            if (cta == 0 && tid == 0) {
-                p.ipiv[p.j0 + j] = p.j0 + piv;
-                ll_store(&mail->piv[j], (unsigned)(p.j0 + piv), want);
-                if (pv == T(0) && *p.info == 0) *p.info = p.j0 + j + 1;
-            }
-            const bool scale = (pv != T(0));
-            const T rinv = T(1) / pv;
+            a[q][W - 1] = l;
+        }
+    }
+    // ragged last block: finish the W-step rotation so registers are in natural order
+#pragma unroll 1
+    for (int j = wc; j < W; ++j) {
 #pragma unroll
-            for (int q = 0; q < RPT; ++q) {
-                if (ri[q] == j) {
+        for (int q = 0; q < RPT; ++q) {
+            const T f = a[q][0];
 #pragma unroll
-                    for (int c = 0; c < W; ++c) a[q][c] = s_prow[c];
-                } else if (ri[q] == piv) {  // piv != j here
-#pragma unroll
-                    for (int c = 0; c < W; ++c) a[q][c] = s_trow[c];
-                }
-                if (ri[q] > j && ri[q] < p.m) {
-                    T l = a[q][j];
-                    if (scale) l *= rinv;
-                    a[q][j] = l;
-#pragma unroll
-                    for (int c = j + 1; c < W; ++c) a[q][c] = tfma(-l, s_prow[c], a[q][c]);
-                }
-            }
+            for (int c = 1; c < W; ++c) a[q][c - 1] = a[q][c];
+            a[q][W - 1] = f;
         }
     }
 

@@ -34,18 +34,30 @@ __global__ void __launch_bounds__(NWARP * 32) trsm_lunit_kernel(const T* __restr
             b[r][c] = (row < w && col0 + c < ncols) ? Bp[(long long)(col0 + c) * ldb + row] : T(0);
         }
 
+    // L11 chunk r (32 columns) is prefetched into registers while chunk r-1 is being
+    // consumed, so the global-load latency of the staging never sits on the k-chain.
+    constexpr int NT = NWARP * 32;
+    constexpr int PER = 32 * WMAXR / NT;  // elements of one chunk per thread
+    T pf[PER];
+    auto prefetch = [&](int r) {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int idx = threadIdx.x + u * NT;
+            const int kk = idx / WMAXR;
+            const int row = idx - kk * WMAXR;
+            const int k = r * 32 + kk;
+            pf[u] = (row < w && k < w && row > k) ? Lp[(long long)k * ldl + row] : T(0);
+        }
+    };
+    prefetch(0);
 #pragma unroll
     for (int r = 0; r < RPL; ++r) {
         if (r * 32 < w) {
-            // stage L[:, 32r .. 32r+31] (rows >= 32r) into shared memory
             __syncthreads();
-            for (int idx = threadIdx.x; idx < 32 * WMAXR; idx += NWARP * 32) {
-                const int kk = idx / WMAXR;
-                const int row = idx - kk * WMAXR;
-                const int k = r * 32 + kk;
-                Ls[idx] = (row < w && k < w && row > k) ? Lp[(long long)k * ldl + row] : T(0);
-            }
+#pragma unroll
+            for (int u = 0; u < PER; ++u) Ls[threadIdx.x + u * NT] = pf[u];
             __syncthreads();
+            if ((r + 1) * 32 < w) prefetch(r + 1);
 #pragma unroll 4
             for (int kk = 0; kk < 32; ++kk) {
                 T xk[CC];

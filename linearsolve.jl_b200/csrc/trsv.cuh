@@ -11,6 +11,7 @@
 // No host round trips, no kernel-per-block launches.
 #pragma once
 #include "common.cuh"
+#include "panel.cuh"  // LL packet helpers
 
 namespace b200lu {
 
@@ -56,23 +57,66 @@ __global__ void __launch_bounds__(TRSV_TB) trtri_diag_kernel(const T* __restrict
     for (int c = 0; c < TRSV_TB; ++c) out[c * TRSV_TB + j] = Ys[j][c];
 }
 
+// Coupling blocks W_r = dinv_r * A[r, r-1] (lower) or dinv_r * A[r, r+1] (upper),
+// 64x64 each, column-major like dinv.  With them the only work a block row has to
+// do AFTER its last dependency arrives is one 64x64 mat-vec:
+//     x_r = dinv_r (b_r - sum_{c not adjacent} A_rc x_c)  -  W_r x_adjacent .
+template <typename T>
+__global__ void __launch_bounds__(256) trsv_coupling_kernel(const T* __restrict__ A, long long lda,
+                                                            int n, const T* __restrict__ dinv,
+                                                            T* __restrict__ wmat, int upper, int nblk) {
+    constexpr int TB = TRSV_TB;
+    __shared__ T s_a[TB][TB + 1];   // A block [k][col]
+    const int r = blockIdx.x;
+    const int c = upper ? r + 1 : r - 1;
+    T* out = wmat + (long long)r * TB * TB;
+    if (c < 0 || c >= nblk) {
+        for (int i = threadIdx.x; i < TB * TB; i += 256) out[i] = T(0);
+        return;
+    }
+    for (int i = threadIdx.x; i < TB * TB; i += 256) {
+        const int row = i % TB, col = i / TB;
+        const int gr = r * TB + row, gc = c * TB + col;
+        s_a[row][col] = (gr < n && gc < n) ? A[(long long)gc * lda + gr] : T(0);
+    }
+    __syncthreads();
+    const T* dp = dinv + (long long)r * TB * TB;   // column-major: element (row, k) at k*TB + row
+    for (int i = threadIdx.x; i < TB * TB; i += 256) {
+        const int row = i % TB, col = i / TB;
+        T acc = T(0);
+#pragma unroll 8
+        for (int k = 0; k < TB; ++k) acc = tfma(dp[k * TB + row], s_a[k][col], acc);
+        out[i] = acc;
+    }
+}
+
 struct TrsvSync {
-    int* flags;    // [nblk] : == epoch when the block's x segment is final
-    int* ticket;   // monotonically increasing
+    unsigned long long* xll;  // LL packets of solved x segments: [grp][npad][NR][words]
+    int* ticket;              // [groups], self-resetting
     int* deverr;
 };
 
-// x (n x nrhs, ldx) holds the right-hand side on entry and the solution on exit.
-// NR right-hand sides per CTA pass (gridDim.y walks the column groups).
+// One triangular sweep.  Lower (UPPER=false): x = L \ rhs with unit L, where
+// rhs = B[perm[i]] when perm != nullptr (row interchanges fused into the load,
+// reference `_naive_lu_ldiv!` pivot loop src/factorization.jl:437-443) else X.
+// Upper: x = U \ X in place.  The solution lands in X (n x nrhs, ldx).
+// NR right-hand sides per CTA (gridDim.y walks the groups of NR columns).
+// Solved 64-row segments travel between CTAs as 64-bit {data32, flag32} LL
+// packets: no fence, no separate flag, one L2 round trip per dependency step.
+// Critical path per block row (after the adjacent segment arrives): one 64x64
+// mat-vec with the precomputed coupling block, a 4-way shared-memory reduce, publish.
 template <typename T, int NR, bool UPPER>
 __global__ void __launch_bounds__(256) trsv_block_kernel(const T* __restrict__ A, long long lda,
                                                          int n, const T* __restrict__ dinv,
-                                                         T* __restrict__ x, long long ldx, int nrhs,
-                                                         TrsvSync sy, int epoch, int ticket_base,
-                                                         int nblk) {
+                                                         const T* __restrict__ wmat,
+                                                         const T* __restrict__ B, long long ldb,
+                                                         const int* __restrict__ perm,
+                                                         T* __restrict__ X, long long ldx, int nrhs,
+                                                         TrsvSync sy, unsigned epoch, int nblk) {
     constexpr int TB = TRSV_TB;
-    __shared__ T s_x[8][NR][16];      // per-warp staging of the x segment it multiplies by
-    __shared__ T s_part[4][NR][TB];   // partial sums per column-quarter
+    constexpr int WN = sizeof(T) / 4;
+    __shared__ __align__(16) T s_x[8][NR][16];   // per-warp staging of the x segment it multiplies by
+    __shared__ T s_part[4][NR][TB];              // partial sums per column-quarter
     __shared__ T s_rhs[NR][TB];
     __shared__ int s_ticket;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -80,28 +124,66 @@ __global__ void __launch_bounds__(256) trsv_block_kernel(const T* __restrict__ A
     const int q = tid >> 6;  // column quarter 0..3 (warps 2q, 2q+1)
     const int grp = blockIdx.y;
     const int r0 = grp * NR;
-    int* flags = sy.flags + (long long)grp * nblk;
+    unsigned long long* xll = sy.xll + (size_t)grp * nblk * TB * NR * WN;
 
-    if (tid == 0) s_ticket = atomicAdd(sy.ticket + grp, 1) - ticket_base;
+    if (tid == 0) {
+        const int t = atomicAdd(sy.ticket + grp, 1);
+        if (t == nblk - 1) sy.ticket[grp] = 0;   // everyone has drawn: re-arm for the next sweep
+        s_ticket = t;
+    }
     __syncthreads();
     const int t = s_ticket;
     const int r = UPPER ? (nblk - 1 - t) : t;
     const int grow = r * TB + row;
     const bool rok = grow < n;
 
-    // diagonal-inverse slice for the final mat-vec: row `row`, columns q*16..q*16+15
-    T dv[16];
+    // right-hand side of my rows (prefetched; only tid < TB uses it)
+    T myb[NR];
+    if (tid < TB) {
+        const int srow = (!UPPER && perm != nullptr && rok) ? perm[grow] : grow;
+#pragma unroll
+        for (int v = 0; v < NR; ++v) {
+            myb[v] = T(0);
+            if (rok && r0 + v < nrhs)
+                myb[v] = (!UPPER && perm != nullptr) ? B[(long long)(r0 + v) * ldb + srow]
+                                                    : X[(long long)(r0 + v) * ldx + grow];
+        }
+    }
+    // slices (row `row`, columns q*16..q*16+15) of the diagonal inverse and the coupling block
+    T dv[16], wv[16];
     {
         const T* dp = dinv + (long long)r * TB * TB + (q * 16) * TB + row;
+        const T* wp = wmat + (long long)r * TB * TB + (q * 16) * TB + row;
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) dv[jj] = dp[jj * TB];
+        for (int jj = 0; jj < 16; ++jj) { dv[jj] = dp[jj * TB]; wv[jj] = wp[jj * TB]; }
     }
 
-    T acc[NR];
-#pragma unroll
-    for (int v = 0; v < NR; ++v) acc[v] = T(0);
+    // gather 16 x-values (x NR x WN words) of block c, quarter q, into this warp's staging
+    bool dead = false;
+    auto gather_x = [&](int c) {
+        const unsigned long long* src = xll + (size_t)(c * TB + q * 16) * NR * WN;
+        unsigned* dstw = reinterpret_cast<unsigned*>(&s_x[warp][0][0]);
+        for (int idx = lane; idx < 16 * NR * WN; idx += 32) {
+            // packet order in xll: [row jj][v][word]; staging order: [v][jj][word]
+            const int jj = idx / (NR * WN);
+            const int rem = idx - jj * (NR * WN);
+            const int v = rem / WN, wd = rem - v * WN;
+            unsigned data = 0;
+            if (!ll_wait(src + idx, epoch, data)) dead = true;
+            dstw[(v * 16 + jj) * WN + wd] = data;
+        }
+        __syncwarp();
+    };
 
-    const int ndep = UPPER ? (nblk - 1 - r) : r;
+    // ---- phase 1 (off the critical path): all dependencies except the adjacent block ----
+    constexpr int NP = NR == 1 ? 4 : (NR <= 4 ? 2 : 1);  // independent FMA chains per right-hand side
+    T acc[NR][NP];
+#pragma unroll
+    for (int v = 0; v < NR; ++v)
+#pragma unroll
+        for (int u = 0; u < NP; ++u) acc[v][u] = T(0);
+    const int ndep = UPPER ? (nblk - 1 - r) : r;   // blocks this row depends on
+    const int nfar = ndep > 0 ? ndep - 1 : 0;      // ... all but the adjacent one
     T an[16];
     auto load_blk = [&](int d, T* dst) {
         const int c = UPPER ? (nblk - 1 - d) : d;
@@ -112,70 +194,72 @@ __global__ void __launch_bounds__(256) trsv_block_kernel(const T* __restrict__ A
             dst[jj] = (rok && gc < n) ? ap[(long long)jj * lda] : T(0);
         }
     };
-    if (ndep > 0) load_blk(0, an);
-    bool dead = false;
-    for (int d = 0; d < ndep; ++d) {
+    if (nfar > 0) load_blk(0, an);
+    for (int d = 0; d < nfar; ++d) {
         T ac[16];
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) ac[jj] = an[jj];
-        if (d + 1 < ndep) load_blk(d + 1, an);
-        const int c = UPPER ? (nblk - 1 - d) : d;
-        if (lane == 0) {
-            long long t0 = clock64();
-            while (ld_acquire(flags + c) != epoch) {
-                if (clock64() - t0 > kSpinTimeoutCycles) { dead = true; break; }
-            }
-        }
-        __syncwarp();
-        if (lane < 16) {
-#pragma unroll
-            for (int v = 0; v < NR; ++v) {
-                const int gc = c * TB + q * 16 + lane;
-                s_x[warp][v][lane] =
-                    (gc < n && r0 + v < nrhs) ? ld_cg(x + (long long)(r0 + v) * ldx + gc) : T(0);
-            }
-        }
-        __syncwarp();
+        if (d + 1 < nfar) load_blk(d + 1, an);
+        gather_x(UPPER ? (nblk - 1 - d) : d);
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj)
 #pragma unroll
-            for (int v = 0; v < NR; ++v) acc[v] = tfma(ac[jj], s_x[warp][v][jj], acc[v]);
+            for (int v = 0; v < NR; ++v) acc[v][jj % NP] = tfma(ac[jj], s_x[warp][v][jj], acc[v][jj % NP]);
         __syncwarp();
     }
-    if (__any_sync(0xffffffffu, dead) && lane == 0) atomicExch(sy.deverr, DEV_ERR_TRSV_TIMEOUT);
-
-#pragma unroll
-    for (int v = 0; v < NR; ++v) s_part[q][v][row] = acc[v];
-    __syncthreads();
-    if (tid < TB) {
-#pragma unroll
-        for (int v = 0; v < NR; ++v) {
-            T b = (rok && r0 + v < nrhs) ? x[(long long)(r0 + v) * ldx + grow] : T(0);
-            b -= (s_part[0][v][row] + s_part[1][v][row]) + (s_part[2][v][row] + s_part[3][v][row]);
-            s_rhs[v][row] = b;
-        }
-    }
-    __syncthreads();
-    // x_r = dinv_r * rhs : thread (row, q) does 16 columns, then reduce over q
 #pragma unroll
     for (int v = 0; v < NR; ++v) {
-        T s = T(0);
+        T sacc = acc[v][0];
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) s = tfma(dv[jj], s_rhs[v][q * 16 + jj], s);
-        s_part[q][v][row] = s;
+        for (int u = 1; u < NP; ++u) sacc += acc[v][u];
+        s_part[q][v][row] = sacc;
     }
     __syncthreads();
     if (tid < TB) {
 #pragma unroll
-        for (int v = 0; v < NR; ++v) {
-            if (rok && r0 + v < nrhs)
-                x[(long long)(r0 + v) * ldx + grow] =
-                    (s_part[0][v][row] + s_part[1][v][row]) + (s_part[2][v][row] + s_part[3][v][row]);
-        }
-        __threadfence();
+        for (int v = 0; v < NR; ++v)
+            s_rhs[v][row] = myb[v] - ((s_part[0][v][row] + s_part[1][v][row]) +
+                                      (s_part[2][v][row] + s_part[3][v][row]));
     }
     __syncthreads();
-    if (tid == 0) st_release(flags + r, epoch);
+    // t = dinv_r * rhs  (partial over my 16 columns; summed over q at the very end)
+    T tq[NR][NP];
+#pragma unroll
+    for (int v = 0; v < NR; ++v) {
+#pragma unroll
+        for (int u = 0; u < NP; ++u) tq[v][u] = T(0);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) tq[v][jj % NP] = tfma(dv[jj], s_rhs[v][q * 16 + jj], tq[v][jj % NP]);
+    }
+    // ---- phase 2 (critical path): x_r = t - W_r * x_adjacent ----
+    if (ndep > 0) {
+        gather_x(UPPER ? r + 1 : r - 1);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj)
+#pragma unroll
+            for (int v = 0; v < NR; ++v) tq[v][jj % NP] = tfma(-wv[jj], s_x[warp][v][jj], tq[v][jj % NP]);
+    }
+    if (__any_sync(0xffffffffu, dead) && lane == 0) atomicExch(sy.deverr, DEV_ERR_TRSV_TIMEOUT);
+#pragma unroll
+    for (int v = 0; v < NR; ++v) {
+        T st = tq[v][0];
+#pragma unroll
+        for (int u = 1; u < NP; ++u) st += tq[v][u];
+        s_part[q][v][row] = st;
+    }
+    __syncthreads();
+    if (tid < TB) {
+        unsigned long long* dst = xll + (size_t)grow * NR * WN;
+#pragma unroll
+        for (int v = 0; v < NR; ++v) {
+            const T xv = (s_part[0][v][row] + s_part[1][v][row]) + (s_part[2][v][row] + s_part[3][v][row]);
+            unsigned w[WN];
+            Words<T>::split(xv, w);
+#pragma unroll
+            for (int x = 0; x < WN; ++x) ll_store(dst + v * WN + x, w[x], epoch);
+            if (rok && r0 + v < nrhs) X[(long long)(r0 + v) * ldx + grow] = xv;
+        }
+    }
 }
 
 // y = b - A x  (FP64 residual for the refinement loop; A n x n column-major).

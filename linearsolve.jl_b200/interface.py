@@ -420,3 +420,30 @@ def defaultalg(A, b, assump: OperatorAssumptions | None = None, *, isopenblas: b
     if usemkl:
         return DefaultLinearSolver(C.MKLLUFactorization)
     return DefaultLinearSolver(C.LUFactorization)
+
+
+# ------------------------------------------------------------- multi-GPU host logic ----
+def shard_batch(batch: int, rank: int, nranks: int):
+    """Contiguous range of the batch index owned by `rank` (independent systems shard
+    with no communication).  Returns (start, stop)."""
+    base, rem = divmod(batch, nranks)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def block_cyclic_columns(n: int, nb: int, rank: int, nranks: int):
+    """1D block-cyclic column distribution used by b200lu_factor_dist: global column
+    block g (width nb, ragged tail) lives on rank g % nranks at local block g // nranks.
+    Returns the global column indices owned by `rank`, in local storage order."""
+    cols = []
+    nblk = -(-n // nb)
+    for g in range(rank, nblk, nranks):
+        cols.extend(range(g * nb, min(n, (g + 1) * nb)))
+    return np.asarray(cols, dtype=np.int64)
+
+
+def reduce_info(infos):
+    """BlockDiagonalFactorization.success = all(issuccess) (ext/LinearSolveBlockDiagonalsExt.jl:121-124)
+    across ranks: the job fails if any shard reported a zero pivot."""
+    infos = np.asarray(infos)
+    return ReturnCode.Success if not np.any(infos != 0) else ReturnCode.Failure
