@@ -46,6 +46,7 @@ def parse():
     p.add_argument("--nb", type=int, default=0)
     p.add_argument("--lookahead", type=int, default=-1)
     p.add_argument("--rpt", type=int, default=-1)
+    p.add_argument("--gemm-cfg", type=int, default=-1)
     return p.parse_args()
 
 
@@ -188,6 +189,8 @@ def main():
         h.set_option(C.OPT_LOOKAHEAD, args.lookahead)
     if args.rpt >= 0:
         h.set_option(C.OPT_PANEL_RPT, args.rpt)
+    if args.gemm_cfg >= 0:
+        h.set_option(C.OPT_GEMM_CFG, args.gemm_cfg)
 
     if args.workload == "batched":
         return bench_batched(args, ls, h, torch, dev, rank, world, barrier, max_over_ranks)

@@ -99,7 +99,8 @@ enum {
     B200LU_OPT_SOLVE_NRHS_TILE = 4, /* right-hand sides per triangular sweep     */
     B200LU_OPT_PROFILE = 5,     /* 1: bracket every trailing GEMM with CUDA events */
     B200LU_OPT_PANEL_RPT = 6,   /* rows per thread in the base panel: 0 auto, 1, 2 */
-    B200LU_OPT_COUNT = 7
+    B200LU_OPT_GEMM_CFG = 7,    /* FP64 trailing-update tile configuration 0..2      */
+    B200LU_OPT_COUNT = 8
 };
 
 /* library/ABI version: major*10000 + minor*100 + patch */

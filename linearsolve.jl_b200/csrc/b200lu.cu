@@ -218,22 +218,33 @@ static int launch_trsm(b200lu_handle* h, cudaStream_t st, const T* Lp, int64_t l
     return 0;
 }
 
-// FP64 Schur update on DMMA
-using DCfg = DgemmCfg<128, 64, 16, 2, 2, 3>;
+// FP64 Schur update on DMMA.  Tile configurations (B200LU_OPT_GEMM_CFG):
+//   0: 128x64 CTA, 4 warps of 64x32, 2 CTAs/SM   (fewest shared-memory reads per DMMA)
+//   1: 128x64 CTA, 8 warps of 32x32, 2 CTAs/SM   (4 warps per scheduler: better latency hiding)
+//   2: 128x128 CTA, 8 warps of 64x32, 1 CTA/SM   (half the L2->smem traffic per flop)
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB>
+static int launch_dgemm_cfg(b200lu_handle* h, cudaStream_t st, int M, int N, int K, const double* A,
+                            int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc) {
+    using Cfg = DgemmCfg<BM, BN, 16, WM, WN, STAGES>;
+    auto kern = dgemm_sub_kernel<BM, BN, 16, WM, WN, STAGES, MINB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    const int tm = cdiv(M, BM), tn = cdiv(N, BN);
+    kern<<<tm * tn, Cfg::NT, Cfg::SMEM, st>>>(M, N, K, A, lda, B, ldb, C, ldc, tm, tn, 16);
+    LAUNCH_CHECK(h);
+    return 0;
+}
 static int launch_gemm(b200lu_handle* h, cudaStream_t st, int M, int N, int K, const double* A,
                        int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    auto kern = dgemm_sub_kernel<128, 64, 16, 2, 2, 3, 2>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)DCfg::SMEM));
-        attr_set = true;
+    switch ((int)h->opt[B200LU_OPT_GEMM_CFG]) {
+        case 1: return launch_dgemm_cfg<128, 64, 4, 2, 3, 2>(h, st, M, N, K, A, lda, B, ldb, C, ldc);
+        case 2: return launch_dgemm_cfg<128, 128, 2, 4, 4, 1>(h, st, M, N, K, A, lda, B, ldb, C, ldc);
+        default: return launch_dgemm_cfg<128, 64, 2, 2, 3, 2>(h, st, M, N, K, A, lda, B, ldb, C, ldc);
     }
-    const int tm = cdiv(M, 128), tn = cdiv(N, 64);
-    kern<<<tm * tn, DCfg::NT, DCfg::SMEM, st>>>(M, N, K, A, lda, B, ldb, C, ldc, tm, tn, 16);
-    LAUNCH_CHECK(h);
-    return 0;
 }
 static int launch_gemm(b200lu_handle* h, cudaStream_t st, int M, int N, int K, const float* A,
                        int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc) {
@@ -521,7 +532,7 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T
     int rc = ensure_trsv_groups(h, groups, NR);
     if (rc) return rc;
     TrsvSync sy{(unsigned long long*)h->d_tflags, h->d_tticket, h->d_deverr};
-    dim3 grid(nblk, groups);
+    dim3 grid(nblk * groups);
     for (int upper = 0; upper < 2; ++upper) {
         if (h->trsv_epoch > (1u << 30)) {
             CU_TRY(h, cudaMemsetAsync(h->d_tflags, 0, h->cap_tflag_bytes, st));
@@ -656,6 +667,7 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     h->opt[B200LU_OPT_SOLVE_NRHS_TILE] = 8;
     h->opt[B200LU_OPT_PROFILE] = 0;
     h->opt[B200LU_OPT_PANEL_RPT] = 0;
+    h->opt[B200LU_OPT_GEMM_CFG] = 0;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) == cudaSuccess;
@@ -778,6 +790,7 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_PANEL_CTAS && (value < 1 || value > PANEL_GMAX)) return -3;
     if (option == B200LU_OPT_REFINE_MAXIT && value < 0) return -3;
     if (option == B200LU_OPT_PANEL_RPT && (value < 0 || value > 2)) return -3;
+    if (option == B200LU_OPT_GEMM_CFG && (value < 0 || value > 2)) return -3;
     h->opt[option] = value;
     return 0;
 }

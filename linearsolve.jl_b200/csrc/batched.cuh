@@ -10,6 +10,7 @@
 // memory, the pivot search is a warp-shuffle arg-max (lowest position on ties).
 #pragma once
 #include "common.cuh"
+#include "panel.cuh"  // warp_argmax
 #include <limits.h>
 
 namespace b200lu {
@@ -21,10 +22,12 @@ __global__ void __launch_bounds__(batched_threads(NMAX)) getrf_batched_kernel(
     const T* __restrict__ A, long long lda, long long strideA, T* __restrict__ LU,
     long long ldlu, long long strideLU, int* __restrict__ ipiv, int* __restrict__ info, int n) {
     constexpr int NW = (NMAX + 31) / 32;  // blockDim.x == max(32, NMAX): lanes >= NMAX are padding rows
-    __shared__ T s_row[NMAX];
-    __shared__ T s_val[NW];
-    __shared__ int s_pos[NW];
-    __shared__ int s_thr[NW];
+    constexpr int NPAD = NMAX < 2 ? 2 : NMAX;
+    // double-buffered by step parity so one barrier per exchange suffices
+    __shared__ __align__(16) T s_row[2][NPAD];
+    __shared__ T s_val[2][NW];
+    __shared__ int s_pos[2][NW];
+    __shared__ int s_thr[2][NW];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long sys = blockIdx.x;
     const T* Ab = A + sys * strideA;
@@ -40,28 +43,26 @@ __global__ void __launch_bounds__(batched_threads(NMAX)) getrf_batched_kernel(
 #pragma unroll
     for (int k = 0; k < NMAX; ++k) {
         if (k < n) {
+            const int par = k & 1;
+            // pivot search: |a| max over the rows not yet used, lowest position on ties
             T best = T(0);
-            int bp = INT_MAX, bt = -1;
+            int bp = INT_MAX;
             if (!done && t < n) {
-                T v = tabs(a[k]);
-                if (v > best) { best = v; bp = pos; bt = t; }
+                const T v = tabs(a[k]);
+                if (v > best) { best = v; bp = pos; }
             }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                T ob = shfl_xor(best, off);
-                int op = shfl_xor(bp, off);
-                int ot = shfl_xor(bt, off);
-                if (ob > best || (ob == best && op < bp)) { best = ob; bp = op; bt = ot; }
-            }
+            int wl;
+            warp_argmax(best, bp, wl);
+            int bt = warp * 32 + wl;   // thread holding the warp's winner (unused when none)
             if (NW > 1) {
-                if (lane == 0) { s_val[warp] = best; s_pos[warp] = bp; s_thr[warp] = bt; }
+                if (lane == 0) { s_val[par][warp] = best; s_pos[par][warp] = bp; s_thr[par][warp] = bt; }
                 __syncthreads();
-                best = s_val[0]; bp = s_pos[0]; bt = s_thr[0];
+                best = s_val[par][0]; bp = s_pos[par][0]; bt = s_thr[par][0];
 #pragma unroll
                 for (int w = 1; w < NW; ++w) {
-                    T ob = s_val[w];
-                    int op = s_pos[w];
-                    if (ob > best || (ob == best && op < bp)) { best = ob; bp = op; bt = s_thr[w]; }
+                    const T ob = s_val[par][w];
+                    const int op = s_pos[par][w];
+                    if (ob > best || (ob == best && op < bp)) { best = ob; bp = op; bt = s_thr[par][w]; }
                 }
             }
             // all-zero / all-NaN subcolumn: kp = k, the row at position k is the "pivot" row
@@ -69,10 +70,10 @@ __global__ void __launch_bounds__(batched_threads(NMAX)) getrf_batched_kernel(
             const bool i_am_piv = none ? (pos == k && !done) : (t == bt);
             if (i_am_piv) {
 #pragma unroll
-                for (int c = k; c < NMAX; ++c) s_row[c] = a[c];
+                for (int c = k; c < NMAX; ++c) s_row[par][c] = a[c];
             }
             __syncthreads();
-            const T pv = s_row[k];
+            const T pv = s_row[par][k];
             const int ppos = none ? k : bp;
             if (i_am_piv) {
                 // this row lands at position k; whoever sat at k takes my old position
@@ -88,22 +89,21 @@ __global__ void __launch_bounds__(batched_threads(NMAX)) getrf_batched_kernel(
                 if (pv != T(0)) l *= (T(1) / pv);
                 a[k] = l;
 #pragma unroll
-                for (int c = k + 1; c < NMAX; ++c) a[c] = tfma(-l, s_row[c], a[c]);
+                for (int c = k + 1; c < NMAX; ++c) a[c] = tfma(-l, s_row[par][c], a[c]);
             }
-            __syncthreads();
         }
     }
     // first zero pivot over the system (each pivot thread saw at most one)
     {
         int v = myinfo ? myinfo : INT_MAX;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v = min(v, shfl_xor(v, off));
+        v = __reduce_min_sync(0xffffffffu, v);
+        __syncthreads();
         if (NW > 1) {
-            if (lane == 0) s_pos[warp] = v;
+            if (lane == 0) s_pos[0][warp] = v;
             __syncthreads();
-            v = s_pos[0];
+            v = s_pos[0][0];
 #pragma unroll
-            for (int w = 1; w < NW; ++w) v = min(v, s_pos[w]);
+            for (int w = 1; w < NW; ++w) v = min(v, s_pos[0][w]);
         }
         if (t == 0) info[sys] = (v == INT_MAX) ? 0 : v;
     }

@@ -34,31 +34,28 @@ __global__ void __launch_bounds__(2 * LASWP_MAXSW)
     if (t < nsw) s_piv[t] = ipiv[k0 + t];
     if (t == 0) s_cnt = 0;
     __syncthreads();
+    // Both loops have a uniform trip count and no early exit: an early `break` here left
+    // the warp diverged for the rest of the kernel and serialised the 256-step walks
+    // thread by thread (110 us instead of a few).
+    const bool is_top = t < LASWP_MAXSW;
+    const int k_me = is_top ? t : t - LASWP_MAXSW;
+    const int pv_me = (k_me < nsw) ? s_piv[k_me] : -1;
+    bool dup = false;
+    for (int kk = 0; kk < nsw; ++kk) dup |= (kk < k_me) & (s_piv[kk] == pv_me);
     int pos = -1;
-    if (t < LASWP_MAXSW) {
-        if (t < nsw) pos = k0 + t;
-    } else {
-        const int k = t - LASWP_MAXSW;
-        if (k < nsw) {
-            const int pv = s_piv[k];
-            if (pv >= k0 + nsw) {
-                pos = pv;
-                for (int kk = 0; kk < k; ++kk)
-                    if (s_piv[kk] == pv) { pos = -1; break; }  // an earlier swap already lists this row
-            }
-        }
+    if (k_me < nsw) {
+        if (is_top) pos = k0 + t;
+        else if (pv_me >= k0 + nsw && !dup) pos = pv_me;   // outside pivot row, first occurrence
     }
-    if (pos >= 0) {
-        int y = pos;
-        for (int k = nsw - 1; k >= 0; --k) {
-            const int a = k0 + k, b = s_piv[k];
-            y = (y == a) ? b : ((y == b) ? a : y);
-        }
-        if (y != pos) {
-            const int slot = atomicAdd(&s_cnt, 1);
-            plan->dst[slot] = pos;
-            plan->src[slot] = y;
-        }
+    int y = pos;
+    for (int k = nsw - 1; k >= 0; --k) {
+        const int a = k0 + k, b = s_piv[k];
+        y = (y == a) ? b : ((y == b) ? a : y);
+    }
+    if (pos >= 0 && y != pos) {
+        const int slot = atomicAdd(&s_cnt, 1);
+        plan->dst[slot] = pos;
+        plan->src[slot] = y;
     }
     __syncthreads();
     if (t == 0) plan->n_tot = s_cnt;

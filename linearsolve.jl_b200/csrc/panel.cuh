@@ -36,7 +36,7 @@ constexpr int PANEL_WMAX = 32;   // max base width
 //   top[par][..]        : the current top row (from CTA 0)
 //   piv[j]              : the chosen pivot row of column j (for the swapper CTA)
 struct PanelMail {
-    unsigned long long hdr[2][PANEL_GMAX][4];
+    unsigned long long hdr[2][PANEL_GMAX][32];   // one 256-byte slot per CTA: spreads the polled lines over L2 slices
     unsigned long long row[2][PANEL_GMAX][2 * PANEL_WMAX];
     unsigned long long top[2][2 * PANEL_WMAX];
     unsigned long long piv[PANEL_WMAX];
@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(NT, 1) panel_base_kernel(PanelArgs<T> p) {
     __shared__ __align__(16) unsigned s_stage[4 + 2 * ROWW];  // [hdr 4][row ROWW][top ROWW]
     __shared__ __align__(16) unsigned s_rows[2 * ROWW];       // fetched [pivot row][top row]
     __shared__ int s_piv;
+    __shared__ int s_win;
     __shared__ int s_abort;
 
     const int tid = threadIdx.x;
@@ -247,38 +248,49 @@ __global__ void __launch_bounds__(NT, 1) panel_base_kernel(PanelArgs<T> p) {
         if (tid <= WN) ll_store(&mail->hdr[par][cta][tid], s_stage[tid], want);
         else if (tid >= 32 && tid < 32 + ROWW) ll_store(&mail->row[par][cta][tid - 32], s_stage[4 + tid - 32], want);
         if (cta == 0 && tid >= NT - ROWW) ll_store(&mail->top[par][tid - (NT - ROWW)], s_stage[4 + ROWW + tid - (NT - ROWW)], want);
-        // 3a. every warp reads all G candidate headers on its own and picks the winner
-        T gv = T(0);
-        int gi = INT_MAX, gc = 0;
+        // 3a. warp 0 polls the G candidate headers (one lane per CTA; a single polling warp per
+        //     CTA keeps the request pressure on the polled L2 lines low) and picks the winner
         bool dead = false;
-        for (int c = lane; c < G; c += 32) {
-            unsigned w[WN + 1];
-            unsigned long long v[WN + 1];
+        if (warp == 0) {
+            T gv = T(0);
+            int gi = INT_MAX, gc = 0;
+            for (int c = lane; c < G; c += 32) {
+                unsigned w[WN + 1];
+                unsigned long long v[WN + 1];
 #pragma unroll
-            for (int x = 0; x <= WN; ++x) v[x] = ll_load(&mail->hdr[par][c][x]);
+                for (int x = 0; x <= WN; ++x) v[x] = ll_load(&mail->hdr[par][c][x]);
 #pragma unroll
-            for (int x = 0; x <= WN; ++x) {
-                if ((unsigned)(v[x] >> 32) != want) {
-                    const long long t0 = clock64();
-                    do {
-                        v[x] = ll_load(&mail->hdr[par][c][x]);
-                        if (clock64() - t0 > kSpinTimeoutCycles) { dead = true; break; }
-                    } while ((unsigned)(v[x] >> 32) != want);
+                for (int x = 0; x <= WN; ++x) {
+                    if ((unsigned)(v[x] >> 32) != want) {
+                        const long long t0 = clock64();
+                        do {
+                            __nanosleep(20);
+                            v[x] = ll_load(&mail->hdr[par][c][x]);
+                            if (clock64() - t0 > kSpinTimeoutCycles) { dead = true; break; }
+                        } while ((unsigned)(v[x] >> 32) != want);
+                    }
+                    w[x] = (unsigned)v[x];
                 }
-                w[x] = (unsigned)v[x];
+                const T cv = Words<T>::join(w);
+                const int cidx = (int)w[WN];
+                if (cv > gv || (cv == gv && cidx < gi)) { gv = cv; gi = cidx; gc = c; }
             }
-            const T cv = Words<T>::join(w);
-            const int cidx = (int)w[WN];
-            if (cv > gv || (cv == gv && cidx < gi)) { gv = cv; gi = cidx; gc = c; }
-        }
-        {
             int gl;
             if (!(gv > T(0))) gi = INT_MAX;
             warp_argmax(gv, gi, gl);
             gc = __shfl_sync(0xffffffffu, gc, gl < 0 ? 0 : gl);
+            if (lane == 0) {
+                const bool none0 = !(gv > T(0));
+                s_piv = none0 ? j : gi;
+                s_win = none0 ? -1 : gc;
+            }
+            if (__any_sync(0xffffffffu, dead) && lane == 0) { atomicExch(p.deverr, DEV_ERR_PANEL_TIMEOUT); s_abort = 1; }
         }
-        const bool none = !(gv > T(0));  // all-zero (or all-NaN) subcolumn: kp = k
-        const int piv = none ? j : gi;
+        __syncthreads();
+        if (s_abort) return;
+        const int piv = s_piv;
+        const int gc = s_win;
+        const bool none = gc < 0;  // all-zero (or all-NaN) subcolumn: kp = k
         // 3b. fetch the winning row and the top row: one packet per thread
         if (tid < 2 * ROWW) {
             const unsigned long long* src = (tid < ROWW)

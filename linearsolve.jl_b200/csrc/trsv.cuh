@@ -100,7 +100,7 @@ struct TrsvSync {
 // rhs = B[perm[i]] when perm != nullptr (row interchanges fused into the load,
 // reference `_naive_lu_ldiv!` pivot loop src/factorization.jl:437-443) else X.
 // Upper: x = U \ X in place.  The solution lands in X (n x nrhs, ldx).
-// NR right-hand sides per CTA (gridDim.y walks the groups of NR columns).
+// NR right-hand sides per CTA; the 1-D grid has nblk * groups CTAs.
 // Solved 64-row segments travel between CTAs as 64-bit {data32, flag32} LL
 // packets: no fence, no separate flag, one L2 round trip per dependency step.
 // Critical path per block row (after the adjacent segment arrives): one 64x64
@@ -122,17 +122,22 @@ __global__ void __launch_bounds__(256) trsv_block_kernel(const T* __restrict__ A
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = tid & (TB - 1);
     const int q = tid >> 6;  // column quarter 0..3 (warps 2q, 2q+1)
-    const int grp = blockIdx.y;
-    const int r0 = grp * NR;
-    unsigned long long* xll = sy.xll + (size_t)grp * nblk * TB * NR * WN;
-
+    // One ticket counter for the whole launch; tickets are dealt round-robin over the
+    // right-hand-side groups so that all groups advance through the block rows together:
+    // the CTAs of one block row (one per group) are co-resident and share the A blocks in L2,
+    // and every group's dependency chain is pipelined instead of the groups running one
+    // after another.
+    const int groups = gridDim.x / nblk;
     if (tid == 0) {
-        const int t = atomicAdd(sy.ticket + grp, 1);
-        if (t == nblk - 1) sy.ticket[grp] = 0;   // everyone has drawn: re-arm for the next sweep
+        const int t = atomicAdd(sy.ticket, 1);
+        if (t == (int)gridDim.x - 1) sy.ticket[0] = 0;   // everyone has drawn: re-arm for the next sweep
         s_ticket = t;
     }
     __syncthreads();
-    const int t = s_ticket;
+    const int grp = s_ticket % groups;
+    const int t = s_ticket / groups;
+    const int r0 = grp * NR;
+    unsigned long long* xll = sy.xll + (size_t)grp * nblk * TB * NR * WN;
     const int r = UPPER ? (nblk - 1 - t) : t;
     const int grow = r * TB + row;
     const bool rok = grow < n;
