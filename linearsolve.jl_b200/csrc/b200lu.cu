@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -20,6 +21,7 @@
 #include "gemm.cuh"
 #include "laswp.cuh"
 #include "panel.cuh"
+#include "panel_cluster.cuh"
 #include "trsm.cuh"
 #include "trsv.cuh"
 #include "util_kernels.cuh"
@@ -54,6 +56,8 @@ struct b200lu_handle {
     LaswpPlan* d_plans = nullptr;
     int cap_plans = 0;
     void* d_panelsync = nullptr;
+    long long* d_pdbg = nullptr;   // B200LU_PANEL_DBG=1: clock64 stamps of the cluster panel launches
+    int pdbg_n = 0;
     unsigned panel_epoch = 0;
     bool factored = false;
     int64_t info = 0;
@@ -181,6 +185,7 @@ static int launch_panel_base(b200lu_handle* h, cudaStream_t st, T* A, int64_t ld
     h->panel_epoch += BASE_W;
     p.mail = (PanelMail*)h->d_panelsync;
     p.deverr = h->d_deverr;
+    p.dbg = nullptr;
     const int has_swapper = (pc1 - pc0) > wc ? 1 : 0;
     if (rpt == 1)
         panel_base_kernel<T, BASE_W, 1, BASE_NT><<<G + has_swapper, BASE_NT, 0, st>>>(p);
@@ -290,17 +295,91 @@ static int launch_laswp(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda, in
     return 0;
 }
 
+// ------------------------------------------------------ cluster base panel --
+template <typename T, int W, int RPT>
+static int launch_panel_cluster_cfg(b200lu_handle* h, cudaStream_t st, PanelArgs<T> p) {
+    auto kern = panel_cluster_kernel<T, W, RPT, PCL_NT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        attr_set = true;
+    }
+    int G = 1;
+    while (G * PCL_NT * RPT < p.m) G *= 2;  // power-of-two cluster sizes only
+    if (G > PCL_GMAX) return set_err(h, 2, "cluster panel of %d rows needs %d CTAs > %d", p.m, G, PCL_GMAX);
+    p.G = G;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G);
+    cfg.blockDim = dim3(PCL_NT);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = G;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CU_TRY(h, cudaLaunchKernelEx(&cfg, kern, p));
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// Base width of the cluster kernel for a panel of m rows (0 = does not fit: use the L2-mailbox
+// kernel of panel.cuh).  256 threads hold up to 128 data registers per thread: 32 doubles x 2
+// rows (16 CTAs x 512 rows = 8192 rows), 16 doubles x 4 rows or 32 floats x 4 rows (16384 rows).
+constexpr int PCL_ROWS2 = PCL_GMAX * PCL_NT * 2;
+template <typename T>
+static int cluster_base_width(const b200lu_handle* h, int m) {
+    if (h->opt[B200LU_OPT_PANEL_MODE] == 1) return 0;
+    if (m <= PCL_ROWS2) return 32;
+    if (m <= 2 * PCL_ROWS2) return sizeof(T) == 8 ? 16 : 32;
+    return 0;
+}
+
+template <typename T>
+static int launch_panel_any(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda, int nrows, int j0,
+                            int wc, int pc0, int pc1, int bw) {
+    const int m = nrows - j0;
+    const bool cluster_ok = h->opt[B200LU_OPT_PANEL_MODE] != 1 && m <= 2 * PCL_ROWS2 &&
+                            (m <= PCL_ROWS2 || sizeof(T) == 4 || bw <= 16);
+    if (!cluster_ok) return launch_panel_base<T>(h, st, A, lda, nrows, j0, wc, pc0, pc1);
+    PanelArgs<T> p;
+    p.A = A;
+    p.lda = lda;
+    p.j0 = j0;
+    p.m = m;
+    p.wc = wc;
+    p.pc0 = pc0;
+    p.pc1 = pc1;
+    p.ipiv = h->d_ipiv;
+    p.info = h->d_info;
+    p.G = 0;
+    p.epoch = 0;
+    p.mail = nullptr;
+    p.deverr = h->d_deverr;
+    p.dbg = h->d_pdbg ? h->d_pdbg + 16 * (h->pdbg_n++ % 4096) : nullptr;
+    if constexpr (sizeof(T) == 8) {
+        if (bw > 16) return launch_panel_cluster_cfg<T, 32, 2>(h, st, p);
+        if (m <= PCL_ROWS2) return launch_panel_cluster_cfg<T, 16, 2>(h, st, p);
+        return launch_panel_cluster_cfg<T, 16, 4>(h, st, p);
+    } else {
+        if (m <= PCL_ROWS2) return launch_panel_cluster_cfg<T, 32, 2>(h, st, p);
+        return launch_panel_cluster_cfg<T, 32, 4>(h, st, p);
+    }
+}
+
 // ---------------------------------------------------------- recursive panel --
 // Factor columns [j0, j0+w) of the nrows x * matrix (rows j0..nrows-1) inside the
-// outer panel [pc0, pc1).  Interchanges are applied to the whole outer panel by
-// the base kernel's swapper CTA, so no laswp appears here.
+// outer panel [pc0, pc1), recursing down to base blocks of width bw.  Interchanges
+// are applied to the whole outer panel by the base kernels, so no laswp appears here.
 template <typename T>
 static int panel_recursive(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda, int nrows, int j0,
-                           int w, int pc0, int pc1) {
-    if (w <= BASE_W) return launch_panel_base<T>(h, st, A, lda, nrows, j0, w, pc0, pc1);
-    const int w1 = ((w / 2 + BASE_W - 1) / BASE_W) * BASE_W;
+                           int w, int pc0, int pc1, int bw) {
+    if (w <= bw) return launch_panel_any<T>(h, st, A, lda, nrows, j0, w, pc0, pc1, bw);
+    const int w1 = ((w / 2 + bw - 1) / bw) * bw;
     const int w2 = w - w1;
-    int rc = panel_recursive<T>(h, st, A, lda, nrows, j0, w1, pc0, pc1);
+    int rc = panel_recursive<T>(h, st, A, lda, nrows, j0, w1, pc0, pc1, bw);
     if (rc) return rc;
     T* L11 = A + (int64_t)j0 * lda + j0;
     T* A12 = A + (int64_t)(j0 + w1) * lda + j0;
@@ -310,7 +389,15 @@ static int panel_recursive(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda,
     rc = launch_gemm(h, st, mrest, w2, w1, A + (int64_t)j0 * lda + (j0 + w1), lda, A12, lda,
                      A + (int64_t)(j0 + w1) * lda + (j0 + w1), lda);
     if (rc) return rc;
-    return panel_recursive<T>(h, st, A, lda, nrows, j0 + w1, w2, pc0, pc1);
+    return panel_recursive<T>(h, st, A, lda, nrows, j0 + w1, w2, pc0, pc1, bw);
+}
+// outer-panel entry: pick the base width from the panel height
+template <typename T>
+static int panel_factor(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda, int nrows, int j0,
+                        int w, int pc0, int pc1) {
+    int bw = cluster_base_width<T>(h, nrows - j0);
+    if (bw == 0) bw = BASE_W;
+    return panel_recursive<T>(h, st, A, lda, nrows, j0, w, pc0, pc1, bw);
 }
 
 static int ensure_events(b200lu_handle* h, int count) {
@@ -343,7 +430,7 @@ static int getrf_device(b200lu_handle* h, T* A, int64_t lda, int n) {
     }
     {
         const int jb = std::min(nb, n);
-        rc = panel_recursive<T>(h, sp, A, lda, n, 0, jb, 0, jb);
+        rc = panel_factor<T>(h, sp, A, lda, n, 0, jb, 0, jb);
         if (rc) return rc;
         laswp_plan_kernel<<<1, 2 * LASWP_MAXSW, 0, sp>>>(h->d_ipiv, 0, jb, h->d_plans + 0);
         LAUNCH_CHECK(h);
@@ -375,7 +462,7 @@ static int getrf_device(b200lu_handle* h, T* A, int64_t lda, int n) {
             CU_TRY(h, cudaEventRecord(h->ev_next, sm));
             CU_TRY(h, cudaStreamWaitEvent(sp, h->ev_next, 0));
         }
-        rc = panel_recursive<T>(h, sp, A, lda, n, j1, jb2, j1, j1 + jb2);
+        rc = panel_factor<T>(h, sp, A, lda, n, j1, jb2, j1, j1 + jb2);
         if (rc) return rc;
         laswp_plan_kernel<<<1, 2 * LASWP_MAXSW, 0, sp>>>(h->d_ipiv, j1, jb2, h->d_plans + (k + 1));
         LAUNCH_CHECK(h);
@@ -668,6 +755,7 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     h->opt[B200LU_OPT_PROFILE] = 0;
     h->opt[B200LU_OPT_PANEL_RPT] = 0;
     h->opt[B200LU_OPT_GEMM_CFG] = 0;
+    h->opt[B200LU_OPT_PANEL_MODE] = 0;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) == cudaSuccess;
@@ -684,6 +772,10 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     ok = ok && cudaMalloc((void**)&h->d_scal, 64) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&h->h_small, 64) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&h->h_scal, 64) == cudaSuccess;
+    if (ok && getenv("B200LU_PANEL_DBG")) {
+        ok = cudaMalloc((void**)&h->d_pdbg, 4096 * 16 * sizeof(long long)) == cudaSuccess;
+        ok = ok && cudaMemset(h->d_pdbg, 0, 4096 * 16 * sizeof(long long)) == cudaSuccess;
+    }
     if (!ok) {
         b200lu_destroy(h);
         return 1;
@@ -697,6 +789,18 @@ void b200lu_destroy(b200lu_handle* h) {
     cudaSetDevice(h->dev);
     if (h->s_main) cudaStreamSynchronize(h->s_main);
     if (h->s_panel) cudaStreamSynchronize(h->s_panel);
+    if (h->d_pdbg) {
+        const int cnt = std::min(h->pdbg_n, 4096);
+        std::vector<long long> t((size_t)cnt * 16);
+        cudaMemcpy(t.data(), h->d_pdbg, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        for (int i = std::max(0, cnt - 256); i < cnt; i += 8) {
+            const long long* s = &t[(size_t)i * 16];
+            fprintf(stderr, "[pdbg] launch %d m=%lld G=%lld: load %lld loop %lld store %lld swaps %lld exit %lld cycles\n", i, s[6], s[7],
+                    s[1] - s[0], s[2] - s[1], s[3] - s[2], s[4] - s[3], s[5] - s[4]);
+            if (s[8] | s[9]) fprintf(stderr, "[pdbg]    per-column sums: argmax+stage %lld | bar+send %lld | wait %lld | reduce %lld | update %lld | loop-overhead %lld\n", s[8], s[9], s[10], s[11], s[12], s[13]);
+        }
+        cudaFree(h->d_pdbg);
+    }
     free_dev(h->dA); free_dev(h->dA64); free_dev(h->d_ipiv); free_dev(h->d_perm);
     free_dev(h->d_info); free_dev(h->d_deverr); free_dev(h->d_plans); free_dev(h->d_panelsync);
     free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_wL); free_dev(h->d_wU); free_dev(h->d_tflags); free_dev(h->d_tticket);
@@ -791,6 +895,7 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_REFINE_MAXIT && value < 0) return -3;
     if (option == B200LU_OPT_PANEL_RPT && (value < 0 || value > 2)) return -3;
     if (option == B200LU_OPT_GEMM_CFG && (value < 0 || value > 2)) return -3;
+    if (option == B200LU_OPT_PANEL_MODE && (value < 0 || value > 1)) return -3;
     h->opt[option] = value;
     return 0;
 }

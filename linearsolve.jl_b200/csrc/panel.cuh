@@ -56,6 +56,7 @@ struct PanelArgs {
     unsigned epoch;      // packets carry epoch + j + 1 at column j
     PanelMail* mail;
     int* deverr;
+    long long* dbg;      // optional: 8 clock64 stamps per launch (B200LU_PANEL_DBG=1)
 };
 
 __device__ __forceinline__ void ll_store(unsigned long long* p, unsigned data, unsigned flag) {

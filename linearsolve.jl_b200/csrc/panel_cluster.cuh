@@ -1,0 +1,501 @@
+// panel_cluster.cuh — partial-pivoting base panel (getf2) on ONE thread-block cluster.
+//
+// Same arithmetic contract as panel.cuh (reference src/blocked_lufact.jl:38-54 pivot rule,
+// :93-122 column loop; src/generic_lufact.jl:117-123 zero-pivot rule): amax starts at 0,
+// strict `>` (NaN never wins), lowest row on ties; zero pivot => info = k once, no scaling,
+// the rank-1 update still runs; scaling multiplies by inv(pivot); updates are FMAs.
+//
+// What changed is the exchange.  Measured on B200 (scripts/microbench/exchange_latency*.cu):
+// the L2-mailbox protocol of panel.cuh costs 3000-4700 cycles per column at 32 CTAs; a
+// cluster-wide all-to-all with `st.async` + mbarrier transaction counts costs 870 (8 CTAs) to
+// 1100 cycles (16 CTAs) including the CTA barrier, and never touches L2, so the concurrent
+// trailing-update GEMM cannot slow it down.  Per column:
+//   1. every warp: redux arg-max over its rows (the reciprocal of each lane's own candidate is
+//      computed under the redux latency); the winning lane stages its row in shared memory;
+//   2. one __syncthreads; the sender threads reduce the warp candidates and push the CTA
+//      candidate {1/pivot, position, row} into EVERY CTA's inbox with st.async (complete_tx on
+//      the receiver's mbarrier) — only the vectors that still hold unfactored columns travel;
+//   3. every thread waits on its own CTA's mbarrier (hardware sleep, no polling traffic), every
+//      warp reduces the <= 16 candidates redundantly and reads the winning row from its own
+//      shared memory;
+//   4. scale + rank-1 update in registers.
+// Rows never move between threads: each thread tracks the current POSITION of its rows (the
+// LAPACK interchange sequence acts on positions), candidates are compared by position, and the
+// rows are scattered to their final positions when the block is written back.  That removes the
+// "top row" message of panel.cuh.  The interchanges of the other columns of the outer panel are
+// applied at the end by the same cluster as one gather/scatter of the <= 2W rows that moved.
+//
+// Latency economy.  In-kernel clock64 stamps of the first versions showed the exchange wait at
+// only ~500 of ~4300 cycles per column; the rest was dependent chains of slow instructions in
+// warps that all sit in the same phase (2 warps per scheduler: nothing hides latency).  So:
+//  * U = 8 columns are unrolled with static register indices, registers rotate by U once per 8
+//    columns, "column already factored" is one warp-uniform branch per chunk of 8 elements;
+//  * arg-max = ONE redux on the top 32 bits + a ballot; ties on the top word (rare) take the
+//    exact slow path;
+//  * 1/pivot is computed by every candidate lane while the redux is in flight;
+//  * software pipelining: the next column's element is updated first and its arg-max issued
+//    before the rest of the rank-1 update.
+#pragma once
+#include "common.cuh"
+#include "panel.cuh"
+
+namespace b200lu {
+
+#ifdef PCL_TIMING
+#define PCL_T(i) do { if (dbg) { const long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; } } while (0)
+#else
+#define PCL_T(i) do {} while (0)
+#endif
+
+constexpr int PCL_GMAX = 16;   // non-portable cluster size limit on sm_100
+constexpr int PCL_NT = 256;    // threads per CTA (up to 255 registers per thread)
+constexpr int PCL_U = 8;       // columns unrolled per loop iteration
+
+__device__ __forceinline__ unsigned pcl_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned pcl_mapa(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void pcl_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ unsigned pcl_cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned pcl_cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void pcl_mbar_init(unsigned addr, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pcl_mbar_expect_tx(unsigned addr, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+// The inbox lives in this CTA's shared memory (never cached in L1), so observing the phase flip
+// orders the st.async payload; the CTA-scope form avoids the L1 invalidate (CCTL.IVALL) that the
+// .acquire.cluster form costs every column.
+__device__ __forceinline__ bool pcl_mbar_try_wait(unsigned addr, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool pcl_mbar_wait(unsigned addr, unsigned parity) {
+    if (pcl_mbar_try_wait(addr, parity)) return true;
+    const long long t0 = clock64();
+    while (!pcl_mbar_try_wait(addr, parity))
+        if (clock64() - t0 > kSpinTimeoutCycles) return false;
+    return true;
+}
+__device__ __forceinline__ void pcl_st_async_v2(unsigned raddr, unsigned long long a, unsigned long long b, unsigned rmbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];"
+                 ::"r"(raddr), "l"(a), "l"(b), "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ unsigned long long pcl_bits(double x) { return (unsigned long long)__double_as_longlong(x); }
+__device__ __forceinline__ unsigned long long pcl_bits(float x) { return (unsigned long long)__float_as_uint(x); }
+__device__ __forceinline__ void pcl_from_bits(unsigned long long b, double& x) { x = __longlong_as_double((long long)b); }
+__device__ __forceinline__ void pcl_from_bits(unsigned long long b, float& x) { x = __uint_as_float((unsigned)b); }
+
+
+// Exact arg-max over the lanes of a warp: largest v (v >= 0, candidates have v > 0), lowest pos
+// among equals.  Returns the winning lane or -1.  Fast path: one redux on the top 32 bits of the
+// value and one ballot; only if several lanes share the top word do the low word / position
+// reductions run.  Split in two so that independent work can be placed under the redux latency.
+__device__ __forceinline__ unsigned pcl_argmax_key(double v) { return (unsigned)((unsigned long long)__double_as_longlong(v) >> 32); }
+__device__ __forceinline__ unsigned pcl_argmax_key(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ unsigned pcl_argmax_issue(unsigned key) { return __reduce_max_sync(0xffffffffu, key); }
+__device__ __forceinline__ int pcl_argmax_finish(double v, int pos, unsigned key, unsigned mkey) {
+    const bool c1 = (key == mkey) && (v > 0.0);
+    const unsigned m1 = __ballot_sync(0xffffffffu, c1);
+    if (m1 == 0u) return -1;
+    if ((m1 & (m1 - 1u)) == 0u) return __ffs(m1) - 1;
+    const unsigned lo = (unsigned)(unsigned long long)__double_as_longlong(v);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
+    const bool c2 = c1 && lo == mlo;
+    const int mpos = __reduce_min_sync(0xffffffffu, c2 ? pos : INT_MAX);
+    return __ffs(__ballot_sync(0xffffffffu, c2 && pos == mpos)) - 1;
+}
+__device__ __forceinline__ int pcl_argmax_finish(float v, int pos, unsigned key, unsigned mkey) {
+    const bool c1 = (key == mkey) && (v > 0.0f);
+    const unsigned m1 = __ballot_sync(0xffffffffu, c1);
+    if (m1 == 0u) return -1;
+    if ((m1 & (m1 - 1u)) == 0u) return __ffs(m1) - 1;
+    const int mpos = __reduce_min_sync(0xffffffffu, c1 ? pos : INT_MAX);
+    return __ffs(__ballot_sync(0xffffffffu, c1 && pos == mpos)) - 1;
+}
+template <typename T>
+__device__ __forceinline__ int pcl_warp_argmax(T v, int pos) {
+    const unsigned key = pcl_argmax_key(v);
+    return pcl_argmax_finish(v, pos, key, pcl_argmax_issue(key));
+}
+
+template <typename T, int W, int RPT, int NT>
+struct PclShared {
+    static constexpr int NW = NT / 32;
+    static constexpr int EPV = 16 / (int)sizeof(T);
+    static constexpr int NV = W / EPV;
+    ulonglong2 box[2][PCL_GMAX][1 + NV];   // inbox: one message {header, row} per source CTA
+    T stage[NW][W];                        // per-warp candidate rows
+    T s_top[W];                            // zero/NaN-pivot path only
+    T s_val[NW];
+    int s_pos[NW];
+    unsigned long long mbar[2];
+    int s_mv_dst[2 * W], s_mv_src[2 * W];
+    int s_nmv;
+    int s_has_top;
+};
+
+// rotate the row registers left by U
+template <typename T, int W, int RPT, int U>
+__device__ __forceinline__ void pcl_rotate(T (&a)[RPT][W]) {
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+        T t[U];
+#pragma unroll
+        for (int e = 0; e < U; ++e) t[e] = a[q][e];
+#pragma unroll
+        for (int e = 0; e + U < W; ++e) a[q][e] = a[q][e + U];
+#pragma unroll
+        for (int e = 0; e < U; ++e) a[q][W - U + e] = t[e];
+    }
+}
+
+// local candidate of the column held at register index E: strict '>' from amax = 0 (NaN never
+// wins), lowest position on ties; rows at positions < j are finished
+template <typename T, int W, int RPT, int E>
+__device__ __forceinline__ void pcl_local_cand(const T (&a)[RPT][W], const int (&pos)[RPT], int j, T& best, int& bpos) {
+    best = T(0);
+    bpos = INT_MAX;
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+        if (pos[q] >= j && pos[q] != INT_MAX) {
+            const T v = tabs(a[q][E]);
+            if (v > best || (v == best && v > T(0) && pos[q] < bpos)) { best = v; bpos = pos[q]; }
+        }
+    }
+}
+
+// The parts of one column that need STATIC register indices (JJ = index of the column inside
+// the current group of U).  Part A: scale, update of the NEXT column, its local candidate.
+// Part B (runs while the warp arg-max of the next column is in flight): the rest of the rank-1
+// update, and the rotation after the last column of a group.
+template <typename T, int W, int RPT, int U, int JJ>
+__device__ __forceinline__ void pcl_core_a(T (&a)[RPT][W], const int (&pos)[RPT], const bool (&upd)[RPT],
+                                           const T* __restrict__ prow, T rinv, bool scale, int ech, int j,
+                                           T& best, int& bpos) {
+#pragma unroll
+    for (int q = 0; q < RPT; ++q)
+        if (upd[q] && scale) a[q][JJ] *= rinv;
+    if (JJ + 1 < U || ech > 1) {   // index U is live unless this is the last group
+        const T pr = prow[JJ + 1];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q)
+            if (upd[q]) a[q][JJ + 1] = tfma(-a[q][JJ], pr, a[q][JJ + 1]);
+    }
+    pcl_local_cand<T, W, RPT, JJ + 1>(a, pos, j + 1, best, bpos);
+}
+template <typename T, int W, int RPT, int U, int JJ>
+__device__ __forceinline__ void pcl_core_b(T (&a)[RPT][W], const bool (&upd)[RPT], const T* __restrict__ prow, int ech) {
+    constexpr int NCH = W / U;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        if (k < ech) {   // warp-uniform: chunk k still holds unfactored columns
+            T pr[U];
+#pragma unroll
+            for (int e = 0; e < U; ++e) pr[e] = prow[k * U + e];
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) {
+                if (upd[q]) {
+#pragma unroll
+                    for (int e = 0; e < U; ++e)
+                        if (k * U + e > JJ + 1) a[q][k * U + e] = tfma(-a[q][JJ], pr[e], a[q][k * U + e]);
+                }
+            }
+        }
+    }
+    if (JJ + 1 == U) pcl_rotate<T, W, RPT, U>(a);
+}
+
+template <typename T, int W, int RPT, int NT>
+__global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
+    constexpr int NW = NT / 32;
+    constexpr int U = PCL_U;
+    constexpr int EPV = 16 / (int)sizeof(T);       // elements per 16-byte vector
+    constexpr int NV = W / EPV;                    // vectors per row
+    constexpr int NIT = W / U;
+    static_assert(U == 8 && W % U == 0 && U % EPV == 0 && W >= 2 * U, "unroll granularity");
+    static_assert(NT / PCL_GMAX >= NV, "one sender thread per (destination, row vector)");
+    static_assert(NW <= 32 && W <= 32 && 2 * W <= NT, "warp-level bookkeeping");
+    __shared__ __align__(16) PclShared<T, W, RPT, NT> sh;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int me = (int)pcl_cluster_rank();
+    const int G = (int)pcl_cluster_size();   // power of two
+    const int lgG = 31 - __clz(G);
+    const int wc = p.wc;
+
+    if (tid == 0) {
+        pcl_mbar_init(pcl_smem_u32(&sh.mbar[0]), 1);
+        pcl_mbar_init(pcl_smem_u32(&sh.mbar[1]), 1);
+        sh.s_has_top = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const bool dbg = p.dbg != nullptr && me == 0 && tid == 0;
+    if (dbg) p.dbg[0] = clock64();
+
+    T a[RPT][W];
+    int ri[RPT];   // panel-local ORIGINAL row of each owned row (where it is loaded from)
+    int pos[RPT];  // its current position in the LAPACK row order
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+        ri[q] = me * (NT * RPT) + q * NT + tid;
+        pos[q] = ri[q] < p.m ? ri[q] : INT_MAX;   // padding rows are never candidates
+        const T* src = p.A + (long long)p.j0 * p.lda + (p.j0 + (ri[q] < p.m ? ri[q] : 0));
+#pragma unroll
+        for (int c = 0; c < W; ++c) {
+            a[q][c] = (ri[q] < p.m && c < wc) ? src[(long long)c * p.lda] : T(0);
+        }
+    }
+    // sender role: thread (dst, k) pushes row vector k of this CTA's message to CTA dst; the
+    // threads with k == 0 also push the header
+    const int s_dst = tid & (G - 1), s_k = tid >> lgG;
+    const unsigned raddr0 = pcl_mapa(pcl_smem_u32(&sh.box[0][me][1 + (s_k < NV ? s_k : 0)]), (unsigned)s_dst);
+    const unsigned rhdr0 = pcl_mapa(pcl_smem_u32(&sh.box[0][me][0]), (unsigned)s_dst);
+    const unsigned rbar0 = pcl_mapa(pcl_smem_u32(&sh.mbar[0]), (unsigned)s_dst);
+    constexpr unsigned BOXB = (unsigned)sizeof(sh.box[0]);   // parity stride of the inbox
+    // warp 0 of every CTA tracks which original row sits at each touched position
+    int top_src = lane;      // lane l < W: original row now at position l
+    int ext_row = -1;        // lane e: e-th position >= W that took part in an interchange
+    int ext_src = -1;        //         and the original row now sitting there
+    int ext_n = 0;
+
+    pcl_cluster_sync();  // mbarriers initialised cluster-wide before any st.async
+    if (dbg) p.dbg[1] = clock64();
+#ifdef PCL_TIMING
+    long long tacc[6] = {0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#endif
+
+    // Register layout: during group `it` register index e holds column (e + U*it) mod W, so the
+    // U columns of the group sit at the static indices 0..U-1; elements e >= W - U*it are
+    // columns factored in earlier groups (their L multipliers) and are left alone.
+    T best;
+    int bpos, wl;
+    pcl_local_cand<T, W, RPT, 0>(a, pos, 0, best, bpos);
+    wl = pcl_warp_argmax(best, bpos);
+    if (lane == wl) {
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+            if (pos[q] == bpos) {
+#pragma unroll
+                for (int c = 0; c < W; ++c) sh.stage[warp][c] = a[q][c];
+            }
+        }
+    }
+    // The column loop is ROLLED: one copy of the exchange code (an unrolled loop ran out of the
+    // 32 KB instruction cache — "no instruction" was the top stall reason); only the register
+    // part is selected by a switch on the column's index inside its group.  Pass j eliminates
+    // column j (j >= 0) and then publishes the candidates of column j + 1.
+#pragma unroll 1
+    for (int j = -1; j < wc; ++j) {
+        if (j >= 0) {
+            const int jj = j & (U - 1), it = j / U;
+            const int par = j & 1;
+            const int ech = NIT - it;            // chunks of U elements that still hold live columns
+            PCL_T(5);
+            if (!pcl_mbar_wait(pcl_smem_u32(&sh.mbar[par]), (unsigned)(j >> 1) & 1u)) {
+                atomicExch(p.deverr, DEV_ERR_PANEL_TIMEOUT);
+                return;
+            }
+            PCL_T(2);
+            // every warp picks the winner among the G candidates; each candidate lane also
+            // computes the reciprocal of its own value under the redux latency
+            T gval = T(1), gv = T(0);
+            int gpos = INT_MAX;
+            if (lane < G) {
+                gpos = (int)(unsigned)sh.box[par][lane][0].x;
+                if (gpos != INT_MAX) { gval = reinterpret_cast<const T*>(&sh.box[par][lane][1])[jj]; gv = tabs(gval); }
+            }
+            const int gl = pcl_warp_argmax(gv, gpos);
+            T rinv = T(1) / gval;
+            const bool none = gl < 0;  // all-zero (or all-NaN) subcolumn: kp = k
+            const int gsel = none ? 0 : gl;
+            rinv = __shfl_sync(0xffffffffu, rinv, gsel);
+            const int piv = none ? j : __shfl_sync(0xffffffffu, gpos, gsel);
+            const T* prow = reinterpret_cast<const T*>(&sh.box[par][gsel][1]);
+            bool scale = true;
+            if (none) {
+                // the pivot row is the row at position j: its owner hands it to every CTA (rare path)
+#pragma unroll
+                for (int q = 0; q < RPT; ++q) {
+                    if (pos[q] == j) {
+#pragma unroll
+                        for (int c = 0; c < W; ++c) sh.s_top[c] = a[q][c];
+                        sh.s_has_top = 1;
+                    }
+                }
+                __syncthreads();
+                if (sh.s_has_top) {
+                    // element-wise remote stores to the OTHER CTAs; a rolled loop keeps this path small
+                    for (int i = tid; i < G * W; i += NT) {
+                        const int d = i / W, c = i - d * W;
+                        if (d == me) continue;
+                        const unsigned ra = pcl_mapa(pcl_smem_u32(&sh.s_top[c]), (unsigned)d);
+                        if constexpr (sizeof(T) == 8)
+                            asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(sh.s_top[c]) : "memory");
+                        else
+                            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(sh.s_top[c]) : "memory");
+                    }
+                }
+                pcl_cluster_sync();
+                if (tid == 0) sh.s_has_top = 0;
+                prow = sh.s_top;
+                const T pv = prow[jj];
+                scale = (pv != T(0));
+                rinv = T(1) / pv;
+                if (me == 0 && tid == 0 && pv == T(0) && *p.info == 0) *p.info = p.j0 + j + 1;
+            }
+            PCL_T(3);
+            if (me == 0 && tid == 0) p.ipiv[p.j0 + j] = p.j0 + piv;
+            // positions
+            bool upd[RPT];
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) {
+                if (pos[q] == piv) pos[q] = j;            // the pivot row: finished
+                else if (pos[q] == j) pos[q] = piv;       // the displaced top row stays active
+                upd[q] = pos[q] > j && pos[q] != INT_MAX;
+            }
+#define PCL_CASES(FN, ...)                                              \
+    switch (jj) {                                                       \
+        case 0: FN<T, W, RPT, U, 0>(__VA_ARGS__); break;                \
+        case 1: FN<T, W, RPT, U, 1>(__VA_ARGS__); break;                \
+        case 2: FN<T, W, RPT, U, 2>(__VA_ARGS__); break;                \
+        case 3: FN<T, W, RPT, U, 3>(__VA_ARGS__); break;                \
+        case 4: FN<T, W, RPT, U, 4>(__VA_ARGS__); break;                \
+        case 5: FN<T, W, RPT, U, 5>(__VA_ARGS__); break;                \
+        case 6: FN<T, W, RPT, U, 6>(__VA_ARGS__); break;                \
+        default: FN<T, W, RPT, U, 7>(__VA_ARGS__); break;               \
+    }
+            PCL_CASES(pcl_core_a, a, pos, upd, prow, rinv, scale, ech, j, best, bpos)
+            const unsigned akey = pcl_argmax_key(best);
+            const unsigned amax = pcl_argmax_issue(akey);          // in flight under part B
+            PCL_CASES(pcl_core_b, a, upd, prow, ech)
+#undef PCL_CASES
+            wl = pcl_argmax_finish(best, bpos, akey, amax);
+            if (lane == wl) {   // stage the whole row (already in the coordinates of column j + 1)
+#pragma unroll
+                for (int q = 0; q < RPT; ++q) {
+                    if (pos[q] == bpos) {
+#pragma unroll
+                        for (int c = 0; c < W; ++c) sh.stage[warp][c] = a[q][c];
+                    }
+                }
+            }
+            if (warp == 0 && piv != j) {  // interchange of positions j and piv
+                const int sj = __shfl_sync(0xffffffffu, top_src, j);
+                if (piv < W) {
+                    const int sp = __shfl_sync(0xffffffffu, top_src, piv);
+                    if (lane == j) top_src = sp;
+                    if (lane == piv) top_src = sj;
+                } else {
+                    const unsigned hit = __ballot_sync(0xffffffffu, ext_row == piv);
+                    int e;
+                    if (hit) e = __ffs(hit) - 1;
+                    else {
+                        e = ext_n++;
+                        if (lane == e) { ext_row = piv; ext_src = piv; }
+                    }
+                    const int sp = __shfl_sync(0xffffffffu, ext_src, e);
+                    if (lane == j) top_src = sp;
+                    if (lane == e) ext_src = sj;
+                }
+            }
+            PCL_T(4);
+        }
+        // ---- publish the candidates of column jn = j + 1 (staged above / in the prologue) ----
+        const int jn = j + 1;
+        if (jn < wc) {
+            const int jjn = jn & (U - 1), itn = jn / U;
+            const int par = jn & 1;
+            if (lane == wl) { sh.s_val[warp] = best; sh.s_pos[warp] = bpos; }
+            if (wl < 0 && lane == 0) { sh.s_val[warp] = T(0); sh.s_pos[warp] = INT_MAX; }
+            const int vmax = (NIT - itn) * (U / EPV);   // live row vectors of that group
+            const int v0 = jjn / EPV;
+            if (tid == 0) pcl_mbar_expect_tx(pcl_smem_u32(&sh.mbar[par]), (unsigned)(G * (1 + vmax - v0)) * 16u);
+            PCL_T(0);
+            __syncthreads();
+            const T cv = lane < NW ? sh.s_val[lane] : T(0);
+            const int cpos = lane < NW ? sh.s_pos[lane] : INT_MAX;
+            int cw = pcl_warp_argmax(cv, cpos);
+            const int cp = cw < 0 ? INT_MAX : __shfl_sync(0xffffffffu, cpos, cw);
+            if (cw < 0) cw = 0;
+            const unsigned rb = rbar0 + (unsigned)par * 8u;
+            if (s_k >= v0 && s_k < vmax) {
+                const ulonglong2 v = reinterpret_cast<const ulonglong2*>(&sh.stage[cw][0])[s_k];
+                pcl_st_async_v2(raddr0 + (unsigned)par * BOXB, v.x, v.y, rb);
+            }
+            if (s_k == 0) pcl_st_async_v2(rhdr0 + (unsigned)par * BOXB, (unsigned long long)(unsigned)cp, 0ull, rb);
+            PCL_T(1);
+        }
+    }
+    // ragged block: bring the registers back to natural order (a group rotates only after its
+    // last column, which a short block never reaches)
+    {
+        int rots = (NIT - wc / U) % NIT;
+#pragma unroll 1
+        for (; rots > 0; --rots) pcl_rotate<T, W, RPT, U>(a);
+    }
+    if (dbg) p.dbg[2] = clock64();
+#ifdef PCL_TIMING
+    if (dbg) for (int i = 0; i < 6; ++i) p.dbg[8 + i] = tacc[i];
+#endif
+    // write the block back, every row at its final position
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+        T* dst = p.A + (long long)p.j0 * p.lda + (p.j0 + (ri[q] < p.m ? pos[q] : 0));
+#pragma unroll
+        for (int c = 0; c < W; ++c) {
+            if (ri[q] < p.m && c < wc) dst[(long long)c * p.lda] = a[q][c];
+        }
+    }
+    if (dbg) p.dbg[3] = clock64();
+    // the same interchanges on the other columns of the outer panel [pc0, pc1)
+    const int nleft = p.j0 - p.pc0;
+    const int ncols = nleft + (p.pc1 - (p.j0 + wc));
+    if (ncols > 0) {
+        if (warp == 0) {
+            const bool m1 = lane < W && top_src != lane;
+            const bool m2 = lane < ext_n && ext_src != ext_row;
+            const unsigned b1 = __ballot_sync(0xffffffffu, m1), b2 = __ballot_sync(0xffffffffu, m2);
+            const unsigned below = (1u << lane) - 1u;
+            if (m1) { const int s = __popc(b1 & below); sh.s_mv_dst[s] = lane; sh.s_mv_src[s] = top_src; }
+            if (m2) { const int s = __popc(b1) + __popc(b2 & below); sh.s_mv_dst[s] = ext_row; sh.s_mv_src[s] = ext_src; }
+            if (lane == 0) sh.s_nmv = __popc(b1) + __popc(b2);
+        }
+        __syncthreads();
+        const int nmv = sh.s_nmv;
+        if (nmv > 0) {
+            // one group of 2W threads per column: all loads of a column before its stores
+            constexpr int GRP = 2 * W, CPP = NT / GRP;
+            const int slot = tid % GRP, sub = tid / GRP;
+            const int src = slot < nmv ? sh.s_mv_src[slot] : 0, dst = slot < nmv ? sh.s_mv_dst[slot] : 0;
+            for (int c0 = me * CPP; c0 < ncols; c0 += G * CPP) {
+                const int c = c0 + sub;
+                const bool on = c < ncols && slot < nmv;
+                const int col = (c < nleft) ? (p.pc0 + c) : (p.j0 + wc + (c - nleft));
+                T* base = p.A + (long long)col * p.lda + p.j0;
+                T v = T(0);
+                if (on) v = base[src];
+                __syncthreads();
+                if (on) base[dst] = v;
+            }
+        }
+    }
+    if (dbg) p.dbg[4] = clock64();
+    pcl_cluster_sync();  // no CTA leaves while a peer could still address its shared memory
+    if (dbg) { p.dbg[5] = clock64(); p.dbg[6] = p.m; p.dbg[7] = G; }
+}
+
+}  // namespace b200lu
