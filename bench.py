@@ -47,6 +47,7 @@ def parse():
     p.add_argument("--lookahead", type=int, default=-1)
     p.add_argument("--rpt", type=int, default=-1)
     p.add_argument("--gemm-cfg", type=int, default=-1)
+    p.add_argument("--panel-mode", type=int, default=-1)
     return p.parse_args()
 
 
@@ -191,6 +192,8 @@ def main():
         h.set_option(C.OPT_PANEL_RPT, args.rpt)
     if args.gemm_cfg >= 0:
         h.set_option(C.OPT_GEMM_CFG, args.gemm_cfg)
+    if args.panel_mode >= 0:
+        h.set_option(C.OPT_PANEL_MODE, args.panel_mode)
 
     if args.workload == "batched":
         return bench_batched(args, ls, h, torch, dev, rank, world, barrier, max_over_ranks)

@@ -100,7 +100,9 @@ enum {
     B200LU_OPT_PROFILE = 5,     /* 1: bracket every trailing GEMM with CUDA events */
     B200LU_OPT_PANEL_RPT = 6,   /* rows per thread in the base panel: 0 auto, 1, 2 */
     B200LU_OPT_GEMM_CFG = 7,    /* FP64 trailing-update tile configuration 0..2      */
-    B200LU_OPT_COUNT = 8
+    B200LU_OPT_PANEL_MODE = 8,  /* base panel: 0 auto (cluster/DSMEM kernel when the panel fits
+                                   16 CTAs, else L2 mailbox), 1 always L2 mailbox  */
+    B200LU_OPT_COUNT = 9
 };
 
 /* library/ABI version: major*10000 + minor*100 + patch */

@@ -195,11 +195,10 @@ static int launch_panel_base(b200lu_handle* h, cudaStream_t st, T* A, int64_t ld
     return 0;
 }
 
-template <typename T>
-static int launch_trsm(b200lu_handle* h, cudaStream_t st, const T* Lp, int64_t ldl, T* Bp,
-                       int64_t ldb, int w, int ncols) {
-    if (w <= 0 || ncols <= 0) return 0;
-    constexpr int CC = 4, NWARP = 8;
+template <typename T, int CC>
+static int launch_trsm_cc(b200lu_handle* h, cudaStream_t st, const T* Lp, int64_t ldl, T* Bp,
+                          int64_t ldb, int w, int ncols) {
+    constexpr int NWARP = 8;
     const int grid = cdiv(ncols, CC * NWARP);
     const int rpl = cdiv(w, 32);
 #define TRSM_CASE(R)                                                                             \
@@ -221,6 +220,15 @@ static int launch_trsm(b200lu_handle* h, cudaStream_t st, const T* Lp, int64_t l
 #undef TRSM_CASE
     LAUNCH_CHECK(h);
     return 0;
+}
+// Few right-hand-side columns (the panel recursion, the look-ahead block): the k-chain latency
+// is the cost, so one column per warp spreads it over 4x more CTAs; many columns: 4 per warp.
+template <typename T>
+static int launch_trsm(b200lu_handle* h, cudaStream_t st, const T* Lp, int64_t ldl, T* Bp,
+                       int64_t ldb, int w, int ncols) {
+    if (w <= 0 || ncols <= 0) return 0;
+    if (ncols <= 1024) return launch_trsm_cc<T, 1>(h, st, Lp, ldl, Bp, ldb, w, ncols);
+    return launch_trsm_cc<T, 4>(h, st, Lp, ldl, Bp, ldb, w, ncols);
 }
 
 // FP64 Schur update on DMMA.  Tile configurations (B200LU_OPT_GEMM_CFG):
@@ -302,6 +310,8 @@ static int launch_panel_cluster_cfg(b200lu_handle* h, cudaStream_t st, PanelArgs
     static bool attr_set = false;
     if (!attr_set) {
         CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)pcl_tile_bytes<T, W, RPT, PCL_NT>()));
         attr_set = true;
     }
     int G = 1;
@@ -311,7 +321,7 @@ static int launch_panel_cluster_cfg(b200lu_handle* h, cudaStream_t st, PanelArgs
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G);
     cfg.blockDim = dim3(PCL_NT);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = pcl_tile_bytes<T, W, RPT, PCL_NT>();
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -442,16 +452,22 @@ static int getrf_device(b200lu_handle* h, T* A, int64_t lda, int n) {
         const int j1 = j0 + jb;
         const LaswpPlan* plan = h->d_plans + k;
         if (la) CU_TRY(h, cudaStreamWaitEvent(sm, h->ev_panel[k], 0));
-        rc = launch_laswp<T>(h, sm, A, lda, 0, j0, plan);
-        if (rc) return rc;
-        rc = launch_laswp<T>(h, sm, A, lda, j1, n, plan);
-        if (rc) return rc;
-        rc = launch_laswp<int>(h, sm, h->d_perm, n, 0, 1, plan);
-        if (rc) return rc;
-        if (j1 >= n) break;
+        const int jb2 = std::min(nb, n - j1);
+        // interchanges: the next panel's columns first (they gate the look-ahead), the rest
+        // of the matrix after the next panel has been handed to the panel stream
+        if (j1 < n) {
+            rc = launch_laswp<T>(h, sm, A, lda, j1, j1 + jb2, plan);
+            if (rc) return rc;
+        }
+        if (j1 >= n) {
+            rc = launch_laswp<T>(h, sm, A, lda, 0, j0, plan);
+            if (rc) return rc;
+            rc = launch_laswp<int>(h, sm, h->d_perm, n, 0, 1, plan);
+            if (rc) return rc;
+            break;
+        }
         T* L11 = A + (int64_t)j0 * lda + j0;
         T* L21 = A + (int64_t)j0 * lda + j1;
-        const int jb2 = std::min(nb, n - j1);
         // next panel's columns first (look-ahead)
         rc = launch_trsm<T>(h, sm, L11, lda, A + (int64_t)j1 * lda + j0, lda, jb, jb2);
         if (rc) return rc;
@@ -467,8 +483,14 @@ static int getrf_device(b200lu_handle* h, T* A, int64_t lda, int n) {
         laswp_plan_kernel<<<1, 2 * LASWP_MAXSW, 0, sp>>>(h->d_ipiv, j1, jb2, h->d_plans + (k + 1));
         LAUNCH_CHECK(h);
         if (la) CU_TRY(h, cudaEventRecord(h->ev_panel[k + 1], sp));
-        // rest of the trailing matrix
+        // the remaining interchanges of panel k, then the rest of the trailing matrix
+        rc = launch_laswp<T>(h, sm, A, lda, 0, j0, plan);
+        if (rc) return rc;
+        rc = launch_laswp<int>(h, sm, h->d_perm, n, 0, 1, plan);
+        if (rc) return rc;
         const int c2 = j1 + jb2;
+        rc = launch_laswp<T>(h, sm, A, lda, c2, n, plan);
+        if (rc) return rc;
         if (c2 < n) {
             rc = launch_trsm<T>(h, sm, L11, lda, A + (int64_t)c2 * lda + j0, lda, jb, n - c2);
             if (rc) return rc;

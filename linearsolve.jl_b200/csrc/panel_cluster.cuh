@@ -25,16 +25,19 @@
 // "top row" message of panel.cuh.  The interchanges of the other columns of the outer panel are
 // applied at the end by the same cluster as one gather/scatter of the <= 2W rows that moved.
 //
-// Latency economy.  In-kernel clock64 stamps of the first versions showed the exchange wait at
-// only ~500 of ~4300 cycles per column; the rest was dependent chains of slow instructions in
-// warps that all sit in the same phase (2 warps per scheduler: nothing hides latency).  So:
-//  * U = 8 columns are unrolled with static register indices, registers rotate by U once per 8
-//    columns, "column already factored" is one warp-uniform branch per chunk of 8 elements;
-//  * arg-max = ONE redux on the top 32 bits + a ballot; ties on the top word (rare) take the
-//    exact slow path;
-//  * 1/pivot is computed by every candidate lane while the redux is in flight;
-//  * software pipelining: the next column's element is updated first and its arg-max issued
-//    before the rest of the rank-1 update.
+// Instruction economy.  In-kernel clock64 stamps and ncu stall sampling of the first versions
+// showed the exchange wait at only ~400 of ~4300 cycles per column: the rest was instruction
+// issue (register rotation, per-element predicates, PHI moves around a switch) and instruction
+// cache misses of an unrolled column loop, in warps that all sit in the same phase.  So:
+//  * LEFT-SHIFTING LIVE WINDOW: a finished column leaves the registers at once (its multipliers
+//    go to a shared-memory tile), and the rank-1 update writes element c to index c - 1, so the
+//    current column is always register 0 with static indices in a ROLLED loop: no rotation, no
+//    per-element predicate (dead elements compute garbage that is never read);
+//  * four copies of the loop body with 32/24/16/8 live elements bound the wasted FMAs;
+//  * a pivot row is frozen when chosen: its warp copies the staged row into the tile;
+//  * arg-max = ONE redux on the top 32 bits + a ballot (ties on the top word take the exact slow
+//    path); the next column's arg-max is in flight under the rest of the rank-1 update;
+//  * 1/pivot is computed by every candidate lane while the redux is in flight.
 #pragma once
 #include "common.cuh"
 #include "panel.cuh"
@@ -135,7 +138,7 @@ struct PclShared {
     static constexpr int EPV = 16 / (int)sizeof(T);
     static constexpr int NV = W / EPV;
     ulonglong2 box[2][PCL_GMAX][1 + NV];   // inbox: one message {header, row} per source CTA
-    T stage[NW][W];                        // per-warp candidate rows
+    T stage[NW][W];                        // per-warp candidate rows (coordinates of their column)
     T s_top[W];                            // zero/NaN-pivot path only
     T s_val[NW];
     int s_pos[NW];
@@ -144,89 +147,36 @@ struct PclShared {
     int s_nmv;
     int s_has_top;
 };
+template <typename T, int W, int RPT, int NT>
+constexpr size_t pcl_tile_bytes() { return (size_t)W * NT * RPT * sizeof(T); }
 
-// rotate the row registers left by U
-template <typename T, int W, int RPT, int U>
-__device__ __forceinline__ void pcl_rotate(T (&a)[RPT][W]) {
-#pragma unroll
-    for (int q = 0; q < RPT; ++q) {
-        T t[U];
-#pragma unroll
-        for (int e = 0; e < U; ++e) t[e] = a[q][e];
-#pragma unroll
-        for (int e = 0; e + U < W; ++e) a[q][e] = a[q][e + U];
-#pragma unroll
-        for (int e = 0; e < U; ++e) a[q][W - U + e] = t[e];
-    }
-}
-
-// local candidate of the column held at register index E: strict '>' from amax = 0 (NaN never
+// local candidate of the current column (register index 0): strict '>' from amax = 0 (NaN never
 // wins), lowest position on ties; rows at positions < j are finished
-template <typename T, int W, int RPT, int E>
+template <typename T, int W, int RPT>
 __device__ __forceinline__ void pcl_local_cand(const T (&a)[RPT][W], const int (&pos)[RPT], int j, T& best, int& bpos) {
     best = T(0);
     bpos = INT_MAX;
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
         if (pos[q] >= j && pos[q] != INT_MAX) {
-            const T v = tabs(a[q][E]);
+            const T v = tabs(a[q][0]);
             if (v > best || (v == best && v > T(0) && pos[q] < bpos)) { best = v; bpos = pos[q]; }
         }
     }
 }
 
-// The parts of one column that need STATIC register indices (JJ = index of the column inside
-// the current group of U).  Part A: scale, update of the NEXT column, its local candidate.
-// Part B (runs while the warp arg-max of the next column is in flight): the rest of the rank-1
-// update, and the rotation after the last column of a group.
-template <typename T, int W, int RPT, int U, int JJ>
-__device__ __forceinline__ void pcl_core_a(T (&a)[RPT][W], const int (&pos)[RPT], const bool (&upd)[RPT],
-                                           const T* __restrict__ prow, T rinv, bool scale, int ech, int j,
-                                           T& best, int& bpos) {
-#pragma unroll
-    for (int q = 0; q < RPT; ++q)
-        if (upd[q] && scale) a[q][JJ] *= rinv;
-    if (JJ + 1 < U || ech > 1) {   // index U is live unless this is the last group
-        const T pr = prow[JJ + 1];
-#pragma unroll
-        for (int q = 0; q < RPT; ++q)
-            if (upd[q]) a[q][JJ + 1] = tfma(-a[q][JJ], pr, a[q][JJ + 1]);
-    }
-    pcl_local_cand<T, W, RPT, JJ + 1>(a, pos, j + 1, best, bpos);
-}
-template <typename T, int W, int RPT, int U, int JJ>
-__device__ __forceinline__ void pcl_core_b(T (&a)[RPT][W], const bool (&upd)[RPT], const T* __restrict__ prow, int ech) {
-    constexpr int NCH = W / U;
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-        if (k < ech) {   // warp-uniform: chunk k still holds unfactored columns
-            T pr[U];
-#pragma unroll
-            for (int e = 0; e < U; ++e) pr[e] = prow[k * U + e];
-#pragma unroll
-            for (int q = 0; q < RPT; ++q) {
-                if (upd[q]) {
-#pragma unroll
-                    for (int e = 0; e < U; ++e)
-                        if (k * U + e > JJ + 1) a[q][k * U + e] = tfma(-a[q][JJ], pr[e], a[q][k * U + e]);
-                }
-            }
-        }
-    }
-    if (JJ + 1 == U) pcl_rotate<T, W, RPT, U>(a);
-}
-
 template <typename T, int W, int RPT, int NT>
 __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
     constexpr int NW = NT / 32;
-    constexpr int U = PCL_U;
     constexpr int EPV = 16 / (int)sizeof(T);       // elements per 16-byte vector
     constexpr int NV = W / EPV;                    // vectors per row
-    constexpr int NIT = W / U;
-    static_assert(U == 8 && W % U == 0 && U % EPV == 0 && W >= 2 * U, "unroll granularity");
+    constexpr int ROWS = NT * RPT;                 // rows of one CTA
+    static_assert(W % 8 == 0 && W <= 32, "live-window steps of 8");
     static_assert(NT / PCL_GMAX >= NV, "one sender thread per (destination, row vector)");
-    static_assert(NW <= 32 && W <= 32 && 2 * W <= NT, "warp-level bookkeeping");
+    static_assert(NW <= 32 && 2 * W <= NT, "warp-level bookkeeping");
     __shared__ __align__(16) PclShared<T, W, RPT, NT> sh;
+    extern __shared__ __align__(16) unsigned char pcl_dyn[];
+    T* tile = reinterpret_cast<T*>(pcl_dyn);       // tile[c * ROWS + local row]: finished entries
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -245,12 +195,12 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
     const bool dbg = p.dbg != nullptr && me == 0 && tid == 0;
     if (dbg) p.dbg[0] = clock64();
 
-    T a[RPT][W];
+    T a[RPT][W];   // a[q][c]: column (j + c) of row q while column j is being eliminated
     int ri[RPT];   // panel-local ORIGINAL row of each owned row (where it is loaded from)
     int pos[RPT];  // its current position in the LAPACK row order
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
-        ri[q] = me * (NT * RPT) + q * NT + tid;
+        ri[q] = me * ROWS + q * NT + tid;
         pos[q] = ri[q] < p.m ? ri[q] : INT_MAX;   // padding rows are never candidates
         const T* src = p.A + (long long)p.j0 * p.lda + (p.j0 + (ri[q] < p.m ? ri[q] : 0));
 #pragma unroll
@@ -278,12 +228,9 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
     long long tprev = clock64();
 #endif
 
-    // Register layout: during group `it` register index e holds column (e + U*it) mod W, so the
-    // U columns of the group sit at the static indices 0..U-1; elements e >= W - U*it are
-    // columns factored in earlier groups (their L multipliers) and are left alone.
     T best;
     int bpos, wl;
-    pcl_local_cand<T, W, RPT, 0>(a, pos, 0, best, bpos);
+    pcl_local_cand<T, W, RPT>(a, pos, 0, best, bpos);
     wl = pcl_warp_argmax(best, bpos);
     if (lane == wl) {
 #pragma unroll
@@ -294,170 +241,201 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
             }
         }
     }
-    // The column loop is ROLLED: one copy of the exchange code (an unrolled loop ran out of the
-    // 32 KB instruction cache — "no instruction" was the top stall reason); only the register
-    // part is selected by a switch on the column's index inside its group.  Pass j eliminates
-    // column j (j >= 0) and then publishes the candidates of column j + 1.
+
+    // publish the candidates of column jn (row staged by the caller in that column's coordinates)
+#define PCL_PUBLISH(jn)                                                                              \
+    {                                                                                                \
+        const int par_ = (jn) & 1;                                                                   \
+        if (lane == wl) { sh.s_val[warp] = best; sh.s_pos[warp] = bpos; }                            \
+        if (wl < 0 && lane == 0) { sh.s_val[warp] = T(0); sh.s_pos[warp] = INT_MAX; }                \
+        const int nv_ = (W - (jn) + EPV - 1) / EPV;   /* live row vectors of that column */          \
+        if (tid == 0) pcl_mbar_expect_tx(pcl_smem_u32(&sh.mbar[par_]), (unsigned)(G * (1 + nv_)) * 16u); \
+        PCL_T(0);                                                                                    \
+        __syncthreads();                                                                             \
+        const T cv_ = lane < NW ? sh.s_val[lane] : T(0);                                             \
+        const int cpos_ = lane < NW ? sh.s_pos[lane] : INT_MAX;                                      \
+        int cw_ = pcl_warp_argmax(cv_, cpos_);                                                       \
+        const int cp_ = cw_ < 0 ? INT_MAX : __shfl_sync(0xffffffffu, cpos_, cw_);                    \
+        if (cw_ < 0) cw_ = 0;                                                                        \
+        const unsigned rb_ = rbar0 + (unsigned)par_ * 8u;                                            \
+        if (s_k < nv_) {                                                                             \
+            const ulonglong2 v_ = reinterpret_cast<const ulonglong2*>(&sh.stage[cw_][0])[s_k];       \
+            pcl_st_async_v2(raddr0 + (unsigned)par_ * BOXB, v_.x, v_.y, rb_);                        \
+        }                                                                                            \
+        if (s_k == 0) pcl_st_async_v2(rhdr0 + (unsigned)par_ * BOXB, (unsigned long long)(unsigned)cp_, 0ull, rb_); \
+        PCL_T(1);                                                                                    \
+    }
+
+    // one column with LIVE live register elements (a[q][0 .. LIVE-1])
+#define PCL_COLUMN(LIVE)                                                                             \
+    {                                                                                                \
+        const int par = j & 1;                                                                       \
+        PCL_T(5);                                                                                    \
+        if (!pcl_mbar_wait(pcl_smem_u32(&sh.mbar[par]), (unsigned)(j >> 1) & 1u)) {                  \
+            atomicExch(p.deverr, DEV_ERR_PANEL_TIMEOUT);                                             \
+            return;                                                                                  \
+        }                                                                                            \
+        PCL_T(2);                                                                                    \
+        /* every warp picks the winner among the G candidates; each candidate lane also computes */  \
+        /* the reciprocal of its own value under the redux latency                               */  \
+        T gval = T(1), gv = T(0);                                                                    \
+        int gpos = INT_MAX;                                                                          \
+        if (lane < G) {                                                                              \
+            gpos = (int)(unsigned)sh.box[par][lane][0].x;                                            \
+            const T v0_ = reinterpret_cast<const T*>(&sh.box[par][lane][1])[0];                      \
+            if (gpos != INT_MAX) { gval = v0_; gv = tabs(v0_); }                                     \
+        }                                                                                            \
+        const unsigned gkey = pcl_argmax_key(gv);                                                    \
+        const unsigned gmax = pcl_argmax_issue(gkey);                                                \
+        T rinv = T(1) / gval;                                                                        \
+        const int gl = pcl_argmax_finish(gv, gpos, gkey, gmax);                                      \
+        const bool none = gl < 0;  /* all-zero (or all-NaN) subcolumn: kp = k */                     \
+        const int gsel = none ? 0 : gl;                                                              \
+        rinv = __shfl_sync(0xffffffffu, rinv, gsel);                                                 \
+        const int piv = none ? j : __shfl_sync(0xffffffffu, gpos, gsel);                             \
+        const T* prow = reinterpret_cast<const T*>(&sh.box[par][gsel][1]);                           \
+        bool scale = true;                                                                           \
+        if (none) PCL_NONE_PATH()                                                                    \
+        PCL_T(3);                                                                                    \
+        if (me == 0 && tid == 0) p.ipiv[p.j0 + j] = p.j0 + piv;                                      \
+        /* the pivot row is frozen: its warp copies the staged row (pivot, U entries) to the tile */ \
+        {                                                                                            \
+            int own = -1;                                                                            \
+            _Pragma("unroll") for (int q = 0; q < RPT; ++q) if (pos[q] == piv) own = q * NT + tid;   \
+            const unsigned ob = __ballot_sync(0xffffffffu, own >= 0);                                \
+            if (ob) {                                                                                \
+                const int orow = __shfl_sync(0xffffffffu, own, __ffs(ob) - 1);                       \
+                const T* srow = none ? sh.s_top : &sh.stage[warp][0];                                \
+                if (lane < W - j && lane < W) tile[(j + lane) * ROWS + orow] = srow[lane];           \
+            }                                                                                        \
+        }                                                                                            \
+        /* positions, multipliers */                                                                 \
+        _Pragma("unroll") for (int q = 0; q < RPT; ++q) {                                            \
+            if (pos[q] == piv) pos[q] = j;            /* the pivot row: finished */                  \
+            else if (pos[q] == j) pos[q] = piv;       /* the displaced top row stays active */       \
+            const bool upd = pos[q] > j && pos[q] != INT_MAX;                                        \
+            if (scale) a[q][0] *= rinv;               /* garbage in frozen rows is never read */     \
+            if (upd) tile[j * ROWS + q * NT + tid] = a[q][0];                                        \
+        }                                                                                            \
+        /* next column first, so that its arg-max is in flight under the rest of the update */       \
+        {                                                                                            \
+            const T pr1 = prow[1];                                                                   \
+            _Pragma("unroll") for (int q = 0; q < RPT; ++q) a[q][1] = tfma(-a[q][0], pr1, a[q][1]);  \
+        }                                                                                            \
+        best = T(0);                                                                                 \
+        bpos = INT_MAX;                                                                              \
+        _Pragma("unroll") for (int q = 0; q < RPT; ++q) {                                            \
+            if (pos[q] >= j + 1 && pos[q] != INT_MAX) {                                              \
+                const T v = tabs(a[q][1]);                                                           \
+                if (v > best || (v == best && v > T(0) && pos[q] < bpos)) { best = v; bpos = pos[q]; } \
+            }                                                                                        \
+        }                                                                                            \
+        const unsigned akey = pcl_argmax_key(best);                                                  \
+        const unsigned amax = pcl_argmax_issue(akey);          /* in flight under the update */      \
+        _Pragma("unroll") for (int q = 0; q < RPT; ++q) {                                            \
+            const T nl = -a[q][0];                                                                   \
+            a[q][0] = a[q][1];                                                                       \
+            _Pragma("unroll") for (int c = 2; c < (LIVE); ++c) a[q][c - 1] = tfma(nl, prow[c], a[q][c]); \
+        }                                                                                            \
+        if (warp == 0 && piv != j) PCL_BOOKKEEP()                                                    \
+        wl = pcl_argmax_finish(best, bpos, akey, amax);                                              \
+        if (lane == wl) {   /* stage the row in the coordinates of column j + 1 */                   \
+            _Pragma("unroll") for (int q = 0; q < RPT; ++q) {                                        \
+                if (pos[q] == bpos) {                                                                \
+                    _Pragma("unroll") for (int c = 0; c < (LIVE) - 1; ++c) sh.stage[warp][c] = a[q][c]; \
+                }                                                                                    \
+            }                                                                                        \
+        }                                                                                            \
+        PCL_T(4);                                                                                    \
+        if (j + 1 < wc) PCL_PUBLISH(j + 1)                                                           \
+    }
+
+#define PCL_NONE_PATH()                                                                              \
+    {   /* the pivot row is the row at position j: its owner hands it to every CTA (rare path) */    \
+        _Pragma("unroll") for (int q = 0; q < RPT; ++q) {                                            \
+            if (pos[q] == j) {                                                                       \
+                _Pragma("unroll") for (int c = 0; c < W; ++c) sh.s_top[c] = a[q][c];                 \
+                sh.s_has_top = 1;                                                                    \
+            }                                                                                        \
+        }                                                                                            \
+        __syncthreads();                                                                             \
+        if (sh.s_has_top) {                                                                          \
+            for (int i = tid; i < G * W; i += NT) {                                                  \
+                const int d = i / W, c = i - d * W;                                                  \
+                if (d == me) continue;                                                               \
+                const unsigned ra = pcl_mapa(pcl_smem_u32(&sh.s_top[c]), (unsigned)d);               \
+                if constexpr (sizeof(T) == 8)                                                        \
+                    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(sh.s_top[c]) : "memory"); \
+                else                                                                                 \
+                    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(sh.s_top[c]) : "memory"); \
+            }                                                                                        \
+        }                                                                                            \
+        pcl_cluster_sync();                                                                          \
+        if (tid == 0) sh.s_has_top = 0;                                                              \
+        prow = sh.s_top;                                                                             \
+        const T pv = prow[0];                                                                        \
+        scale = (pv != T(0));                                                                        \
+        rinv = T(1) / pv;                                                                            \
+        if (me == 0 && tid == 0 && pv == T(0) && *p.info == 0) *p.info = p.j0 + j + 1;               \
+    }
+
+#define PCL_BOOKKEEP()                                                                               \
+    {   /* interchange of positions j and piv */                                                     \
+        const int sj = __shfl_sync(0xffffffffu, top_src, j);                                         \
+        if (piv < W) {                                                                               \
+            const int sp = __shfl_sync(0xffffffffu, top_src, piv);                                   \
+            if (lane == j) top_src = sp;                                                             \
+            if (lane == piv) top_src = sj;                                                           \
+        } else {                                                                                     \
+            const unsigned hit = __ballot_sync(0xffffffffu, ext_row == piv);                         \
+            int e;                                                                                   \
+            if (hit) e = __ffs(hit) - 1;                                                             \
+            else {                                                                                   \
+                e = ext_n++;                                                                         \
+                if (lane == e) { ext_row = piv; ext_src = piv; }                                     \
+            }                                                                                        \
+            const int sp = __shfl_sync(0xffffffffu, ext_src, e);                                     \
+            if (lane == j) top_src = sp;                                                             \
+            if (lane == e) ext_src = sj;                                                             \
+        }                                                                                            \
+    }
+
+    PCL_PUBLISH(0)
+    // Four copies of the rolled column loop: the live window shrinks by one element per column,
+    // the copies bound the dead elements a column still computes on to < 8.
+    int j = 0;
+    if constexpr (W >= 32) {
 #pragma unroll 1
-    for (int j = -1; j < wc; ++j) {
-        if (j >= 0) {
-            const int jj = j & (U - 1), it = j / U;
-            const int par = j & 1;
-            const int ech = NIT - it;            // chunks of U elements that still hold live columns
-            PCL_T(5);
-            if (!pcl_mbar_wait(pcl_smem_u32(&sh.mbar[par]), (unsigned)(j >> 1) & 1u)) {
-                atomicExch(p.deverr, DEV_ERR_PANEL_TIMEOUT);
-                return;
-            }
-            PCL_T(2);
-            // every warp picks the winner among the G candidates; each candidate lane also
-            // computes the reciprocal of its own value under the redux latency
-            T gval = T(1), gv = T(0);
-            int gpos = INT_MAX;
-            if (lane < G) {
-                gpos = (int)(unsigned)sh.box[par][lane][0].x;
-                if (gpos != INT_MAX) { gval = reinterpret_cast<const T*>(&sh.box[par][lane][1])[jj]; gv = tabs(gval); }
-            }
-            const int gl = pcl_warp_argmax(gv, gpos);
-            T rinv = T(1) / gval;
-            const bool none = gl < 0;  // all-zero (or all-NaN) subcolumn: kp = k
-            const int gsel = none ? 0 : gl;
-            rinv = __shfl_sync(0xffffffffu, rinv, gsel);
-            const int piv = none ? j : __shfl_sync(0xffffffffu, gpos, gsel);
-            const T* prow = reinterpret_cast<const T*>(&sh.box[par][gsel][1]);
-            bool scale = true;
-            if (none) {
-                // the pivot row is the row at position j: its owner hands it to every CTA (rare path)
-#pragma unroll
-                for (int q = 0; q < RPT; ++q) {
-                    if (pos[q] == j) {
-#pragma unroll
-                        for (int c = 0; c < W; ++c) sh.s_top[c] = a[q][c];
-                        sh.s_has_top = 1;
-                    }
-                }
-                __syncthreads();
-                if (sh.s_has_top) {
-                    // element-wise remote stores to the OTHER CTAs; a rolled loop keeps this path small
-                    for (int i = tid; i < G * W; i += NT) {
-                        const int d = i / W, c = i - d * W;
-                        if (d == me) continue;
-                        const unsigned ra = pcl_mapa(pcl_smem_u32(&sh.s_top[c]), (unsigned)d);
-                        if constexpr (sizeof(T) == 8)
-                            asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(sh.s_top[c]) : "memory");
-                        else
-                            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(sh.s_top[c]) : "memory");
-                    }
-                }
-                pcl_cluster_sync();
-                if (tid == 0) sh.s_has_top = 0;
-                prow = sh.s_top;
-                const T pv = prow[jj];
-                scale = (pv != T(0));
-                rinv = T(1) / pv;
-                if (me == 0 && tid == 0 && pv == T(0) && *p.info == 0) *p.info = p.j0 + j + 1;
-            }
-            PCL_T(3);
-            if (me == 0 && tid == 0) p.ipiv[p.j0 + j] = p.j0 + piv;
-            // positions
-            bool upd[RPT];
-#pragma unroll
-            for (int q = 0; q < RPT; ++q) {
-                if (pos[q] == piv) pos[q] = j;            // the pivot row: finished
-                else if (pos[q] == j) pos[q] = piv;       // the displaced top row stays active
-                upd[q] = pos[q] > j && pos[q] != INT_MAX;
-            }
-#define PCL_CASES(FN, ...)                                              \
-    switch (jj) {                                                       \
-        case 0: FN<T, W, RPT, U, 0>(__VA_ARGS__); break;                \
-        case 1: FN<T, W, RPT, U, 1>(__VA_ARGS__); break;                \
-        case 2: FN<T, W, RPT, U, 2>(__VA_ARGS__); break;                \
-        case 3: FN<T, W, RPT, U, 3>(__VA_ARGS__); break;                \
-        case 4: FN<T, W, RPT, U, 4>(__VA_ARGS__); break;                \
-        case 5: FN<T, W, RPT, U, 5>(__VA_ARGS__); break;                \
-        case 6: FN<T, W, RPT, U, 6>(__VA_ARGS__); break;                \
-        default: FN<T, W, RPT, U, 7>(__VA_ARGS__); break;               \
+        for (; j < wc && j < W - 24; ++j) PCL_COLUMN(W)
     }
-            PCL_CASES(pcl_core_a, a, pos, upd, prow, rinv, scale, ech, j, best, bpos)
-            const unsigned akey = pcl_argmax_key(best);
-            const unsigned amax = pcl_argmax_issue(akey);          // in flight under part B
-            PCL_CASES(pcl_core_b, a, upd, prow, ech)
-#undef PCL_CASES
-            wl = pcl_argmax_finish(best, bpos, akey, amax);
-            if (lane == wl) {   // stage the whole row (already in the coordinates of column j + 1)
-#pragma unroll
-                for (int q = 0; q < RPT; ++q) {
-                    if (pos[q] == bpos) {
-#pragma unroll
-                        for (int c = 0; c < W; ++c) sh.stage[warp][c] = a[q][c];
-                    }
-                }
-            }
-            if (warp == 0 && piv != j) {  // interchange of positions j and piv
-                const int sj = __shfl_sync(0xffffffffu, top_src, j);
-                if (piv < W) {
-                    const int sp = __shfl_sync(0xffffffffu, top_src, piv);
-                    if (lane == j) top_src = sp;
-                    if (lane == piv) top_src = sj;
-                } else {
-                    const unsigned hit = __ballot_sync(0xffffffffu, ext_row == piv);
-                    int e;
-                    if (hit) e = __ffs(hit) - 1;
-                    else {
-                        e = ext_n++;
-                        if (lane == e) { ext_row = piv; ext_src = piv; }
-                    }
-                    const int sp = __shfl_sync(0xffffffffu, ext_src, e);
-                    if (lane == j) top_src = sp;
-                    if (lane == e) ext_src = sj;
-                }
-            }
-            PCL_T(4);
-        }
-        // ---- publish the candidates of column jn = j + 1 (staged above / in the prologue) ----
-        const int jn = j + 1;
-        if (jn < wc) {
-            const int jjn = jn & (U - 1), itn = jn / U;
-            const int par = jn & 1;
-            if (lane == wl) { sh.s_val[warp] = best; sh.s_pos[warp] = bpos; }
-            if (wl < 0 && lane == 0) { sh.s_val[warp] = T(0); sh.s_pos[warp] = INT_MAX; }
-            const int vmax = (NIT - itn) * (U / EPV);   // live row vectors of that group
-            const int v0 = jjn / EPV;
-            if (tid == 0) pcl_mbar_expect_tx(pcl_smem_u32(&sh.mbar[par]), (unsigned)(G * (1 + vmax - v0)) * 16u);
-            PCL_T(0);
-            __syncthreads();
-            const T cv = lane < NW ? sh.s_val[lane] : T(0);
-            const int cpos = lane < NW ? sh.s_pos[lane] : INT_MAX;
-            int cw = pcl_warp_argmax(cv, cpos);
-            const int cp = cw < 0 ? INT_MAX : __shfl_sync(0xffffffffu, cpos, cw);
-            if (cw < 0) cw = 0;
-            const unsigned rb = rbar0 + (unsigned)par * 8u;
-            if (s_k >= v0 && s_k < vmax) {
-                const ulonglong2 v = reinterpret_cast<const ulonglong2*>(&sh.stage[cw][0])[s_k];
-                pcl_st_async_v2(raddr0 + (unsigned)par * BOXB, v.x, v.y, rb);
-            }
-            if (s_k == 0) pcl_st_async_v2(rhdr0 + (unsigned)par * BOXB, (unsigned long long)(unsigned)cp, 0ull, rb);
-            PCL_T(1);
-        }
-    }
-    // ragged block: bring the registers back to natural order (a group rotates only after its
-    // last column, which a short block never reaches)
-    {
-        int rots = (NIT - wc / U) % NIT;
+    if constexpr (W >= 24) {
 #pragma unroll 1
-        for (; rots > 0; --rots) pcl_rotate<T, W, RPT, U>(a);
+        for (; j < wc && j < W - 16; ++j) PCL_COLUMN(W >= 32 ? 24 : W)
     }
+    if constexpr (W >= 16) {
+#pragma unroll 1
+        for (; j < wc && j < W - 8; ++j) PCL_COLUMN(W >= 24 ? 16 : W)
+    }
+#pragma unroll 1
+    for (; j < wc; ++j) PCL_COLUMN(W >= 16 ? 8 : W)
+#undef PCL_COLUMN
+#undef PCL_PUBLISH
+#undef PCL_NONE_PATH
+#undef PCL_BOOKKEEP
     if (dbg) p.dbg[2] = clock64();
 #ifdef PCL_TIMING
     if (dbg) for (int i = 0; i < 6; ++i) p.dbg[8 + i] = tacc[i];
 #endif
-    // write the block back, every row at its final position
+    // every finished entry of this CTA's rows now sits in the tile: write the block back, every
+    // row at its final position
+    __syncthreads();
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
-        T* dst = p.A + (long long)p.j0 * p.lda + (p.j0 + (ri[q] < p.m ? pos[q] : 0));
-#pragma unroll
-        for (int c = 0; c < W; ++c) {
-            if (ri[q] < p.m && c < wc) dst[(long long)c * p.lda] = a[q][c];
+        if (ri[q] < p.m) {
+            T* dst = p.A + (long long)p.j0 * p.lda + (p.j0 + pos[q]);
+            const T* srcT = tile + q * NT + tid;
+#pragma unroll 8
+            for (int c = 0; c < wc; ++c) dst[(long long)c * p.lda] = srcT[c * ROWS];
         }
     }
     if (dbg) p.dbg[3] = clock64();
