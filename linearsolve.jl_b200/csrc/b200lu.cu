@@ -92,6 +92,7 @@ struct b200lu_handle {
     void* dB_LU = nullptr;
     int* dB_ipiv = nullptr;
     int* dB_info = nullptr;
+    int* dB_perm = nullptr;    // batched: original row that ends at each position (for getrs)
     void* dB_in = nullptr;     // host-path staging for A
     int64_t b_cap_in = 0;
     void* dB_rhs = nullptr;
@@ -827,7 +828,7 @@ void b200lu_destroy(b200lu_handle* h) {
     free_dev(h->d_info); free_dev(h->d_deverr); free_dev(h->d_plans); free_dev(h->d_panelsync);
     free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_wL); free_dev(h->d_wU); free_dev(h->d_tflags); free_dev(h->d_tticket);
     free_dev(h->d_B); free_dev(h->d_X); free_dev(h->d_r); free_dev(h->d_r32); free_dev(h->d_scal);
-    free_dev(h->dB_LU); free_dev(h->dB_ipiv); free_dev(h->dB_info); free_dev(h->dB_in);
+    free_dev(h->dB_LU); free_dev(h->dB_ipiv); free_dev(h->dB_info); free_dev(h->dB_perm); free_dev(h->dB_in);
     free_dev(h->dB_rhs); free_dev(h->dB_x);
     if (h->h_ipiv) cudaFreeHost(h->h_ipiv);
     if (h->h_small) cudaFreeHost(h->h_small);
@@ -1173,6 +1174,8 @@ static int ensure_batched(b200lu_handle* h, int64_t batch, int64_t n) {
         CU_TRY(h, cudaStreamSynchronize(h->s_main));
         free_dev(h->dB_ipiv);
         free_dev(h->dB_info);
+        free_dev(h->dB_perm);
+        CU_TRY(h, cudaMalloc((void**)&h->dB_perm, (size_t)(batch * n) * sizeof(int)));
         CU_TRY(h, cudaMalloc((void**)&h->dB_ipiv, (size_t)(batch * n) * sizeof(int)));
         CU_TRY(h, cudaMalloc((void**)&h->dB_info, (size_t)(batch * n) * sizeof(int)));
         h->b_cap_batch_n = batch * n;
@@ -1189,11 +1192,11 @@ static int batched_factor_launch(b200lu_handle* h, const T* A, int64_t lda, int6
     T* LU = (T*)h->dB_LU;
     cudaStream_t st = h->s_main;
     if (n <= 16)
-        getrf_batched_kernel<T, 16><<<(unsigned)batch, 32, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_info, n);
+        getrf_batched_kernel<T, 16><<<(unsigned)batch, 32, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_perm, h->dB_info, n);
     else if (n <= 32)
-        getrf_batched_kernel<T, 32><<<(unsigned)batch, 32, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_info, n);
+        getrf_batched_kernel<T, 32><<<(unsigned)batch, 32, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_perm, h->dB_info, n);
     else
-        getrf_batched_kernel<T, 64><<<(unsigned)batch, 64, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_info, n);
+        getrf_batched_kernel<T, 64><<<(unsigned)batch, 64, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_perm, h->dB_info, n);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -1205,12 +1208,19 @@ static int batched_solve_launch(b200lu_handle* h, int nrhs, const T* B, int64_t 
     const int64_t batch = h->b_batch;
     const T* LU = (const T*)h->dB_LU;
     cudaStream_t st = h->s_main;
-    if (n <= 16)
-        getrs_batched_kernel<T, 16><<<(unsigned)batch, 32, 0, st>>>(LU, n, (int64_t)n * n, h->dB_ipiv, B, ldb, strideB, X, ldx, strideX, n, nrhs);
-    else if (n <= 32)
-        getrs_batched_kernel<T, 32><<<(unsigned)batch, 32, 0, st>>>(LU, n, (int64_t)n * n, h->dB_ipiv, B, ldb, strideB, X, ldx, strideX, n, nrhs);
-    else
-        getrs_batched_kernel<T, 64><<<(unsigned)batch, 64, 0, st>>>(LU, n, (int64_t)n * n, h->dB_ipiv, B, ldb, strideB, X, ldx, strideX, n, nrhs);
+    // WPC systems (warps) per CTA: about 32 KB of staged factors per CTA
+#define GETRS_B(NMAXV, WPCV)                                                                      \
+    {                                                                                             \
+        const size_t smem = (size_t)(WPCV) * (NMAXV) * (NMAXV) * sizeof(T);                        \
+        const unsigned grid = (unsigned)((batch + (WPCV) - 1) / (WPCV));                           \
+        getrs_batched_kernel<T, NMAXV, WPCV><<<grid, 32 * (WPCV), smem, st>>>(                     \
+            LU, n, (int64_t)n * n, h->dB_perm, B, ldb, strideB, X, ldx, strideX, n, nrhs, batch);  \
+    }
+    if (n <= 16) GETRS_B(16, 8)
+    else if (n <= 32) GETRS_B(32, 4)
+    else if (sizeof(T) == 4) GETRS_B(64, 2)
+    else GETRS_B(64, 1)
+#undef GETRS_B
     LAUNCH_CHECK(h);
     return 0;
 }

@@ -3,14 +3,22 @@
 // (ext/LinearSolveBlockDiagonalsExt.jl:119-125,183-205).  Pivot/info semantics
 // as src/blocked_lufact.jl:38-54,58-90.
 //
-// HBM-bound (read A once, write LU once).  B200 mapping: one CTA of NMAX threads
-// per system, thread t holds ROW t in registers for the whole factorization;
-// rows never move — each thread tracks the logical position of its row
-// (implicit permutation), the pivot row tail is broadcast through shared
-// memory, the pivot search is a warp-shuffle arg-max (lowest position on ties).
+// HBM-bound in the limit (read A once, write LU once: 66,816 bytes per 64x64 FP64
+// system).  B200 mapping of getrf: one CTA of max(32, NMAX) threads per system, thread t
+// holds ROW t in registers; rows never move (each thread tracks the logical position of
+// its row, the LAPACK interchange sequence acts on positions).  Same instruction economy
+// as the cluster panel kernel (panel_cluster.cuh): LEFT-SHIFTING LIVE WINDOW — the rank-1
+// update writes element c to register c - 1, so the current column is always register 0 in
+// a ROLLED loop (no 64-fold unrolled body that overflows the instruction cache, no
+// per-element predicates); finished entries (multipliers, frozen pivot rows) go to a
+// shared-memory tile that is written out once, permuted, fully coalesced; one barrier
+// per column (each warp publishes its candidate row, every thread picks the winner).
+// getrs: one warp per system, the packed LU staged in shared memory with cp.async, the
+// substitution chains run on warp shuffles (no barriers); the row permutation is the
+// `perm` vector the factorization leaves behind.
 #pragma once
 #include "common.cuh"
-#include "panel.cuh"  // warp_argmax
+#include "panel_cluster.cuh"  // pcl_warp_argmax
 #include <limits.h>
 
 namespace b200lu {
@@ -18,150 +26,211 @@ namespace b200lu {
 __host__ __device__ constexpr int batched_threads(int nmax) { return nmax < 32 ? 32 : nmax; }
 
 template <typename T, int NMAX>
+struct BatchedShared {
+    static constexpr int NW = (NMAX + 31) / 32;
+    T tile[NMAX * NMAX];          // finished entry (row t, column c) at c * NMAX + ((t + c) % NMAX):
+                                  // the skew makes row-wise AND column-wise warp accesses conflict-free
+    T cand_row[2][NW][NMAX];      // per-warp candidate rows, double-buffered by column parity
+    T cand_val[2][NW];
+    T cand_rinv[2][NW];           // 1 / candidate value, computed by the candidate lane
+    int cand_pos[2][NW];
+    int cand_thr[2][NW];
+    int red[NW];
+};
+
+// A: batch systems, column-major n x n (lda, strideA).  LU: packed n x n (ldlu = n).
+// ipiv: 0-based LAPACK interchange sequence per system; perm[sys*n + p] = original row that
+// ends at position p (for getrs); info: 0 or 1-based first zero pivot.
+template <typename T, int NMAX>
 __global__ void __launch_bounds__(batched_threads(NMAX)) getrf_batched_kernel(
     const T* __restrict__ A, long long lda, long long strideA, T* __restrict__ LU,
-    long long ldlu, long long strideLU, int* __restrict__ ipiv, int* __restrict__ info, int n) {
-    constexpr int NW = (NMAX + 31) / 32;  // blockDim.x == max(32, NMAX): lanes >= NMAX are padding rows
-    constexpr int NPAD = NMAX < 2 ? 2 : NMAX;
-    // double-buffered by step parity so one barrier per exchange suffices
-    __shared__ __align__(16) T s_row[2][NPAD];
-    __shared__ T s_val[2][NW];
-    __shared__ int s_pos[2][NW];
-    __shared__ int s_thr[2][NW];
+    long long ldlu, long long strideLU, int* __restrict__ ipiv, int* __restrict__ perm,
+    int* __restrict__ info, int n) {
+    constexpr int NW = (NMAX + 31) / 32;
+    __shared__ __align__(16) BatchedShared<T, NMAX> sh;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long sys = blockIdx.x;
     const T* Ab = A + sys * strideA;
 
-    T a[NMAX];
+    T a[NMAX];   // a[c]: column (k + c) of my row while column k is being eliminated
 #pragma unroll
-    for (int c = 0; c < NMAX; ++c)
-        a[c] = (t < n && c < n) ? Ab[(long long)c * lda + t] : (t == c ? T(1) : T(0));
-    int pos = t;        // logical row position of this thread's row (t >= n: never a candidate)
-    bool done = false;  // row already used as a pivot row
+    for (int c = 0; c < NMAX; ++c) a[c] = (t < n && c < n) ? Ab[(long long)c * lda + t] : T(0);
+    int pos = t < n ? t : INT_MAX;   // logical position of my row; padding rows never compete
+    bool done = t >= n;              // row already used as a pivot row (frozen)
     int myinfo = 0;
 
-#pragma unroll
-    for (int k = 0; k < NMAX; ++k) {
-        if (k < n) {
-            const int par = k & 1;
-            // pivot search: |a| max over the rows not yet used, lowest position on ties
-            T best = T(0);
-            int bp = INT_MAX;
-            if (!done && t < n) {
-                const T v = tabs(a[k]);
-                if (v > best) { best = v; bp = pos; }
-            }
-            int wl;
-            warp_argmax(best, bp, wl);
-            int bt = warp * 32 + wl;   // thread holding the warp's winner (unused when none)
-            if (NW > 1) {
-                if (lane == 0) { s_val[par][warp] = best; s_pos[par][warp] = bp; s_thr[par][warp] = bt; }
-                __syncthreads();
-                best = s_val[par][0]; bp = s_pos[par][0]; bt = s_thr[par][0];
-#pragma unroll
-                for (int w = 1; w < NW; ++w) {
-                    const T ob = s_val[par][w];
-                    const int op = s_pos[par][w];
-                    if (ob > best || (ob == best && op < bp)) { best = ob; bp = op; bt = s_thr[par][w]; }
-                }
-            }
-            // all-zero / all-NaN subcolumn: kp = k, the row at position k is the "pivot" row
-            const bool none = !(best > T(0));
-            const bool i_am_piv = none ? (pos == k && !done) : (t == bt);
-            if (i_am_piv) {
-#pragma unroll
-                for (int c = k; c < NMAX; ++c) s_row[par][c] = a[c];
-            }
-            __syncthreads();
-            const T pv = s_row[par][k];
-            const int ppos = none ? k : bp;
-            if (i_am_piv) {
-                // this row lands at position k; whoever sat at k takes my old position
-                done = true;
-                pos = k;
-                ipiv[sys * n + k] = ppos;
-                if (pv == T(0) && myinfo == 0) myinfo = k + 1;
-            } else if (!done && pos == k) {
-                pos = ppos;
-            }
-            if (!done && t < n) {
-                T l = a[k];
-                if (pv != T(0)) l *= (T(1) / pv);
-                a[k] = l;
-#pragma unroll
-                for (int c = k + 1; c < NMAX; ++c) a[c] = tfma(-l, s_row[par][c], a[c]);
-            }
-        }
+#define B200_BATCHED_COLUMN(LIVE)                                                                  \
+    {                                                                                              \
+        const int par = k & 1;                                                                     \
+        /* pivot search: |a| max over the rows not yet used, lowest position on ties */            \
+        const T v = done ? T(0) : tabs(a[0]);                                                      \
+        const int wl = pcl_warp_argmax(v, pos);                                                    \
+        if (lane == wl) {                                                                          \
+            _Pragma("unroll") for (int c = 0; c < (LIVE); ++c) sh.cand_row[par][warp][c] = a[c];   \
+            sh.cand_val[par][warp] = v;                                                            \
+            sh.cand_rinv[par][warp] = T(1) / a[0];   /* off the other threads' critical path */    \
+            sh.cand_pos[par][warp] = pos;                                                          \
+            sh.cand_thr[par][warp] = t;                                                            \
+        }                                                                                          \
+        if (wl < 0 && lane == 0) { sh.cand_val[par][warp] = T(0); sh.cand_pos[par][warp] = INT_MAX; } \
+        if (NW > 1) __syncthreads(); else __syncwarp();                                            \
+        int bw = 0;                                                                                \
+        T bv = sh.cand_val[par][0];                                                                \
+        int bp = sh.cand_pos[par][0];                                                              \
+        _Pragma("unroll") for (int w = 1; w < NW; ++w) {                                           \
+            const T ov = sh.cand_val[par][w];                                                      \
+            const int op = sh.cand_pos[par][w];                                                    \
+            if (ov > bv || (ov == bv && op < bp)) { bv = ov; bp = op; bw = w; }                    \
+        }                                                                                          \
+        const bool none = !(bv > T(0));   /* all-zero / all-NaN subcolumn: kp = k */               \
+        if (none) {                                                                                \
+            /* the "pivot" row is the row at position k: a second, rare exchange */                \
+            if (NW > 1) __syncthreads(); else __syncwarp();                                        \
+            if (!done && pos == k) {                                                               \
+                _Pragma("unroll") for (int c = 0; c < (LIVE); ++c) sh.cand_row[par][0][c] = a[c];  \
+                sh.cand_thr[par][0] = t;                                                           \
+                sh.cand_rinv[par][0] = T(1) / a[0];                                                \
+            }                                                                                      \
+            if (NW > 1) __syncthreads(); else __syncwarp();                                        \
+            bw = 0;                                                                                \
+            bp = k;                                                                                \
+        }                                                                                          \
+        const T* prow = &sh.cand_row[par][bw][0];                                                  \
+        const int pthr = sh.cand_thr[par][bw];                                                     \
+        const T pv = prow[0];                                                                      \
+        /* the pivot row is frozen: all threads copy its staged entries into the tile */           \
+        if (t < n - k) sh.tile[(k + t) * NMAX + ((pthr + k + t) & (NMAX - 1))] = prow[t];                                   \
+        if (t == pthr) {                                                                           \
+            done = true;                                                                           \
+            pos = k;                                                                               \
+            ipiv[sys * n + k] = bp;                                                                \
+            if (pv == T(0) && myinfo == 0) myinfo = k + 1;                                         \
+        } else if (!done && pos == k) {                                                            \
+            pos = bp;                                                                              \
+        }                                                                                          \
+        /* multiplier and rank-1 update, shifted one register to the left (frozen and padding */   \
+        /* rows compute garbage that is never read)                                           */   \
+        T l = a[0];                                                                                \
+        if (pv != T(0)) l *= sh.cand_rinv[par][bw];                                                        \
+        if (!done) sh.tile[k * NMAX + ((t + k) & (NMAX - 1))] = l;                                                      \
+        const T nl = -l;                                                                           \
+        _Pragma("unroll") for (int c = 1; c < (LIVE); ++c) a[c - 1] = tfma(nl, prow[c], a[c]);     \
     }
+
+    int k = 0;
+    // copies of the rolled column loop with 64/56/.../8 live elements bound the dead elements
+    // a column still computes on to < 8
+#define B200_BATCHED_PHASE(LIVE)                                        \
+    if constexpr (NMAX >= (LIVE)) {                                     \
+        _Pragma("unroll 1") for (; k < n && k <= NMAX - ((LIVE) - 7); ++k) B200_BATCHED_COLUMN(LIVE) \
+    }
+    B200_BATCHED_PHASE(64)
+    B200_BATCHED_PHASE(56)
+    B200_BATCHED_PHASE(48)
+    B200_BATCHED_PHASE(40)
+    B200_BATCHED_PHASE(32)
+    B200_BATCHED_PHASE(24)
+    B200_BATCHED_PHASE(16)
+    B200_BATCHED_PHASE(8)
+#undef B200_BATCHED_PHASE
+#undef B200_BATCHED_COLUMN
+
     // first zero pivot over the system (each pivot thread saw at most one)
     {
         int v = myinfo ? myinfo : INT_MAX;
         v = __reduce_min_sync(0xffffffffu, v);
+        if (lane == 0) sh.red[warp] = v;
         __syncthreads();
-        if (NW > 1) {
-            if (lane == 0) s_pos[0][warp] = v;
-            __syncthreads();
-            v = s_pos[0][0];
+        v = sh.red[0];
 #pragma unroll
-            for (int w = 1; w < NW; ++w) v = min(v, s_pos[0][w]);
-        }
+        for (int w = 1; w < NW; ++w) v = min(v, sh.red[w]);
         if (t == 0) info[sys] = (v == INT_MAX) ? 0 : v;
     }
+    // every entry of row t is in the tile now: write it at its final position
     if (t < n) {
-        T* Lb = LU + sys * strideLU;
-#pragma unroll
-        for (int c = 0; c < NMAX; ++c)
-            if (c < n) Lb[(long long)c * ldlu + pos] = a[c];
+        T* Lb = LU + sys * strideLU + pos;
+        perm[sys * n + pos] = t;
+#pragma unroll 8
+        for (int c = 0; c < n; ++c) Lb[(long long)c * ldlu] = sh.tile[c * NMAX + ((t + c) & (NMAX - 1))];
     }
 }
 
 // getrs on the cached batched factors: X = U \ (L \ (P B)), nrhs columns.
-// One CTA of NMAX threads per system; thread t holds row t of the packed LU.
-template <typename T, int NMAX>
-__global__ void __launch_bounds__(batched_threads(NMAX)) getrs_batched_kernel(
-    const T* __restrict__ LU, long long ldlu, long long strideLU, const int* __restrict__ ipiv,
+// One warp per system (lane l holds rows l and l + 32); the packed LU is staged in shared
+// memory; the substitution chains run on shuffles.  WPC systems per CTA.
+template <typename T, int NMAX, int WPC>
+__global__ void __launch_bounds__(32 * WPC) getrs_batched_kernel(
+    const T* __restrict__ LU, long long ldlu, long long strideLU, const int* __restrict__ perm,
     const T* __restrict__ B, long long ldb, long long strideB, T* __restrict__ X, long long ldx,
-    long long strideX, int n, int nrhs) {
-    __shared__ T s_b[batched_threads(NMAX)];
-    __shared__ int s_perm[batched_threads(NMAX)];
-    const int t = threadIdx.x;
-    const long long sys = blockIdx.x;
+    long long strideX, int n, int nrhs, long long batch) {
+    constexpr int RPL = (NMAX + 31) / 32;
+    extern __shared__ __align__(16) unsigned char getrs_b_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long sys = (long long)blockIdx.x * WPC + warp;
+    if (sys >= batch) return;
+    T* s_lu = reinterpret_cast<T*>(getrs_b_smem) + (size_t)warp * NMAX * NMAX;   // packed, ld = n
     const T* Lb = LU + sys * strideLU;
-    T a[NMAX];
-#pragma unroll
-    for (int c = 0; c < NMAX; ++c) a[c] = (t < n && c < n) ? Lb[(long long)c * ldlu + t] : T(0);
-    s_perm[t] = t;
-    __syncthreads();
-    if (t == 0) {
-        for (int k = 0; k < n; ++k) {
-            const int p = ipiv[sys * n + k];
-            if (p != k) { int tmp = s_perm[k]; s_perm[k] = s_perm[p]; s_perm[p] = tmp; }
+    {
+        // packed n x n block: 16-byte chunks when the block is 16-byte sized and aligned
+        const int total = n * n;
+        constexpr int EPV = 16 / (int)sizeof(T);
+        if (ldlu == n && (total % EPV) == 0 && ((strideLU * (long long)sizeof(T)) % 16) == 0) {
+            for (int i = lane * EPV; i < total; i += 32 * EPV) cp_async16(s_lu + i, Lb + i, true);
+            cp_async_commit();
+            cp_async_wait<0>();
+        } else {
+            for (int i = lane; i < total; i += 32) {
+                const int c = i / n, r = i - c * n;
+                s_lu[i] = Lb[(long long)c * ldlu + r];
+            }
         }
+        __syncwarp();
     }
-    __syncthreads();
-    const int src = s_perm[t];
-    for (int r = 0; r < nrhs; ++r) {
-        T b = (t < n) ? B[sys * strideB + (long long)r * ldb + src] : T(0);
+    int src[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int row = r * 32 + lane;
+        src[r] = row < n ? perm[sys * n + row] : 0;
+    }
+    for (int rhs = 0; rhs < nrhs; ++rhs) {
+        T b[RPL];
+#pragma unroll
+        for (int r = 0; r < RPL; ++r)
+            b[r] = (r * 32 + lane < n) ? B[sys * strideB + (long long)rhs * ldb + src[r]] : T(0);
         // forward: unit lower, column oriented
 #pragma unroll
-        for (int k = 0; k < NMAX; ++k) {
-            if (k < n) {
-                if (t == k) s_b[k] = b;
-                __syncthreads();
-                if (t > k) b = tfma(-a[k], s_b[k], b);
+        for (int kr = 0; kr < RPL; ++kr) {
+            const int kend = min(32, n - kr * 32);
+#pragma unroll 4
+            for (int kk = 0; kk < kend; ++kk) {
+                const int k = kr * 32 + kk;
+                const T xk = __shfl_sync(0xffffffffu, b[kr], kk);
+#pragma unroll
+                for (int r = kr; r < RPL; ++r) {
+                    const int row = r * 32 + lane;
+                    if (row > k && row < n) b[r] = tfma(-s_lu[k * n + row], xk, b[r]);
+                }
             }
         }
         // backward: upper, divide by the diagonal (vector right-hand side form)
 #pragma unroll
-        for (int k = NMAX - 1; k >= 0; --k) {
-            if (k < n) {
-                if (t == k) { b = b / a[k]; s_b[k] = b; }
-                __syncthreads();
-                if (t < k) b = tfma(-a[k], s_b[k], b);
+        for (int kr = RPL - 1; kr >= 0; --kr) {
+            const int kend = min(32, n - kr * 32);
+#pragma unroll 4
+            for (int kk = kend - 1; kk >= 0; --kk) {
+                const int k = kr * 32 + kk;
+                if (lane == kk) b[kr] = b[kr] / s_lu[k * n + k];
+                const T xk = __shfl_sync(0xffffffffu, b[kr], kk);
+#pragma unroll
+                for (int r = 0; r <= kr; ++r) {
+                    const int row = r * 32 + lane;
+                    if (row < k) b[r] = tfma(-s_lu[k * n + row], xk, b[r]);
+                }
             }
         }
-        if (t < n) X[sys * strideX + (long long)r * ldx + t] = b;
-        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RPL; ++r)
+            if (r * 32 + lane < n) X[sys * strideX + (long long)rhs * ldx + r * 32 + lane] = b[r];
     }
 }
 
