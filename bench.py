@@ -48,6 +48,7 @@ def parse():
     p.add_argument("--rpt", type=int, default=-1)
     p.add_argument("--gemm-cfg", type=int, default=-1)
     p.add_argument("--panel-mode", type=int, default=-1)
+    p.add_argument("--sgemm-mode", type=int, default=-1)
     return p.parse_args()
 
 
@@ -194,6 +195,8 @@ def main():
         h.set_option(C.OPT_GEMM_CFG, args.gemm_cfg)
     if args.panel_mode >= 0:
         h.set_option(C.OPT_PANEL_MODE, args.panel_mode)
+    if args.sgemm_mode >= 0:
+        h.set_option(C.OPT_SGEMM_MODE, args.sgemm_mode)
 
     if args.workload == "batched":
         return bench_batched(args, ls, h, torch, dev, rank, world, barrier, max_over_ranks)

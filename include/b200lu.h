@@ -102,7 +102,9 @@ enum {
     B200LU_OPT_GEMM_CFG = 7,    /* FP64 trailing-update tile configuration 0..2      */
     B200LU_OPT_PANEL_MODE = 8,  /* base panel: 0 auto (cluster/DSMEM kernel when the panel fits
                                    16 CTAs, else L2 mailbox), 1 always L2 mailbox  */
-    B200LU_OPT_COUNT = 9
+    B200LU_OPT_SGEMM_MODE = 9,  /* FP32 trailing update: 0 auto (tcgen05 3xTF32 kernel for large
+                                   updates, FFMA otherwise), 1 always FFMA          */
+    B200LU_OPT_COUNT = 10
 };
 
 /* library/ABI version: major*10000 + minor*100 + patch */
@@ -123,6 +125,11 @@ void b200lu_destroy(b200lu_handle* h);
 const char* b200lu_last_error(const b200lu_handle* h);
 double b200lu_last_timing(const b200lu_handle* h, int phase);
 double b200lu_last_counter(const b200lu_handle* h, int which);
+/* test hook: C -= A * B on DEVICE pointers with the handle's trailing-update kernel (column-major;
+   element type = the handle's factor type).  Mirrors the reference's `_blocked_lu_schur!`
+   (src/blocked_lufact.jl:186-620) so the kernel can be checked against a plain FP32/FP64 matmul. */
+int b200lu_debug_gemm_sub(b200lu_handle* h, int64_t M, int64_t N, int64_t K, const void* dA, int64_t lda,
+                          const void* dB, int64_t ldb, void* dC, int64_t ldc);
 int b200lu_probe_peak(b200lu_handle* h, int kind, double* out);
 int b200lu_set_option(b200lu_handle* h, int option, int64_t value);
 int64_t b200lu_get_option(const b200lu_handle* h, int option);

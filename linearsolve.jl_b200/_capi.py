@@ -18,14 +18,14 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libb200lu.so")
 
 F64, F32, MIXED = 0, 1, 2
 T_H2D, T_FACTOR, T_SOLVE, T_D2H, T_GEMM = range(5)
-OPT_NB, OPT_LOOKAHEAD, OPT_REFINE_MAXIT, OPT_PANEL_CTAS, OPT_SOLVE_NRHS_TILE, OPT_PROFILE, OPT_PANEL_RPT, OPT_GEMM_CFG, OPT_PANEL_MODE = range(9)
+OPT_NB, OPT_LOOKAHEAD, OPT_REFINE_MAXIT, OPT_PANEL_CTAS, OPT_SOLVE_NRHS_TILE, OPT_PROFILE, OPT_PANEL_RPT, OPT_GEMM_CFG, OPT_PANEL_MODE, OPT_SGEMM_MODE = range(10)
 C_GEMM_FLOPS, C_GEMM_LAUNCHES, C_REFINE_ITERS = range(3)
 PEAK_FP64_DMMA, PEAK_FP64_DFMA, PEAK_HBM_COPY = range(3)
 
 # every symbol include/b200lu.h declares (tests check the export list against this)
 SYMBOLS = [
     "b200lu_version", "b200lu_launch_count", "b200lu_create", "b200lu_destroy",
-    "b200lu_last_error", "b200lu_last_timing", "b200lu_last_counter", "b200lu_probe_peak",
+    "b200lu_last_error", "b200lu_last_timing", "b200lu_last_counter", "b200lu_probe_peak", "b200lu_debug_gemm_sub",
     "b200lu_set_option", "b200lu_get_option",
     "b200lu_factor", "b200lu_solve", "b200lu_factor_device", "b200lu_solve_device",
     "b200lu_get_factors", "b200lu_get_ipiv",
@@ -67,6 +67,7 @@ def load():
     P("b200lu_last_timing", cd, [vp, ci])
     P("b200lu_last_counter", cd, [vp, ci])
     P("b200lu_probe_peak", ci, [vp, ci, ctypes.POINTER(cd)])
+    P("b200lu_debug_gemm_sub", ci, [vp, i64, i64, i64, vp, i64, vp, i64, vp, i64])
     P("b200lu_set_option", ci, [vp, ci, i64])
     P("b200lu_get_option", i64, [vp, ci])
     P("b200lu_factor", ci, [vp, i64, vp, i64, vp, pi64])
@@ -153,6 +154,10 @@ class Handle:
 
     def counter(self, which):
         return float(self.lib.b200lu_last_counter(self._h, which))
+
+    def debug_gemm_sub(self, M, N, K, dA, lda, dB, ldb, dC, ldc):
+        """C -= A @ B on device pointers with the handle's trailing-update kernel (test hook)."""
+        self._check(self.lib.b200lu_debug_gemm_sub(self._h, M, N, K, dA, lda, dB, ldb, dC, ldc))
 
     def probe_peak(self, kind):
         out = ctypes.c_double(0.0)

@@ -19,6 +19,7 @@
 #include "batched.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
+#include "gemm_tc.cuh"
 #include "laswp.cuh"
 #include "panel.cuh"
 #include "panel_cluster.cuh"
@@ -56,6 +57,8 @@ struct b200lu_handle {
     LaswpPlan* d_plans = nullptr;
     int cap_plans = 0;
     void* d_panelsync = nullptr;
+    float* d_split = nullptr;      // tcgen05 SGEMM: hi/lo TF32 splits of the current L21 and U12
+    int64_t cap_split_n = 0;
     long long* d_pdbg = nullptr;   // B200LU_PANEL_DBG=1: clock64 stamps of the cluster panel launches
     int pdbg_n = 0;
     unsigned panel_epoch = 0;
@@ -260,13 +263,96 @@ static int launch_gemm(b200lu_handle* h, cudaStream_t st, int M, int N, int K, c
         default: return launch_dgemm_cfg<128, 64, 2, 2, 3, 2>(h, st, M, N, K, A, lda, B, ldb, C, ldc);
     }
 }
-static int launch_gemm(b200lu_handle* h, cudaStream_t st, int M, int N, int K, const float* A,
-                       int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc) {
-    if (M <= 0 || N <= 0 || K <= 0) return 0;
+// ---- FP32: tcgen05 (TMA + TMEM) 3xTF32 kernel for the large updates, FFMA kernel otherwise ----
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled get_tmap_encode() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)p;
+    }
+    return fn;
+}
+// 2-D FP32 tensor map: dim0 = rows (contiguous), dim1 = cols (stride ld), 128-byte swizzle
+static int make_tmap_2d(b200lu_handle* h, CUtensorMap* m, const float* base, int64_t rows, int64_t cols,
+                        int64_t ld, int box0, int box1) {
+    PFN_tmapEncodeTiled enc = get_tmap_encode();
+    if (!enc) return set_err(h, 1, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(h, 1, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+static int ensure_split(b200lu_handle* h, int64_t n) {
+    if (n <= h->cap_split_n) return 0;
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    free_dev(h->d_split);
+    const int64_t n32 = ((n + 31) / 32) * 32;
+    // A_hi, A_lo: n32 x 256 each; B_hi, B_lo: 256 x n each
+    CU_TRY(h, cudaMalloc((void**)&h->d_split, (size_t)(2 * n32 * 256 + 2 * 256 * n32) * sizeof(float)));
+    h->cap_split_n = n;
+    return 0;
+}
+static int launch_sgemm_tc(b200lu_handle* h, cudaStream_t st, int M, int N, int K, const float* A,
+                           int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc) {
+    const int64_t need = std::max(M, N);
+    int rc = ensure_split(h, std::max<int64_t>(need, h->n));
+    if (rc) return rc;
+    const int64_t n32 = ((h->cap_split_n + 31) / 32) * 32;
+    float* Ahi = h->d_split;
+    float* Alo = Ahi + n32 * 256;
+    float* Bhi = Alo + n32 * 256;
+    float* Blo = Bhi + 256 * n32;
+    const int64_t lst = 256;   // both splits are stored K-major with a fixed leading dimension of 256
+    split_tf32_transpose_kernel<<<dim3(cdiv(M, 32), cdiv(K, 32)), 256, 0, st>>>(A, lda, Ahi, Alo, lst, M, K);
+    LAUNCH_CHECK(h);
+    split_tf32_kernel<<<dim3(cdiv(K, 1024), N), 256, 0, st>>>(B, ldb, Bhi, Blo, lst, K, N);
+    LAUNCH_CHECK(h);
+    CUtensorMap tAhi, tAlo, tBhi, tBlo;
+    if ((rc = make_tmap_2d(h, &tAhi, Ahi, K, M, lst, TC_BK, TC_BM))) return rc;
+    if ((rc = make_tmap_2d(h, &tAlo, Alo, K, M, lst, TC_BK, TC_BM))) return rc;
+    if ((rc = make_tmap_2d(h, &tBhi, Bhi, K, N, lst, TC_BK, TC_BN))) return rc;
+    if ((rc = make_tmap_2d(h, &tBlo, Blo, K, N, lst, TC_BK, TC_BN))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU_TRY(h, cudaFuncSetAttribute(sgemm3x_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    TcGemmParams p{C, ldc, M, N, K, h->d_deverr};
+    sgemm3x_tc_kernel<<<dim3(cdiv(M, TC_BM), cdiv(N, TC_BN)), TC_THREADS, TC_SMEM_BYTES, st>>>(tAhi, tAlo, tBhi, tBlo, p);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+static int launch_sgemm_ffma(b200lu_handle* h, cudaStream_t st, int M, int N, int K, const float* A,
+                             int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc) {
     dim3 grid(cdiv(M, 128), cdiv(N, 128));
     sgemm_sub_kernel<128, 128, 8><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc);
     LAUNCH_CHECK(h);
     return 0;
+}
+static int launch_gemm(b200lu_handle* h, cudaStream_t st, int M, int N, int K, const float* A,
+                       int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    // The tcgen05 path owns one scratch set: main-stream updates only (the panel recursion's small
+    // GEMMs run concurrently on the panel stream); K <= 256 by construction (K = panel width).
+    const int64_t mode = h->opt[B200LU_OPT_SGEMM_MODE];   // 0 auto, 1 FFMA, 2 tcgen05 whenever legal (tests)
+    const bool tc = mode != 1 && st == h->s_main && K <= 256 && (ldc % 4) == 0 &&
+                    (mode == 2 || (int64_t)M * N >= (int64_t)512 * 512);
+    if (tc) return launch_sgemm_tc(h, st, M, N, K, A, lda, B, ldb, C, ldc);
+    return launch_sgemm_ffma(h, st, M, N, K, A, lda, B, ldb, C, ldc);
 }
 
 // trailing-update GEMM, optionally bracketed by events for the in-situ roofline
@@ -779,6 +865,7 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     h->opt[B200LU_OPT_PANEL_RPT] = 0;
     h->opt[B200LU_OPT_GEMM_CFG] = 0;
     h->opt[B200LU_OPT_PANEL_MODE] = 0;
+    h->opt[B200LU_OPT_SGEMM_MODE] = 0;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) == cudaSuccess;
@@ -825,7 +912,7 @@ void b200lu_destroy(b200lu_handle* h) {
         cudaFree(h->d_pdbg);
     }
     free_dev(h->dA); free_dev(h->dA64); free_dev(h->d_ipiv); free_dev(h->d_perm);
-    free_dev(h->d_info); free_dev(h->d_deverr); free_dev(h->d_plans); free_dev(h->d_panelsync);
+    free_dev(h->d_info); free_dev(h->d_deverr); free_dev(h->d_plans); free_dev(h->d_panelsync); free_dev(h->d_split);
     free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_wL); free_dev(h->d_wU); free_dev(h->d_tflags); free_dev(h->d_tticket);
     free_dev(h->d_B); free_dev(h->d_X); free_dev(h->d_r); free_dev(h->d_r32); free_dev(h->d_scal);
     free_dev(h->dB_LU); free_dev(h->dB_ipiv); free_dev(h->dB_info); free_dev(h->dB_perm); free_dev(h->dB_in);
@@ -856,6 +943,38 @@ double b200lu_last_counter(const b200lu_handle* h, int which) {
     if (!h || which < 0 || which >= B200LU_C_COUNT) return -1.0;
     if (which == B200LU_C_REFINE_ITERS) return (double)h->last_refine_iters;
     return h->counters[which];
+}
+
+int b200lu_debug_gemm_sub(b200lu_handle* h, int64_t M, int64_t N, int64_t K, const void* dA, int64_t lda,
+                          const void* dB, int64_t ldb, void* dC, int64_t ldc) {
+    if (!h) return -1;
+    if (M < 0 || N < 0 || K < 0 || !dA || !dB || !dC) return set_err(h, -2, "bad gemm arguments");
+    CU_TRY(h, cudaSetDevice(h->dev));
+    int rc;
+    if (h->dtype == B200LU_F64)
+        rc = launch_gemm(h, h->s_main, (int)M, (int)N, (int)K, (const double*)dA, lda, (const double*)dB, ldb, (double*)dC, ldc);
+    else
+        rc = launch_gemm(h, h->s_main, (int)M, (int)N, (int)K, (const float*)dA, lda, (const float*)dB, ldb, (float*)dC, ldc);
+    if (rc) return rc;
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    int de = 0;
+    CU_TRY(h, cudaMemcpy(&de, h->d_deverr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (de) return set_err(h, 1, "device-side error %d in gemm", de);
+#ifdef TC_DEBUG
+    if (h->dtype != B200LU_F64) {
+        float dbg[1024];
+        cudaMemcpyFromSymbol(dbg, g_tc_dbg, sizeof(dbg));
+        const char* nm[4] = {"A_hi", "A_lo", "B_hi", "B_lo"};
+        for (int t = 0; t < 4; ++t) {
+            fprintf(stderr, "[tcdbg] %s:", nm[t]);
+            for (int i = 0; i < 40; ++i) fprintf(stderr, " %g", dbg[t * 64 + i]);
+            fprintf(stderr, "\n");
+        }
+        for (int qq = 0; qq < 4; ++qq) { fprintf(stderr, "[tcdbg] D lane %d:", 32 * qq); for (int i = 0; i < 8; ++i) fprintf(stderr, " %g", dbg[256 + qq * 8 + i]); fprintf(stderr, "\n"); }
+        unsigned tm; memcpy(&tm, &dbg[300], 4); fprintf(stderr, "\n[tcdbg] tmem base 0x%x\n", tm);
+    }
+#endif
+    return 0;
 }
 
 int b200lu_probe_peak(b200lu_handle* h, int kind, double* out) {
@@ -919,6 +1038,7 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_PANEL_RPT && (value < 0 || value > 2)) return -3;
     if (option == B200LU_OPT_GEMM_CFG && (value < 0 || value > 2)) return -3;
     if (option == B200LU_OPT_PANEL_MODE && (value < 0 || value > 1)) return -3;
+    if (option == B200LU_OPT_SGEMM_MODE && (value < 0 || value > 2)) return -3;
     h->opt[option] = value;
     return 0;
 }

@@ -18,6 +18,7 @@ enum DevErr : int {
     DEV_OK = 0,
     DEV_ERR_PANEL_TIMEOUT = 1,
     DEV_ERR_TRSV_TIMEOUT = 2,
+    DEV_ERR_GEMM_TIMEOUT = 3,
 };
 
 // ~2 s at 1.9 GHz: a spin loop that runs this long means a lost CTA, not work.

@@ -1,0 +1,318 @@
+// gemm_tc.cuh — FP32 trailing-matrix update C -= A * B on the 5th-generation tensor cores:
+// tcgen05.mma kind::tf32 issued by one thread, operands staged in shared memory by TMA
+// (cp.async.bulk.tensor, 128-byte swizzle), accumulator in TMEM, read back with tcgen05.ld.
+// (reference `_blocked_lu_schur!`, src/blocked_lufact.jl:186-620 — the FP32 instantiation that
+// the *32MixedLUFactorization algorithms factor with, src/openblas.jl:470-543.)
+//
+// FP32 accuracy from TF32 tensor cores: error-compensated 3xTF32.  Every operand x is split
+// once, in a bandwidth-trivial pre-pass over the panel, into hi = rn_tf32(x) and
+// lo = rn_tf32(x - hi) (both exactly representable, so the tensor core's truncation to TF32 is
+// exact), and the product is accumulated as  A_hi*B_lo + A_lo*B_hi + A_hi*B_hi  in the FP32
+// TMEM accumulator (the dropped lo*lo term is 2^-22 relative).
+//
+// Operand layouts: both operands are fed K-major (K contiguous), the canonical UMMA layout.
+//   B = U12 (K x N, K contiguous in the column-major factor matrix) is K-major as it lies;
+//   A = L21 (M x K, M contiguous) is TRANSPOSED by the split pre-pass (measured: an MN-major
+//       32-bit operand under the plain 128-byte swizzle yields zeros — it needs the 32-byte-atom
+//       swizzle variant — so the pre-pass that splits anyway also transposes).
+//   One TMA box {32 (k), rows} per operand lands as `rows` rows of 128 bytes (SBO = 1024 bytes
+//   between groups of 8 rows); a UMMA K-step (8 TF32) advances the start address by 32 bytes.
+// CTA tile 128 x 256 (UMMA M = 128, N = 256, K = 8 per instruction), BK = 32, two stages of
+// 96 KB; warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+// (TMEM -> registers, C += D with D = (-A) B by the instruction descriptor's negate bit).
+#pragma once
+#include <cuda.h>   // CUtensorMap (types only; the encode entry point is fetched at run time)
+#include "common.cuh"
+
+namespace b200lu {
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 2;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;              // 16 KB: one of A_hi / A_lo
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;              // 32 KB: one of B_hi / B_lo
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 96 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;
+
+// hi = rn_tf32(x), lo = rn_tf32(x - hi) for a rows x cols column-major block
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ src, long long lds,
+                                                         float* __restrict__ hi, float* __restrict__ lo,
+                                                         long long ldd, int rows, int cols) {
+    const int r4 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    const int c = blockIdx.y;
+    if (r4 >= rows || c >= cols) return;
+    const float* s = src + (long long)c * lds + r4;
+    float x[4];
+    if (r4 + 3 < rows && ((reinterpret_cast<uintptr_t>(s) & 15) == 0)) {
+        const float4 v = *reinterpret_cast<const float4*>(s);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = (r4 + i < rows) ? s[i] : 0.f;
+    }
+    float h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        unsigned hb, lb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x[i]));
+        h[i] = __uint_as_float(hb);
+        const float d = x[i] - h[i];
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(d));
+        l[i] = __uint_as_float(lb);
+    }
+    float* ph = hi + (long long)c * ldd + r4;
+    float* pl = lo + (long long)c * ldd + r4;
+    if (r4 + 3 < rows) {   // ldd is a multiple of 4 and the scratch base is 16-byte aligned
+        *reinterpret_cast<float4*>(ph) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(pl) = make_float4(l[0], l[1], l[2], l[3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (r4 + i < rows) { ph[i] = h[i]; pl[i] = l[i]; }
+    }
+}
+
+// transposing variant for A: src is rows x cols column-major (rows = M contiguous); hiT/loT are
+// [rows][ldt] with the `cols` (K) values of one row contiguous
+__global__ void __launch_bounds__(256) split_tf32_transpose_kernel(const float* __restrict__ src, long long lds,
+                                                                   float* __restrict__ hiT, float* __restrict__ loT,
+                                                                   long long ldt, int rows, int cols) {
+    __shared__ float th[32][33], tl[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;
+        const float x = (r < rows && c < cols) ? src[(long long)c * lds + r] : 0.f;
+        unsigned hb, lb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+        const float h = __uint_as_float(hb);
+        const float d = x - h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(d));
+        th[ty + 8 * i][tx] = h;
+        tl[ty + 8 * i][tx] = __uint_as_float(lb);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + tx;
+        if (r < rows && c < cols) {
+            hiT[(long long)r * ldt + c] = th[tx][ty + 8 * i];
+            loT[(long long)r * ldt + c] = tl[tx][ty + 8 * i];
+        }
+    }
+}
+
+// ---- PTX wrappers --------------------------------------------------------------------------
+__device__ __forceinline__ unsigned tc_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool tc_mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// returns false on watchdog timeout (a lost TMA / MMA completion would otherwise hang the GPU)
+__device__ __forceinline__ bool tc_mbar_wait(unsigned bar, unsigned parity) {
+    if (tc_mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!tc_mbar_try_wait(bar, parity))
+        if (clock64() - t0 > kSpinTimeoutCycles) return false;
+    return true;
+}
+__device__ __forceinline__ void tc_tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_mma_tf32(unsigned tmem_d, unsigned long long da, unsigned long long db,
+                                            unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// shared-memory matrix descriptor, 128-byte swizzle, Blackwell version field = 1
+__device__ __forceinline__ unsigned long long tc_smem_desc(unsigned addr, unsigned lbo_bytes, unsigned sbo_bytes) {
+    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | ((unsigned long long)(lbo_bytes >> 4) << 16) |
+           ((unsigned long long)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+#ifdef TC_DEBUG
+__device__ float g_tc_dbg[1024];
+#endif
+
+struct TcGemmParams {
+    float* C;
+    long long ldc;
+    int M, N, K;
+    int* deverr;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+sgemm3x_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+                  const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                  TcGemmParams p) {
+    extern __shared__ unsigned char tc_smem_raw[];
+    const unsigned raw = tc_smem_u32(tc_smem_raw);
+    const unsigned base = (raw + 1023u) & ~1023u;            // 128-byte swizzle atoms need 1024-byte alignment
+    unsigned char* gen = tc_smem_raw + (base - raw);
+    // [stage][A_hi | A_lo | B_hi | B_lo] ... then the barriers
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(gen + TC_STAGES * TC_STAGE_BYTES);
+    const unsigned bar_full = tc_smem_u32(&bars[0]);         // [TC_STAGES]
+    const unsigned bar_empty = tc_smem_u32(&bars[TC_STAGES]);   // [TC_STAGES]
+    const unsigned bar_acc = tc_smem_u32(&bars[2 * TC_STAGES]);
+    unsigned* s_tmem = reinterpret_cast<unsigned*>(&bars[2 * TC_STAGES + 1]);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
+    const int KB = (p.K + TC_BK - 1) / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            tc_mbar_init(bar_full + 8 * s, 1);
+            tc_mbar_init(bar_empty + 8 * s, 1);
+        }
+        tc_mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tc_prefetch_tensormap(&tmAhi);
+        tc_prefetch_tensormap(&tmAlo);
+        tc_prefetch_tensormap(&tmBhi);
+        tc_prefetch_tensormap(&tmBlo);
+    }
+    if (warp == 1) {   // TMEM: 256 columns (128 lanes x 256 FP32 accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(s_tmem)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = *s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % TC_STAGES;
+                const unsigned ph = (unsigned)(kb / TC_STAGES) & 1u;
+                if (!tc_mbar_wait(bar_empty + 8 * s, ph ^ 1u)) { atomicExch(p.deverr, DEV_ERR_GEMM_TIMEOUT); break; }
+                const unsigned st = base + s * TC_STAGE_BYTES;
+                tc_mbar_expect_tx(bar_full + 8 * s, (unsigned)TC_STAGE_BYTES);
+                const int k0 = kb * TC_BK;
+                tc_tma_load_2d(st, &tmAhi, k0, m0, bar_full + 8 * s);
+                tc_tma_load_2d(st + TC_A_BYTES, &tmAlo, k0, m0, bar_full + 8 * s);
+                tc_tma_load_2d(st + 2 * TC_A_BYTES, &tmBhi, k0, n0, bar_full + 8 * s);
+                tc_tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmBlo, k0, n0, bar_full + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = TF32, A negated, both K-major, N = 256, M = 128
+            constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) |
+                                       ((unsigned)(TC_BN >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
+            bool ok = true;
+            for (int kb = 0; kb < KB && ok; ++kb) {
+                const int s = kb % TC_STAGES;
+                const unsigned ph = (unsigned)(kb / TC_STAGES) & 1u;
+                ok = tc_mbar_wait(bar_full + 8 * s, ph);
+                if (!ok) { atomicExch(p.deverr, DEV_ERR_GEMM_TIMEOUT); break; }
+                tc_fence_after();
+                const unsigned st = base + s * TC_STAGE_BYTES;
+#ifdef TC_DEBUG
+                if (kb == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+                    const float* sp = reinterpret_cast<const float*>(gen + s * TC_STAGE_BYTES);
+                    for (int i = 0; i < 64; ++i) {
+                        g_tc_dbg[i] = sp[i];                                   // A_hi
+                        g_tc_dbg[64 + i] = sp[TC_A_BYTES / 4 + i];             // A_lo
+                        g_tc_dbg[128 + i] = sp[2 * TC_A_BYTES / 4 + i];        // B_hi
+                        g_tc_dbg[192 + i] = sp[(2 * TC_A_BYTES + TC_B_BYTES) / 4 + i];  // B_lo
+                    }
+                    g_tc_dbg[300] = __uint_as_float(tmem);
+                }
+#endif
+#pragma unroll
+                for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                    const unsigned long long a_hi = tc_smem_desc(st + ks * 32, 16, 1024);
+                    const unsigned long long a_lo = tc_smem_desc(st + TC_A_BYTES + ks * 32, 16, 1024);
+                    const unsigned long long b_hi = tc_smem_desc(st + 2 * TC_A_BYTES + ks * 32, 16, 1024);
+                    const unsigned long long b_lo = tc_smem_desc(st + 2 * TC_A_BYTES + TC_B_BYTES + ks * 32, 16, 1024);
+                    tc_mma_tf32(tmem, a_hi, b_lo, IDESC, (kb | ks) != 0 ? 1u : 0u);
+                    tc_mma_tf32(tmem, a_lo, b_hi, IDESC, 1u);
+                    tc_mma_tf32(tmem, a_hi, b_hi, IDESC, 1u);
+                }
+                tc_commit(bar_empty + 8 * s);   // frees the stage when these MMAs have read it
+            }
+            tc_commit(bar_acc);                 // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int row = m0 + 32 * q + lane;
+#ifdef TC_DEBUG
+        {
+            const unsigned taddr0 = tmem + ((unsigned)(32 * q) << 16);
+            const unsigned pat = __float_as_uint(7.0f + q);
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};\ntcgen05.wait::st.sync.aligned;" ::"r"(taddr0), "r"(pat) : "memory");
+        }
+#endif
+        const bool ok = tc_mbar_wait(bar_acc, 0);
+        if (!ok && lane == 0) atomicExch(p.deverr, DEV_ERR_GEMM_TIMEOUT);
+        tc_fence_after();
+        if (ok) {
+#pragma unroll 1
+            for (int c = 0; c < TC_BN / 32; ++c) {
+                float cv[32];
+                float* cp = p.C + (long long)(n0 + c * 32) * p.ldc + row;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    cv[j] = (row < p.M && n0 + c * 32 + j < p.N) ? cp[(long long)j * p.ldc] : 0.f;
+                unsigned v[32];
+                const unsigned taddr = tmem + ((unsigned)(32 * q) << 16) + (unsigned)(c * 32);
+                // load + wait in ONE asm statement: nothing may read v[] before tcgen05.wait::ld
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                    "tcgen05.wait::ld.sync.aligned;"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+#ifdef TC_DEBUG
+                if (blockIdx.x == 0 && blockIdx.y == 0 && c == 0 && lane == 0)
+                    for (int j = 0; j < 8; ++j) g_tc_dbg[256 + q * 8 + j] = __uint_as_float(v[j]);
+#endif
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (row < p.M && n0 + c * 32 + j < p.N) cp[(long long)j * p.ldc] = cv[j] + __uint_as_float(v[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+    }
+}
+
+}  // namespace b200lu
