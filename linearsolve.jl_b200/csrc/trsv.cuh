@@ -189,7 +189,11 @@ __global__ void __launch_bounds__(256) trsv_block_kernel(const T* __restrict__ A
         for (int u = 0; u < NP; ++u) acc[v][u] = T(0);
     const int ndep = UPPER ? (nblk - 1 - r) : r;   // blocks this row depends on
     const int nfar = ndep > 0 ? ndep - 1 : 0;      // ... all but the adjacent one
-    T an[16];
+    // The far blocks stream through a ring of PF prefetched blocks per thread: with one block in
+    // flight the stream ran at one HBM latency per 32 KB block and the LAST block row (n/64 - 2
+    // blocks) took as long as the whole dependency chain.
+    constexpr int PF = NR == 1 ? ((sizeof(T) == 8) ? 4 : 6) : (NR <= 4 ? 2 : 1);   // register budget: 16 values per block
+    T an[PF][16];
     auto load_blk = [&](int d, T* dst) {
         const int c = UPPER ? (nblk - 1 - d) : d;
         const T* ap = A + (long long)(c * TB + q * 16) * lda + grow;
@@ -199,18 +203,26 @@ __global__ void __launch_bounds__(256) trsv_block_kernel(const T* __restrict__ A
             dst[jj] = (rok && gc < n) ? ap[(long long)jj * lda] : T(0);
         }
     };
-    if (nfar > 0) load_blk(0, an);
-    for (int d = 0; d < nfar; ++d) {
-        T ac[16];
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) ac[jj] = an[jj];
-        if (d + 1 < nfar) load_blk(d + 1, an);
-        gather_x(UPPER ? (nblk - 1 - d) : d);
+    for (int u = 0; u < PF; ++u)
+        if (u < nfar) load_blk(u, an[u]);
+    for (int d0 = 0; d0 < nfar; d0 += PF) {
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj)
+        for (int u = 0; u < PF; ++u) {
+            const int d = d0 + u;
+            if (d < nfar) {
+                T ac[16];
 #pragma unroll
-            for (int v = 0; v < NR; ++v) acc[v][jj % NP] = tfma(ac[jj], s_x[warp][v][jj], acc[v][jj % NP]);
-        __syncwarp();
+                for (int jj = 0; jj < 16; ++jj) ac[jj] = an[u][jj];
+                if (d + PF < nfar) load_blk(d + PF, an[u]);
+                gather_x(UPPER ? (nblk - 1 - d) : d);
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj)
+#pragma unroll
+                    for (int v = 0; v < NR; ++v) acc[v][jj % NP] = tfma(ac[jj], s_x[warp][v][jj], acc[v][jj % NP]);
+                __syncwarp();
+            }
+        }
     }
 #pragma unroll
     for (int v = 0; v < NR; ++v) {

@@ -7,12 +7,12 @@ C = ls._capi
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 what = sys.argv[2] if len(sys.argv) > 2 else "lu"
 dev = torch.device("cuda", 0)
-h = ls.Handle(C.F64)
-if what == "lu":
+h = ls.Handle(C.MIXED if what == "mixed" else C.F64)
+if what in ("lu", "mixed"):
     A = torch.empty((n, n), dtype=torch.float64, device=dev)
     B = torch.empty((16, n), dtype=torch.float64, device=dev)
     X = torch.empty_like(B)
-    h.fill_uniform_device(A.data_ptr(), n, n, n, seed=1)
+    h.fill_uniform_device(A.data_ptr(), n, n, n, seed=1, diag_shift=5.0 if what == "mixed" else 0.0)
     h.fill_uniform_device(B.data_ptr(), n, n, 16, seed=2)
     for _ in range(2):
         h.factor_device(A.data_ptr(), n, n)
