@@ -104,7 +104,9 @@ enum {
                                    16 CTAs, else L2 mailbox), 1 always L2 mailbox  */
     B200LU_OPT_SGEMM_MODE = 9,  /* FP32 trailing update: 0 auto (tcgen05 3xTF32 kernel for large
                                    updates, FFMA otherwise), 1 always FFMA          */
-    B200LU_OPT_COUNT = 10
+    B200LU_OPT_TRSV_MODE = 10,  /* single-RHS getrs: 0 = 2-D work items on a persistent grid,
+                                   1 = one CTA per block row                        */
+    B200LU_OPT_COUNT = 11
 };
 
 /* library/ABI version: major*10000 + minor*100 + patch */

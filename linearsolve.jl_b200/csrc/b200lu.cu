@@ -75,6 +75,13 @@ struct b200lu_handle {
     int cap_tgroups = 0;
     size_t cap_tflag_bytes = 0;
     unsigned trsv_epoch = 0;
+    // single-RHS TRSV v2 (2-D work items)
+    Trsv2Item* d_t2items = nullptr;
+    unsigned long long* d_t2x = nullptr;
+    unsigned long long* d_t2p = nullptr;
+    int* d_t2ticket = nullptr;
+    int t2_nblk = 0, t2_nitems = 0, t2_kmax = 0, t2_grid = 0;
+    unsigned t2_epoch = 0;
     void* d_B = nullptr;       // staging for host solves / permuted rhs
     void* d_X = nullptr;
     int64_t cap_rhs = 0;
@@ -722,6 +729,60 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T
         LAUNCH_CHECK(h);
         h->solve_ready = true;
     }
+    if (nrhs == 1 && h->opt[B200LU_OPT_TRSV_MODE] == 0 && nblk >= 4) {
+        // ---- version 2: 2-D work items on a persistent, fully resident grid ----
+        if (h->t2_nblk != nblk) {
+            CU_TRY(h, cudaStreamSynchronize(st));
+            free_dev(h->d_t2items); free_dev(h->d_t2x); free_dev(h->d_t2p);
+            std::vector<Trsv2Item> items;
+            int kmax = 1;
+            for (int t = 0; t < nblk; ++t) {
+                const int nfar = t > 2 ? t - 2 : 0;
+                const int nch = (nfar + TRSV2_CH - 1) / TRSV2_CH;
+                kmax = std::max(kmax, nch);
+                for (int k = 0; k < nch; ++k) items.push_back(Trsv2Item{t, k});
+                items.push_back(Trsv2Item{t, -1});
+            }
+            CU_TRY(h, cudaMalloc((void**)&h->d_t2items, items.size() * sizeof(Trsv2Item)));
+            CU_TRY(h, cudaMemcpy(h->d_t2items, items.data(), items.size() * sizeof(Trsv2Item), cudaMemcpyHostToDevice));
+            const size_t xb = (size_t)nblk * TRSV_TB * 2 * sizeof(unsigned long long);
+            const size_t pb = (size_t)nblk * kmax * TRSV_TB * 2 * sizeof(unsigned long long);
+            CU_TRY(h, cudaMalloc((void**)&h->d_t2x, xb));
+            CU_TRY(h, cudaMemset(h->d_t2x, 0, xb));
+            CU_TRY(h, cudaMalloc((void**)&h->d_t2p, pb));
+            CU_TRY(h, cudaMemset(h->d_t2p, 0, pb));
+            if (!h->d_t2ticket) {
+                CU_TRY(h, cudaMalloc((void**)&h->d_t2ticket, 64));
+                CU_TRY(h, cudaMemset(h->d_t2ticket, 0, 64));
+            }
+            int occ = 0, sms = 0;
+            CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trsv2_kernel<T, false>, 256, 0));
+            int occ_u = 0;
+            CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, trsv2_kernel<T, true>, 256, 0));
+            CU_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->dev));
+            h->t2_grid = std::max(1, std::min(occ, occ_u)) * sms;   // every CTA resident: tickets cannot deadlock
+            h->t2_nblk = nblk;
+            h->t2_nitems = (int)items.size();
+            h->t2_kmax = kmax;
+            h->t2_epoch = 0;
+        }
+        const int grid = std::min(h->t2_grid, h->t2_nitems);
+        for (int upper = 0; upper < 2; ++upper) {
+            if (h->t2_epoch > (1u << 30)) {
+                CU_TRY(h, cudaMemsetAsync(h->d_t2x, 0, (size_t)nblk * TRSV_TB * 2 * sizeof(unsigned long long), st));
+                CU_TRY(h, cudaMemsetAsync(h->d_t2p, 0, (size_t)nblk * h->t2_kmax * TRSV_TB * 2 * sizeof(unsigned long long), st));
+                h->t2_epoch = 0;
+            }
+            const unsigned epoch = ++h->t2_epoch;
+            Trsv2Sync sy{h->d_t2x, h->d_t2p, h->d_t2ticket, h->d_deverr, h->d_t2items, h->t2_nitems, h->t2_kmax};
+            if (upper)
+                trsv2_kernel<T, true><<<grid, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvU, (const T*)h->d_wU, nullptr, nullptr, X, sy, epoch, nblk);
+            else
+                trsv2_kernel<T, false><<<grid, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvL, (const T*)h->d_wL, B, h->d_perm, X, sy, epoch, nblk);
+            LAUNCH_CHECK(h);
+        }
+        return 0;
+    }
     const int tile = (int)h->opt[B200LU_OPT_SOLVE_NRHS_TILE];
     const int NR = nrhs == 1 ? 1 : (tile >= 8 ? 8 : (tile >= 4 ? 4 : 1));
     const int groups = cdiv(nrhs, NR);
@@ -866,6 +927,7 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     h->opt[B200LU_OPT_GEMM_CFG] = 0;
     h->opt[B200LU_OPT_PANEL_MODE] = 0;
     h->opt[B200LU_OPT_SGEMM_MODE] = 0;
+    h->opt[B200LU_OPT_TRSV_MODE] = 0;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) == cudaSuccess;
@@ -913,7 +975,7 @@ void b200lu_destroy(b200lu_handle* h) {
     }
     free_dev(h->dA); free_dev(h->dA64); free_dev(h->d_ipiv); free_dev(h->d_perm);
     free_dev(h->d_info); free_dev(h->d_deverr); free_dev(h->d_plans); free_dev(h->d_panelsync); free_dev(h->d_split);
-    free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_wL); free_dev(h->d_wU); free_dev(h->d_tflags); free_dev(h->d_tticket);
+    free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_wL); free_dev(h->d_wU); free_dev(h->d_tflags); free_dev(h->d_tticket); free_dev(h->d_t2items); free_dev(h->d_t2x); free_dev(h->d_t2p); free_dev(h->d_t2ticket);
     free_dev(h->d_B); free_dev(h->d_X); free_dev(h->d_r); free_dev(h->d_r32); free_dev(h->d_scal);
     free_dev(h->dB_LU); free_dev(h->dB_ipiv); free_dev(h->dB_info); free_dev(h->dB_perm); free_dev(h->dB_in);
     free_dev(h->dB_rhs); free_dev(h->dB_x);
@@ -1039,6 +1101,7 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_GEMM_CFG && (value < 0 || value > 2)) return -3;
     if (option == B200LU_OPT_PANEL_MODE && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_SGEMM_MODE && (value < 0 || value > 2)) return -3;
+    if (option == B200LU_OPT_TRSV_MODE && (value < 0 || value > 1)) return -3;
     h->opt[option] = value;
     return 0;
 }

@@ -279,6 +279,216 @@ __global__ void __launch_bounds__(256) trsv_block_kernel(const T* __restrict__ A
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single right-hand side, version 2: 2-D work items.  One CTA per block row (above) leaves the
+// LAST block row streaming n/64 - 2 blocks alone — twice the average — and serialises each row's
+// stream behind one thread block.  Here a block row t (logical order: t = 0 is solved first) is
+// split into
+//   * partial items (t, k): the far dependencies d in [8k, 8k + 8) ∩ [0, t - 2): eight 64x64
+//     blocks times already-solved segments, result = 64 partial sums written as LL packets;
+//   * one final item (t): rhs - sum of the partial items (fixed order: deterministic), minus the
+//     block at d = t - 2, times the inverted diagonal block, minus the coupling block times the
+//     adjacent segment x_{t-1}; publishes x_t.
+// Items are drawn from one ticket counter in (t, k) order by a persistent grid that is fully
+// resident, so an item only ever waits for items with smaller tickets: no deadlock.  The
+// dependency chain per block row is the same single 64x64 mat-vec as before; the streaming work
+// is spread over every SM.
+struct Trsv2Item { int t, k; };   // k < 0: final item
+
+struct Trsv2Sync {
+    unsigned long long* xll;     // [nblk*64][WN]   solved x segments (LL packets)
+    unsigned long long* pll;     // [nblk][kmax][64][WN] partial sums (LL packets)
+    int* ticket;
+    int* deverr;
+    const Trsv2Item* items;
+    int nitems, kmax;
+};
+
+constexpr int TRSV2_CH = 8;   // far blocks per partial item
+
+template <typename T, bool UPPER>
+__global__ void __launch_bounds__(256, 1) trsv2_kernel(const T* __restrict__ A, long long lda, int n,
+                                                       const T* __restrict__ dinv, const T* __restrict__ wmat,
+                                                       const T* __restrict__ B, const int* __restrict__ perm,
+                                                       T* __restrict__ X, Trsv2Sync sy, unsigned epoch, int nblk) {
+    constexpr int TB = TRSV_TB;
+    constexpr int WN = sizeof(T) / 4;
+    __shared__ __align__(16) T s_x[8][16];       // per-warp staging of the 16 x values it multiplies by
+    __shared__ T s_part[4][TB];
+    __shared__ T s_rhs[TB];
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = tid & (TB - 1);
+    const int q = tid >> 6;   // column quarter 0..3
+    bool dead = false;
+
+    // gather the 16 x values (quarter q of logical block d) into this warp's staging
+    auto gather_x = [&](int d) {
+        const int c = UPPER ? (nblk - 1 - d) : d;
+        const unsigned long long* src = sy.xll + (size_t)(c * TB + q * 16) * WN;
+        unsigned* dstw = reinterpret_cast<unsigned*>(&s_x[warp][0]);
+        for (int idx = lane; idx < 16 * WN; idx += 32) {
+            unsigned data = 0;
+            if (!ll_wait(src + idx, epoch, data)) dead = true;
+            dstw[idx] = data;
+        }
+        __syncwarp();
+    };
+    auto load_blk = [&](int d, int grow, bool rok, T* dst) {
+        const int c = UPPER ? (nblk - 1 - d) : d;
+        const T* ap = A + (long long)(c * TB + q * 16) * lda + grow;
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const int gc = c * TB + q * 16 + jj;
+            dst[jj] = (rok && gc < n) ? ap[(long long)jj * lda] : T(0);
+        }
+    };
+
+    for (;;) {
+        __syncthreads();   // s_ticket / staging reuse
+        if (tid == 0) {
+            const int tk = atomicAdd(sy.ticket, 1);
+            if (tk == sy.nitems + (int)gridDim.x - 1) sy.ticket[0] = 0;   // last draw of the sweep: re-arm
+            s_ticket = tk;
+        }
+        __syncthreads();
+        const int tk = s_ticket;
+        if (tk >= sy.nitems) break;
+        const Trsv2Item it = sy.items[tk];
+        const int t = it.t;
+        const int r = UPPER ? (nblk - 1 - t) : t;
+        const int grow = r * TB + row;
+        const bool rok = grow < n;
+        const int nfar = t > 2 ? t - 2 : 0;
+        if (it.k >= 0) {
+            // ---------------- partial item ----------------
+            const int d0 = it.k * TRSV2_CH, d1 = min(d0 + TRSV2_CH, nfar);
+            constexpr int PF = 4;
+            T an[PF][16];
+#pragma unroll
+            for (int u = 0; u < PF; ++u)
+                if (d0 + u < d1) load_blk(d0 + u, grow, rok, an[u]);
+            T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
+            for (int db = d0; db < d1; db += PF) {
+#pragma unroll
+                for (int u = 0; u < PF; ++u) {
+                    const int d = db + u;
+                    if (d < d1) {
+                        T ac[16];
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) ac[jj] = an[u][jj];
+                        if (d + PF < d1) load_blk(d + PF, grow, rok, an[u]);
+                        gather_x(d);
+#pragma unroll
+                        for (int jj = 0; jj < 16; jj += 4) {
+                            acc0 = tfma(ac[jj], s_x[warp][jj], acc0);
+                            acc1 = tfma(ac[jj + 1], s_x[warp][jj + 1], acc1);
+                            acc2 = tfma(ac[jj + 2], s_x[warp][jj + 2], acc2);
+                            acc3 = tfma(ac[jj + 3], s_x[warp][jj + 3], acc3);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            s_part[q][row] = (acc0 + acc1) + (acc2 + acc3);
+            __syncthreads();
+            if (tid < TB) {
+                const T sum = (s_part[0][row] + s_part[1][row]) + (s_part[2][row] + s_part[3][row]);
+                unsigned w[WN];
+                Words<T>::split(sum, w);
+                unsigned long long* dst = sy.pll + ((size_t)(t * sy.kmax + it.k) * TB + row) * WN;
+#pragma unroll
+                for (int x = 0; x < WN; ++x) ll_store(dst + x, w[x], epoch);
+            }
+        } else {
+            // ---------------- final item ----------------
+            T myb = T(0);
+            if (tid < TB && rok) {
+                if (!UPPER && perm != nullptr) myb = B[perm[grow]];
+                else myb = X[grow];
+            }
+            T dv[16], wv[16], av[16];
+            {
+                const T* dp = dinv + (long long)r * TB * TB + (q * 16) * TB + row;
+                const T* wp = wmat + (long long)r * TB * TB + (q * 16) * TB + row;
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) { dv[jj] = dp[jj * TB]; wv[jj] = wp[jj * TB]; }
+            }
+            if (t >= 2) load_blk(t - 2, grow, rok, av);
+            // sum of the partial items, fixed order
+            const int nch = (nfar + TRSV2_CH - 1) / TRSV2_CH;
+            if (tid < TB) {
+                T sum = T(0);
+                const unsigned long long* src = sy.pll + ((size_t)(t * sy.kmax) * TB + row) * WN;
+                for (int k = 0; k < nch; ++k) {
+                    unsigned w[WN];
+#pragma unroll
+                    for (int x = 0; x < WN; ++x) {
+                        unsigned data = 0;
+                        if (!ll_wait(src + (size_t)k * TB * WN + x, epoch, data)) dead = true;
+                        w[x] = data;
+                    }
+                    sum += Words<T>::join(w);
+                }
+                s_rhs[row] = myb - sum;
+            }
+            // the block at d = t - 2
+            if (t >= 2) {
+                gather_x(t - 2);
+                T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+#pragma unroll
+                for (int jj = 0; jj < 16; jj += 4) {
+                    a0 = tfma(av[jj], s_x[warp][jj], a0);
+                    a1 = tfma(av[jj + 1], s_x[warp][jj + 1], a1);
+                    a2 = tfma(av[jj + 2], s_x[warp][jj + 2], a2);
+                    a3 = tfma(av[jj + 3], s_x[warp][jj + 3], a3);
+                }
+                __syncwarp();
+                s_part[q][row] = (a0 + a1) + (a2 + a3);
+            }
+            __syncthreads();
+            if (t >= 2 && tid < TB)
+                s_rhs[row] -= (s_part[0][row] + s_part[1][row]) + (s_part[2][row] + s_part[3][row]);
+            __syncthreads();
+            // tq = dinv_r * rhs (my 16 columns)
+            T t0 = T(0), t1 = T(0), t2 = T(0), t3 = T(0);
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4) {
+                t0 = tfma(dv[jj], s_rhs[q * 16 + jj], t0);
+                t1 = tfma(dv[jj + 1], s_rhs[q * 16 + jj + 1], t1);
+                t2 = tfma(dv[jj + 2], s_rhs[q * 16 + jj + 2], t2);
+                t3 = tfma(dv[jj + 3], s_rhs[q * 16 + jj + 3], t3);
+            }
+            // critical path: x_t = tq - W_t * x_{t-1}
+            if (t >= 1) {
+                gather_x(t - 1);
+#pragma unroll
+                for (int jj = 0; jj < 16; jj += 4) {
+                    t0 = tfma(-wv[jj], s_x[warp][jj], t0);
+                    t1 = tfma(-wv[jj + 1], s_x[warp][jj + 1], t1);
+                    t2 = tfma(-wv[jj + 2], s_x[warp][jj + 2], t2);
+                    t3 = tfma(-wv[jj + 3], s_x[warp][jj + 3], t3);
+                }
+                __syncwarp();
+            }
+            __syncthreads();   // all reads of s_part (d = t-2 sums) done before it is reused
+            s_part[q][row] = (t0 + t1) + (t2 + t3);
+            __syncthreads();
+            if (tid < TB) {
+                const T xv = (s_part[0][row] + s_part[1][row]) + (s_part[2][row] + s_part[3][row]);
+                unsigned w[WN];
+                Words<T>::split(xv, w);
+                unsigned long long* dst = sy.xll + (size_t)grow * WN;
+#pragma unroll
+                for (int x = 0; x < WN; ++x) ll_store(dst + x, w[x], epoch);
+                if (rok) X[grow] = xv;
+            }
+        }
+        if (__any_sync(0xffffffffu, dead) && lane == 0) atomicExch(sy.deverr, DEV_ERR_TRSV_TIMEOUT);
+        if (__syncthreads_or(dead ? 1 : 0)) break;
+    }
+}
+
 // y = b - A x  (FP64 residual for the refinement loop; A n x n column-major).
 // CTA: 256 rows x `cchunk` columns; one atomicAdd per row per CTA.
 template <typename TA>
