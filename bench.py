@@ -37,9 +37,9 @@ def parse():
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--n", type=int, default=8192)
+    p.add_argument("--n", "--size", dest="n", type=int, default=8192)   # use --size under torchrun (its parser abbreviates --n)
     p.add_argument("--nrhs", type=int, default=100)
-    p.add_argument("--workload", default="lu", choices=["lu", "batched", "mixed"])
+    p.add_argument("--workload", default="lu", choices=["lu", "batched", "mixed", "dist"])
     p.add_argument("--batch", type=int, default=65536)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -183,6 +183,8 @@ def main():
         return float(t.item())
 
     n, nrhs = args.n, args.nrhs
+    if args.workload == "dist":
+        return bench_dist(args, ls, torch, dist, dev, rank, world, local, barrier, max_over_ranks)
     dtype_code = {"lu": C.F64, "mixed": C.MIXED, "batched": C.F64}[args.workload]
     h = ls.Handle(dtype_code, device=local)
     if args.nb:
@@ -261,26 +263,45 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
-    roofline = {
-        "bound": "tensor", "kernel": "dgemm_sub_kernel (FP64 DMMA trailing update)",
-        "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma if peak_dmma else None,
-        "traffic": None,
-        "peak_source": "library DMMA.8x8x4 register-resident probe on this GPU (no FP64 entry in MEASURED_PEAKS.json)",
-        "launches_profiled": int(g_n), "gemm_share_of_getrf": (g_ms / 2) / t_fact_prof if t_fact_prof else None,
-        "dfma_probe_tflops": peak_dfma, "hbm_copy_probe_gbs": hbm_copy,
-        "getrf_frac_of_fp64_peak": (lu_flops(n) / ((tf / args.steps) * 1e-3) / 1e12) / peak_dmma if peak_dmma else None,
-        "getrs": {"bound": "hbm",
-                  "achieved": (1 if nrhs == 1 else -(-nrhs // 8)) * 8.0 * n * n / ((ts / args.steps) * 1e-3) / 1e9,
-                  "peak": hbm_peak, "unit": "GB/s",
-                  "note": "8 n^2 bytes of factors per pass; nrhs > 1 runs ceil(nrhs/8) passes of 8 right-hand sides"},
-    }
+    if args.workload == "mixed":
+        # FP32 factorization: the trailing update runs on tcgen05 kind::tf32 as 3 MMAs per product
+        # (error-compensated 3xTF32).  No measured TF32 figure exists: the yardstick is the measured
+        # bf16 cuBLAS burst (MEASURED_PEAKS.json) / 2 (TF32 is half the bf16 rate) / 3 (three MMAs).
+        bf16 = peaks_file.get("bf16_tflops", 1590.0)
+        tc_peak = bf16 / 2.0 / 3.0
+        roofline = {
+            "bound": "tensor", "kernel": "sgemm3x_tc_kernel (tcgen05 kind::tf32, TMA-fed, TMEM accumulator, 3xTF32)",
+            "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": None,
+            "peak_source": "measured bf16 burst %.0f TFLOP/s / 2 (tf32 rate) / 3 (MMAs per FP32-accurate product); "
+                           "achieved counts 2MNK useful flops" % bf16,
+            "launches_profiled": int(g_n), "gemm_share_of_getrf": (g_ms / 2) / t_fact_prof if t_fact_prof else None,
+            "hbm_copy_probe_gbs": hbm_copy,
+        }
+    else:
+        roofline = {
+            "bound": "tensor", "kernel": "dgemm_sub_kernel (FP64 DMMA trailing update)",
+            "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma if peak_dmma else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu capture
+            # (profiles/r01_ncu_dgemm_details.txt: M=7936 N=7680 K=256, the first trailing update at n=8192):
+            # 1.056e9 B measured vs 1.007e9 B algorithmic (C read + written once, L21 and U12 once)
+            "traffic": 1.0556e9, "traffic_algorithmic": 2 * 7936 * 7680 * 8 + (7936 + 7680) * 256 * 8,
+            "peak_source": "library DMMA.8x8x4 register-resident probe on this GPU (no FP64 entry in MEASURED_PEAKS.json)",
+            "launches_profiled": int(g_n), "gemm_share_of_getrf": (g_ms / 2) / t_fact_prof if t_fact_prof else None,
+            "dfma_probe_tflops": peak_dfma, "hbm_copy_probe_gbs": hbm_copy,
+            "getrf_frac_of_fp64_peak": (lu_flops(n) / ((tf / args.steps) * 1e-3) / 1e12) / peak_dmma if peak_dmma else None,
+        }
+    roofline["getrs"] = {"bound": "hbm",
+                         "achieved": (1 if nrhs == 1 else -(-nrhs // 8)) * (8.0 if args.workload == "lu" else 4.0) * n * n / ((ts / args.steps) * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s",
+                         "note": "bytes of factors per pass (8 n^2 FP64, 4 n^2 FP32); nrhs > 1 runs ceil(nrhs/8) passes of 8 right-hand sides; MIXED adds refinement sweeps, so its figure is a lower bound"}
 
     line = {
         "metric": "FP64 LU GFLOP/s (2/3 n^3), getrf + getrs over nrhs right-hand sides",
         "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64" if args.workload == "lu" else "f32 factor + f64 refine", "data": "synthetic",
-        "config": {"workload": f"f64 getrf n={n} + getrs {nrhs} rhs (LinearCache reuse)", "n": n, "nrhs": nrhs,
+        "config": {"workload": (f"f64 getrf n={n} + getrs {nrhs} rhs (LinearCache reuse)" if args.workload == "lu" else
+                                f"f32-factor + f64-refinement getrf n={n} + getrs {nrhs} rhs (mixed-precision LU)"), "n": n, "nrhs": nrhs,
                    "multi_gpu": "independent replicas per rank" if world > 1 else "single GPU",
                    "l2": "inputs (A = %.0f MiB) larger than L2" % (n * n * 8 / 2 ** 20),
                    "nb": h.get_option(C.OPT_NB), "lookahead": h.get_option(C.OPT_LOOKAHEAD)},
@@ -331,6 +352,70 @@ def main():
         line["cpu_baseline"] = {"value": lu_flops(n) / tc / 1e9, "unit": "GFLOP/s", "cores": host_threads(),
                                 "kind": "port", "sample": "the full workload once (LAPACK dgetrf + dgetrs, scipy OpenBLAS)",
                                 "seconds": tc}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_dist(args, ls, torch, dist, dev, rank, world, local, barrier, max_over_ranks):
+    """BASELINE config 5: ONE FP64 system factored by all ranks — 1-D block-cyclic columns (nb = 256),
+    owner factors the panel, NCCL broadcast of panel + pivots, look-ahead.  Strong scaling: `value` =
+    2/3 n^3 / (max over ranks of the device time of factor_dist)."""
+    C = ls._capi
+    n, nb = args.n, 256
+    h = C.Handle(C.F64, device=local)
+    h.set_option(C.OPT_NB, nb)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(C.Handle.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        h.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        nloc = h.dist_local_cols(n)
+    else:
+        nloc = n
+    Aloc = torch.empty((nloc, n), dtype=torch.float64, device=dev)
+
+    def fill():
+        if world > 1:
+            h.fill_uniform_device(Aloc.data_ptr(), n, n, nloc, seed=321, first_global_col=rank * nb,
+                                  col_block=nb, col_block_stride=world * nb)
+        else:
+            h.fill_uniform_device(Aloc.data_ptr(), n, n, n, seed=321)
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step():
+        fill()
+        barrier()
+        t0 = time.perf_counter()
+        if world > 1:
+            info = h.factor_dist(Aloc.data_ptr(), n, n)
+        else:
+            info = h.factor_device(Aloc.data_ptr(), n, n)
+        torch.cuda.synchronize()
+        return info, (time.perf_counter() - t0) * 1e3
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ls.launch_count()
+    ts = []
+    for _ in range(args.steps):
+        info, ms = step()
+        ts.append(ms)
+    clocks = sampler.stop()
+    launches = ls.launch_count() - l0
+    assert info == 0
+    ms = max_over_ranks(float(np.mean(ts)))
+    line = {"metric": "FP64 LU GFLOP/s (2/3 n^3), one system block-cyclic over all GPUs", "value": lu_flops(n) / (ms * 1e-3) / 1e9,
+            "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"f64 getrf n={n}, 1-D block-cyclic columns nb={nb}, NCCL panel broadcast + look-ahead",
+                       "n": n, "l2": "inputs larger than L2", "timing": "host clock around the blocking call, barrier before, max over ranks"},
+            "gpu_launches": int(launches), "clocks": clocks}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
