@@ -455,19 +455,28 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
         __syncthreads();
         const int nmv = sh.s_nmv;
         if (nmv > 0) {
-            // one group of 2W threads per column: all loads of a column before its stores
-            constexpr int GRP = 2 * W, CPP = NT / GRP;
+            // one group of 2W threads per column (all loads of a column before its stores); every
+            // thread keeps up to 4 columns in flight so the pass costs one memory latency, not four
+            constexpr int GRP = 2 * W, CPP = NT / GRP, MLP = 4;
             const int slot = tid % GRP, sub = tid / GRP;
             const int src = slot < nmv ? sh.s_mv_src[slot] : 0, dst = slot < nmv ? sh.s_mv_dst[slot] : 0;
-            for (int c0 = me * CPP; c0 < ncols; c0 += G * CPP) {
-                const int c = c0 + sub;
-                const bool on = c < ncols && slot < nmv;
-                const int col = (c < nleft) ? (p.pc0 + c) : (p.j0 + wc + (c - nleft));
-                T* base = p.A + (long long)col * p.lda + p.j0;
-                T v = T(0);
-                if (on) v = base[src];
+            for (int c0 = me * CPP; c0 < ncols; c0 += G * CPP * MLP) {
+                T v[MLP];
+                T* base[MLP];
+                bool on[MLP];
+#pragma unroll
+                for (int u = 0; u < MLP; ++u) {
+                    const int c = c0 + u * G * CPP + sub;
+                    on[u] = c < ncols && slot < nmv;
+                    const int col = (c < nleft) ? (p.pc0 + c) : (p.j0 + wc + (c - nleft));
+                    base[u] = p.A + (long long)col * p.lda + p.j0;
+                    v[u] = T(0);
+                    if (on[u]) v[u] = base[u][src];
+                }
                 __syncthreads();
-                if (on) base[dst] = v;
+#pragma unroll
+                for (int u = 0; u < MLP; ++u)
+                    if (on[u]) base[u][dst] = v[u];
             }
         }
     }
