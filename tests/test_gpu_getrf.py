@@ -199,3 +199,57 @@ def test_large_n_properties(gpu_required, ls, oracle):
     L = np.tril(LU, -1) + np.eye(n)
     U = np.triu(LU)
     np.testing.assert_allclose(L[rows, :] @ U, A[perm[rows], :], atol=1e-10 * n)
+
+
+@pytest.mark.parametrize("dtype,n", [(np.float64, 8192), (np.float64, 9000), (np.float32, 9000)])
+def test_full_size_config2_and_tall_panels(gpu_required, ls, oracle, dtype, n):
+    """BASELINE config 2 at full size (n = 8192, FP64: 16-CTA cluster panels of 8192 rows) and the
+    tall-panel variants of the cluster kernel (8193..16384 rows: 16-wide FP64 blocks with 4 rows per
+    thread, FP32 blocks with 4 rows per thread): ipiv equal to LAPACK's up to admissible ties,
+    backward error <= 10 n eps, P A = L U on a row sample."""
+    rng = np.random.default_rng(77 + n)
+    A = np.asfortranarray(rng.random((n, n)).astype(dtype))
+    b = rng.random(n).astype(dtype)
+    h = _handle(ls, dtype)
+    ipiv, info = h.factor(A)
+    assert info == 0
+    x = h.solve(b)
+    assert oracle.backward_error(A, x, b) <= 10 * n * np.finfo(dtype).eps
+    if dtype == np.float64:
+        # FP64 pivots are decisive on this matrix: equal to LAPACK's outright.  (In FP32 a
+        # rounding-level tie appears after a few thousand columns and the oracle's tie check
+        # replays that many unblocked elimination steps in numpy — minutes; the FP32 pivot rule is
+        # pinned at n <= 1025 above and here by P A = L U below.)
+        _, ipiv_ref, _ = oracle.lapack_getrf(A)
+        assert np.array_equal(np.asarray(ipiv), np.asarray(ipiv_ref))
+    LU = h.get_factors()
+    perm = oracle.ipiv_to_perm(ipiv)
+    rows = rng.choice(n, 32, replace=False)
+    L = np.tril(LU, -1) + np.eye(n, dtype=dtype)
+    U = np.triu(LU)
+    tol = (1e-10 if dtype == np.float64 else 2e-3) * n
+    np.testing.assert_allclose((L[rows, :].astype(np.float64) @ U.astype(np.float64)), A[perm[rows], :].astype(np.float64), atol=tol)
+
+
+def test_l2_mailbox_fallback_panels(gpu_required, ls):
+    """n = 16640 > 16384: the first outer panels are taller than one cluster and take the L2-mailbox
+    kernel (panel.cuh), later ones the 16-wide and 32-wide cluster kernels — all three panel paths in
+    one factorization.  Size-independent property (LAPACK at this size is too slow for a test):
+    backward error of the solve, computed on the device."""
+    import torch
+    C = ls._capi
+    n = 16640
+    dev = torch.device("cuda", 0)
+    h = ls.Handle(C.F64)
+    A = torch.empty((n, n), dtype=torch.float64, device=dev)        # column-major: A[j, i] = entry (i, j)
+    b = torch.empty((1, n), dtype=torch.float64, device=dev)
+    x = torch.empty_like(b)
+    h.fill_uniform_device(A.data_ptr(), n, n, n, seed=4242)
+    h.fill_uniform_device(b.data_ptr(), n, n, 1, seed=4243)
+    A0 = A.clone()
+    assert h.factor_device(A.data_ptr(), n, n) == 0
+    h.solve_device(b.data_ptr(), n, x.data_ptr(), n, 1)
+    torch.cuda.synchronize()
+    r = A0.T @ x[0] - b[0]
+    berr = (r.norm() / (A0.norm() * x[0].norm())).item()
+    assert berr <= 10 * n * np.finfo(np.float64).eps, berr
