@@ -338,8 +338,12 @@ static int launch_sgemm_tc(b200lu_handle* h, cudaStream_t st, int M, int N, int 
         CU_TRY(h, cudaFuncSetAttribute(sgemm3x_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         attr_set = true;
     }
-    TcGemmParams p{C, ldc, M, N, K, h->d_deverr};
-    sgemm3x_tc_kernel<<<dim3(cdiv(M, TC_BM), cdiv(N, TC_BN)), TC_THREADS, TC_SMEM_BYTES, st>>>(tAhi, tAlo, tBhi, tBlo, p);
+    static int sms = 0;
+    if (!sms) CU_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->dev));
+    const int ntiles = cdiv(M, TC_BM) * cdiv(N, TC_BN);
+    const int tpc = std::max(1, std::min(4, ntiles / (2 * sms)));
+    TcGemmParams p{C, ldc, M, N, K, tpc, h->d_deverr};
+    sgemm3x_tc_kernel<<<cdiv(ntiles, tpc), TC_THREADS, TC_SMEM_BYTES, st>>>(tAhi, tAlo, tBhi, tBlo, p);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -1022,20 +1026,6 @@ int b200lu_debug_gemm_sub(b200lu_handle* h, int64_t M, int64_t N, int64_t K, con
     int de = 0;
     CU_TRY(h, cudaMemcpy(&de, h->d_deverr, sizeof(int), cudaMemcpyDeviceToHost));
     if (de) return set_err(h, 1, "device-side error %d in gemm", de);
-#ifdef TC_DEBUG
-    if (h->dtype != B200LU_F64) {
-        float dbg[1024];
-        cudaMemcpyFromSymbol(dbg, g_tc_dbg, sizeof(dbg));
-        const char* nm[4] = {"A_hi", "A_lo", "B_hi", "B_lo"};
-        for (int t = 0; t < 4; ++t) {
-            fprintf(stderr, "[tcdbg] %s:", nm[t]);
-            for (int i = 0; i < 40; ++i) fprintf(stderr, " %g", dbg[t * 64 + i]);
-            fprintf(stderr, "\n");
-        }
-        for (int qq = 0; qq < 4; ++qq) { fprintf(stderr, "[tcdbg] D lane %d:", 32 * qq); for (int i = 0; i < 8; ++i) fprintf(stderr, " %g", dbg[256 + qq * 8 + i]); fprintf(stderr, "\n"); }
-        unsigned tm; memcpy(&tm, &dbg[300], 4); fprintf(stderr, "\n[tcdbg] tmem base 0x%x\n", tm);
-    }
-#endif
     return 0;
 }
 

@@ -18,8 +18,10 @@
 //   One TMA box {32 (k), rows} per operand lands as `rows` rows of 128 bytes (SBO = 1024 bytes
 //   between groups of 8 rows); a UMMA K-step (8 TF32) advances the start address by 32 bytes.
 // CTA tile 128 x 256 (UMMA M = 128, N = 256, K = 8 per instruction), BK = 32, two stages of
-// 96 KB; warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-// (TMEM -> registers, C += D with D = (-A) B by the instruction descriptor's negate bit).
+// 96 KB; persistent CTAs (one per SM) with TWO TMEM accumulators so the HBM-bound epilogue of a
+// tile overlaps the main loop of the next; warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer, warps 2..5 = epilogue (TMEM -> registers, C += D with D = (-A) B by the instruction
+// descriptor's negate bit).
 #pragma once
 #include <cuda.h>   // CUtensorMap (types only; the encode entry point is fetched at run time)
 #include "common.cuh"
@@ -30,7 +32,7 @@ constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 2;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;              // 16 KB: one of A_hi / A_lo
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;              // 32 KB: one of B_hi / B_lo
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 96 KB
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;   // 197,888 B: one CTA per SM
 constexpr int TC_THREADS = 192;
 
 // hi = rn_tf32(x), lo = rn_tf32(x - hi) for a rows x cols column-major block
@@ -154,17 +156,19 @@ __device__ __forceinline__ unsigned long long tc_smem_desc(unsigned addr, unsign
            ((unsigned long long)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-#ifdef TC_DEBUG
-__device__ float g_tc_dbg[1024];
-#endif
-
 struct TcGemmParams {
     float* C;
     long long ldc;
     int M, N, K;
+    int tiles_per_cta;   // consecutive tiles per CTA (see the kernel comment)
     int* deverr;
 };
 
+// Semi-persistent: CTA b works on `tiles_per_cta` consecutive tiles (M-fastest order, so neighbours
+// share the B strip in L2) and then EXITS — a fully persistent grid would hold every SM for the whole
+// update and starve the look-ahead panel kernels of the high-priority stream (measured).  Two TMEM accumulators (2 x 256 columns):
+// the epilogue of tile i (TMEM -> registers -> C, HBM-bound: 128 KB read + 128 KB written) runs
+// under the main loop of tile i + 1.  The shared-memory ring runs continuously across tiles.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 sgemm3x_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                   const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
@@ -175,29 +179,35 @@ sgemm3x_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
     unsigned char* gen = tc_smem_raw + (base - raw);
     // [stage][A_hi | A_lo | B_hi | B_lo] ... then the barriers
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(gen + TC_STAGES * TC_STAGE_BYTES);
-    const unsigned bar_full = tc_smem_u32(&bars[0]);         // [TC_STAGES]
-    const unsigned bar_empty = tc_smem_u32(&bars[TC_STAGES]);   // [TC_STAGES]
-    const unsigned bar_acc = tc_smem_u32(&bars[2 * TC_STAGES]);
-    unsigned* s_tmem = reinterpret_cast<unsigned*>(&bars[2 * TC_STAGES + 1]);
+    const unsigned bar_full = tc_smem_u32(&bars[0]);              // [TC_STAGES] TMA -> MMA
+    const unsigned bar_empty = tc_smem_u32(&bars[TC_STAGES]);     // [TC_STAGES] MMA -> TMA
+    const unsigned bar_accf = tc_smem_u32(&bars[2 * TC_STAGES]);  // [2] MMA -> epilogue (accumulator full)
+    const unsigned bar_acce = tc_smem_u32(&bars[2 * TC_STAGES + 2]);  // [2] epilogue -> MMA (accumulator drained)
+    unsigned* s_tmem = reinterpret_cast<unsigned*>(&bars[2 * TC_STAGES + 4]);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
     const int KB = (p.K + TC_BK - 1) / TC_BK;
+    const int tiles_m = (p.M + TC_BM - 1) / TC_BM, tiles_n = (p.N + TC_BN - 1) / TC_BN;
+    const int ntiles = tiles_m * tiles_n;
+    const int tile0 = blockIdx.x * p.tiles_per_cta, tile1 = min(tile0 + p.tiles_per_cta, ntiles);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             tc_mbar_init(bar_full + 8 * s, 1);
             tc_mbar_init(bar_empty + 8 * s, 1);
         }
-        tc_mbar_init(bar_acc, 1);
+        for (int a = 0; a < 2; ++a) {
+            tc_mbar_init(bar_accf + 8 * a, 1);
+            tc_mbar_init(bar_acce + 8 * a, 4);   // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tc_prefetch_tensormap(&tmAhi);
         tc_prefetch_tensormap(&tmAlo);
         tc_prefetch_tensormap(&tmBhi);
         tc_prefetch_tensormap(&tmBlo);
     }
-    if (warp == 1) {   // TMEM: 256 columns (128 lanes x 256 FP32 accumulators)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(s_tmem)), "r"(256u) : "memory");
+    if (warp == 1) {   // TMEM: all 512 columns = two 128 x 256 FP32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -208,17 +218,23 @@ sgemm3x_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % TC_STAGES;
-                const unsigned ph = (unsigned)(kb / TC_STAGES) & 1u;
-                if (!tc_mbar_wait(bar_empty + 8 * s, ph ^ 1u)) { atomicExch(p.deverr, DEV_ERR_GEMM_TIMEOUT); break; }
-                const unsigned st = base + s * TC_STAGE_BYTES;
-                tc_mbar_expect_tx(bar_full + 8 * s, (unsigned)TC_STAGE_BYTES);
-                const int k0 = kb * TC_BK;
-                tc_tma_load_2d(st, &tmAhi, k0, m0, bar_full + 8 * s);
-                tc_tma_load_2d(st + TC_A_BYTES, &tmAlo, k0, m0, bar_full + 8 * s);
-                tc_tma_load_2d(st + 2 * TC_A_BYTES, &tmBhi, k0, n0, bar_full + 8 * s);
-                tc_tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmBlo, k0, n0, bar_full + 8 * s);
+            int it = 0;   // running k-block index across tiles
+            bool ok = true;
+            for (int tile = tile0; tile < tile1 && ok; ++tile) {
+                const int m0 = (tile % tiles_m) * TC_BM, n0 = (tile / tiles_m) * TC_BN;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    const unsigned ph = (unsigned)(it / TC_STAGES) & 1u;
+                    ok = tc_mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    if (!ok) { atomicExch(p.deverr, DEV_ERR_GEMM_TIMEOUT); break; }
+                    const unsigned st = base + s * TC_STAGE_BYTES;
+                    tc_mbar_expect_tx(bar_full + 8 * s, (unsigned)TC_STAGE_BYTES);
+                    const int k0 = kb * TC_BK;
+                    tc_tma_load_2d(st, &tmAhi, k0, m0, bar_full + 8 * s);
+                    tc_tma_load_2d(st + TC_A_BYTES, &tmAlo, k0, m0, bar_full + 8 * s);
+                    tc_tma_load_2d(st + 2 * TC_A_BYTES, &tmBhi, k0, n0, bar_full + 8 * s);
+                    tc_tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmBlo, k0, n0, bar_full + 8 * s);
+                }
             }
         }
     } else if (warp == 1) {
@@ -227,64 +243,59 @@ sgemm3x_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
             // instruction descriptor: D = F32, A = B = TF32, A negated, both K-major, N = 256, M = 128
             constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) |
                                        ((unsigned)(TC_BN >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
+            int it = 0, j = 0;
             bool ok = true;
-            for (int kb = 0; kb < KB && ok; ++kb) {
-                const int s = kb % TC_STAGES;
-                const unsigned ph = (unsigned)(kb / TC_STAGES) & 1u;
-                ok = tc_mbar_wait(bar_full + 8 * s, ph);
+            for (int tile = tile0; tile < tile1 && ok; ++tile, ++j) {
+                const int acc = j & 1;
+                const unsigned aph = (unsigned)(j >> 1) & 1u;
+                // the epilogue must have drained this accumulator (first use: passes immediately)
+                ok = tc_mbar_wait(bar_acce + 8 * acc, aph ^ 1u);
                 if (!ok) { atomicExch(p.deverr, DEV_ERR_GEMM_TIMEOUT); break; }
                 tc_fence_after();
-                const unsigned st = base + s * TC_STAGE_BYTES;
-#ifdef TC_DEBUG
-                if (kb == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
-                    const float* sp = reinterpret_cast<const float*>(gen + s * TC_STAGE_BYTES);
-                    for (int i = 0; i < 64; ++i) {
-                        g_tc_dbg[i] = sp[i];                                   // A_hi
-                        g_tc_dbg[64 + i] = sp[TC_A_BYTES / 4 + i];             // A_lo
-                        g_tc_dbg[128 + i] = sp[2 * TC_A_BYTES / 4 + i];        // B_hi
-                        g_tc_dbg[192 + i] = sp[(2 * TC_A_BYTES + TC_B_BYTES) / 4 + i];  // B_lo
-                    }
-                    g_tc_dbg[300] = __uint_as_float(tmem);
-                }
-#endif
+                const unsigned tacc = tmem + (unsigned)(acc * TC_BN);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    const unsigned ph = (unsigned)(it / TC_STAGES) & 1u;
+                    ok = tc_mbar_wait(bar_full + 8 * s, ph);
+                    if (!ok) { atomicExch(p.deverr, DEV_ERR_GEMM_TIMEOUT); break; }
+                    tc_fence_after();
+                    const unsigned st = base + s * TC_STAGE_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < TC_BK / 8; ++ks) {
-                    const unsigned long long a_hi = tc_smem_desc(st + ks * 32, 16, 1024);
-                    const unsigned long long a_lo = tc_smem_desc(st + TC_A_BYTES + ks * 32, 16, 1024);
-                    const unsigned long long b_hi = tc_smem_desc(st + 2 * TC_A_BYTES + ks * 32, 16, 1024);
-                    const unsigned long long b_lo = tc_smem_desc(st + 2 * TC_A_BYTES + TC_B_BYTES + ks * 32, 16, 1024);
-                    tc_mma_tf32(tmem, a_hi, b_lo, IDESC, (kb | ks) != 0 ? 1u : 0u);
-                    tc_mma_tf32(tmem, a_lo, b_hi, IDESC, 1u);
-                    tc_mma_tf32(tmem, a_hi, b_hi, IDESC, 1u);
+                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                        const unsigned long long a_hi = tc_smem_desc(st + ks * 32, 16, 1024);
+                        const unsigned long long a_lo = tc_smem_desc(st + TC_A_BYTES + ks * 32, 16, 1024);
+                        const unsigned long long b_hi = tc_smem_desc(st + 2 * TC_A_BYTES + ks * 32, 16, 1024);
+                        const unsigned long long b_lo = tc_smem_desc(st + 2 * TC_A_BYTES + TC_B_BYTES + ks * 32, 16, 1024);
+                        tc_mma_tf32(tacc, a_hi, b_lo, IDESC, (kb | ks) != 0 ? 1u : 0u);
+                        tc_mma_tf32(tacc, a_lo, b_hi, IDESC, 1u);
+                        tc_mma_tf32(tacc, a_hi, b_hi, IDESC, 1u);
+                    }
+                    tc_commit(bar_empty + 8 * s);   // frees the stage when these MMAs have read it
                 }
-                tc_commit(bar_empty + 8 * s);   // frees the stage when these MMAs have read it
+                if (ok) tc_commit(bar_accf + 8 * acc);   // accumulator complete
             }
-            tc_commit(bar_acc);                 // accumulator complete
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
-        const int row = m0 + 32 * q + lane;
-#ifdef TC_DEBUG
-        {
-            const unsigned taddr0 = tmem + ((unsigned)(32 * q) << 16);
-            const unsigned pat = __float_as_uint(7.0f + q);
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};\ntcgen05.wait::st.sync.aligned;" ::"r"(taddr0), "r"(pat) : "memory");
-        }
-#endif
-        const bool ok = tc_mbar_wait(bar_acc, 0);
-        if (!ok && lane == 0) atomicExch(p.deverr, DEV_ERR_GEMM_TIMEOUT);
-        tc_fence_after();
-        if (ok) {
+        int j = 0;
+        for (int tile = tile0; tile < tile1; ++tile, ++j) {
+            const int m0 = (tile % tiles_m) * TC_BM, n0 = (tile / tiles_m) * TC_BN;
+            const int acc = j & 1;
+            const unsigned aph = (unsigned)(j >> 1) & 1u;
+            const int row = m0 + 32 * q + lane;
+            const bool ok = tc_mbar_wait(bar_accf + 8 * acc, aph);
+            if (!ok) { if (lane == 0) atomicExch(p.deverr, DEV_ERR_GEMM_TIMEOUT); break; }
+            tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < TC_BN / 32; ++c) {
                 float cv[32];
                 float* cp = p.C + (long long)(n0 + c * 32) * p.ldc + row;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    cv[j] = (row < p.M && n0 + c * 32 + j < p.N) ? cp[(long long)j * p.ldc] : 0.f;
+                for (int jj = 0; jj < 32; ++jj)
+                    cv[jj] = (row < p.M && n0 + c * 32 + jj < p.N) ? cp[(long long)jj * p.ldc] : 0.f;
                 unsigned v[32];
-                const unsigned taddr = tmem + ((unsigned)(32 * q) << 16) + (unsigned)(c * 32);
+                const unsigned taddr = tmem + ((unsigned)(32 * q) << 16) + (unsigned)(acc * TC_BN + c * 32);
                 // load + wait in ONE asm statement: nothing may read v[] before tcgen05.wait::ld
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -297,21 +308,21 @@ sgemm3x_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr)
                     : "memory");
-#ifdef TC_DEBUG
-                if (blockIdx.x == 0 && blockIdx.y == 0 && c == 0 && lane == 0)
-                    for (int j = 0; j < 8; ++j) g_tc_dbg[256 + q * 8 + j] = __uint_as_float(v[j]);
-#endif
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (row < p.M && n0 + c * 32 + j < p.N) cp[(long long)j * p.ldc] = cv[j] + __uint_as_float(v[j]);
+                for (int jj = 0; jj < 32; ++jj)
+                    if (row < p.M && n0 + c * 32 + jj < p.N) cp[(long long)jj * p.ldc] = cv[jj] + __uint_as_float(v[jj]);
             }
+            // this warp has read its lanes of the accumulator: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acce + 8 * acc) : "memory");
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
 
