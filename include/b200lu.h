@@ -150,7 +150,11 @@ int b200lu_factor(b200lu_handle* h, int64_t n, const void* A_host, int64_t lda,
  * getrs with the cached factors: op(A) X = B, trans in {'N','T','C'}.
  * B_host: n x nrhs, X_host: n x nrhs (may alias B_host).  Element type: double
  * for F64/MIXED, float for F32.  Returns 1000+info-style failure (status 3) if
- * the cached factorization is singular (info > 0) or absent.
+ * the cached factorization is singular (info > 0) or absent.  'T'/'C' (the
+ * reference's `solve!(cache; adjoint = true)`, src/common.jl:1012-1027; LAPACK
+ * getrs trans argument, src/openblas.jl:247-278) reuse the same factors:
+ * U^T y = b, L^T z = y, x = P^T z; supported for F64 and F32 handles (status -2
+ * for MIXED).
  */
 int b200lu_solve(b200lu_handle* h, char trans, int64_t nrhs,
                  const void* B_host, int64_t ldb, void* X_host, int64_t ldx);

@@ -75,6 +75,9 @@ struct b200lu_handle {
     int cap_tgroups = 0;
     size_t cap_tflag_bytes = 0;
     unsigned trsv_epoch = 0;
+    void* d_wLt = nullptr;  // transposed solves: coupling blocks of U^T (first sweep) ...
+    void* d_wUt = nullptr;  // ... and of L^T (second sweep)
+    bool solve_ready_t = false;
     // single-RHS TRSV v2 (2-D work items)
     Trsv2Item* d_t2items = nullptr;
     unsigned long long* d_t2x = nullptr;
@@ -648,6 +651,8 @@ static int ensure_capacity(b200lu_handle* h, int64_t n) {
     free_dev(h->d_dinvU);
     free_dev(h->d_wL);
     free_dev(h->d_wU);
+    free_dev(h->d_wLt);
+    free_dev(h->d_wUt);
     free_dev(h->d_r);
     free_dev(h->d_r32);
     h->n = n;
@@ -712,7 +717,7 @@ static int ensure_trsv_groups(b200lu_handle* h, int groups, int NR) {
 // through the permutation); getrs_device stages an aliased right-hand side.
 template <typename T>
 static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T* B, int64_t ldb,
-                       T* X, int64_t ldx, int nrhs) {
+                       T* X, int64_t ldx, int nrhs, bool trans = false) {
     cudaStream_t st = h->s_main;
     const int nblk = cdiv(n, TRSV_TB);
     if (!h->solve_ready) {
@@ -727,13 +732,25 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T
         LAUNCH_CHECK(h);
         trtri_diag_kernel<T><<<nblk, TRSV_TB, tsm, st>>>(A, lda, n, (T*)h->d_dinvU, 1);
         LAUNCH_CHECK(h);
-        trsv_coupling_kernel<T><<<nblk, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvL, (T*)h->d_wL, 0, nblk);
+        trsv_coupling_kernel<T><<<nblk, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvL, (T*)h->d_wL, 0, nblk, 0);
         LAUNCH_CHECK(h);
-        trsv_coupling_kernel<T><<<nblk, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvU, (T*)h->d_wU, 1, nblk);
+        trsv_coupling_kernel<T><<<nblk, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvU, (T*)h->d_wU, 1, nblk, 0);
         LAUNCH_CHECK(h);
         h->solve_ready = true;
     }
-    if (nrhs == 1 && h->opt[B200LU_OPT_TRSV_MODE] == 0 && nblk >= 4) {
+    if (trans && !h->solve_ready_t) {
+        // A^T = U^T L^T P: first sweep with U^T (lower order, coupling with block r-1), second with L^T
+        const size_t wb = (size_t)nblk * TRSV_TB * TRSV_TB * sizeof(T);
+        if (!h->d_wLt) CU_TRY(h, cudaMalloc(&h->d_wLt, (size_t)cdiv(h->cap_n, TRSV_TB) * TRSV_TB * TRSV_TB * sizeof(T)));
+        if (!h->d_wUt) CU_TRY(h, cudaMalloc(&h->d_wUt, (size_t)cdiv(h->cap_n, TRSV_TB) * TRSV_TB * TRSV_TB * sizeof(T)));
+        (void)wb;
+        trsv_coupling_kernel<T><<<nblk, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvU, (T*)h->d_wUt, 0, nblk, 1);
+        LAUNCH_CHECK(h);
+        trsv_coupling_kernel<T><<<nblk, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvL, (T*)h->d_wLt, 1, nblk, 1);
+        LAUNCH_CHECK(h);
+        h->solve_ready_t = true;
+    }
+    if (trans || (nrhs == 1 && h->opt[B200LU_OPT_TRSV_MODE] == 0 && nblk >= 4)) {
         // ---- version 2: 2-D work items on a persistent, fully resident grid ----
         if (h->t2_nblk != nblk) {
             CU_TRY(h, cudaStreamSynchronize(st));
@@ -760,9 +777,9 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T
                 CU_TRY(h, cudaMemset(h->d_t2ticket, 0, 64));
             }
             int occ = 0, sms = 0;
-            CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trsv2_kernel<T, false>, 256, 0));
+            CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trsv2_kernel<T, false, false>, 256, 0));
             int occ_u = 0;
-            CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, trsv2_kernel<T, true>, 256, 0));
+            CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, trsv2_kernel<T, true, true>, 256, 0));
             CU_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->dev));
             h->t2_grid = std::max(1, std::min(occ, occ_u)) * sms;   // every CTA resident: tickets cannot deadlock
             h->t2_nblk = nblk;
@@ -771,19 +788,40 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T
             h->t2_epoch = 0;
         }
         const int grid = std::min(h->t2_grid, h->t2_nitems);
-        for (int upper = 0; upper < 2; ++upper) {
-            if (h->t2_epoch > (1u << 30)) {
-                CU_TRY(h, cudaMemsetAsync(h->d_t2x, 0, (size_t)nblk * TRSV_TB * 2 * sizeof(unsigned long long), st));
-                CU_TRY(h, cudaMemsetAsync(h->d_t2p, 0, (size_t)nblk * h->t2_kmax * TRSV_TB * 2 * sizeof(unsigned long long), st));
-                h->t2_epoch = 0;
+        if (trans) {
+            int rc = ensure_rhs(h, 1);
+            if (rc) return rc;
+        }
+        for (int col = 0; col < nrhs; ++col) {
+            const T* Bc = B + (int64_t)col * ldb;
+            T* Xc = X + (int64_t)col * ldx;
+            for (int upper = 0; upper < 2; ++upper) {
+                if (h->t2_epoch > (1u << 30)) {
+                    CU_TRY(h, cudaMemsetAsync(h->d_t2x, 0, (size_t)nblk * TRSV_TB * 2 * sizeof(unsigned long long), st));
+                    CU_TRY(h, cudaMemsetAsync(h->d_t2p, 0, (size_t)nblk * h->t2_kmax * TRSV_TB * 2 * sizeof(unsigned long long), st));
+                    h->t2_epoch = 0;
+                }
+                const unsigned epoch = ++h->t2_epoch;
+                Trsv2Sync sy{h->d_t2x, h->d_t2p, h->d_t2ticket, h->d_deverr, h->d_t2items, h->t2_nitems, h->t2_kmax};
+                if (!trans) {
+                    if (upper)
+                        trsv2_kernel<T, true, false><<<grid, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvU, (const T*)h->d_wU, nullptr, nullptr, Xc, sy, epoch, nblk);
+                    else
+                        trsv2_kernel<T, false, false><<<grid, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvL, (const T*)h->d_wL, Bc, h->d_perm, Xc, sy, epoch, nblk);
+                } else {
+                    if (upper)   // L^T z = y: block rows in descending order
+                        trsv2_kernel<T, true, true><<<grid, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvL, (const T*)h->d_wLt, nullptr, nullptr, Xc, sy, epoch, nblk);
+                    else         // U^T y = b: block rows in ascending order, no row gather
+                        trsv2_kernel<T, false, true><<<grid, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvU, (const T*)h->d_wUt, Bc, nullptr, Xc, sy, epoch, nblk);
+                }
+                LAUNCH_CHECK(h);
             }
-            const unsigned epoch = ++h->t2_epoch;
-            Trsv2Sync sy{h->d_t2x, h->d_t2p, h->d_t2ticket, h->d_deverr, h->d_t2items, h->t2_nitems, h->t2_kmax};
-            if (upper)
-                trsv2_kernel<T, true><<<grid, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvU, (const T*)h->d_wU, nullptr, nullptr, X, sy, epoch, nblk);
-            else
-                trsv2_kernel<T, false><<<grid, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvL, (const T*)h->d_wL, B, h->d_perm, X, sy, epoch, nblk);
-            LAUNCH_CHECK(h);
+            if (trans) {   // x = P^T z
+                T* tmp = (T*)h->d_B;
+                CU_TRY(h, cudaMemcpyAsync(tmp, Xc, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+                perm_scatter_kernel<T><<<cdiv(n, 256), 256, 0, st>>>(tmp, h->d_perm, Xc, n);
+                LAUNCH_CHECK(h);
+            }
         }
         return 0;
     }
@@ -821,12 +859,12 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T
 // X = A^{-1} B on the device with the cached factors, all in the factor type T.
 // B and X may alias.
 template <typename T>
-static int getrs_device(b200lu_handle* h, const T* B, int64_t ldb, T* X, int64_t ldx, int nrhs) {
+static int getrs_device(b200lu_handle* h, const T* B, int64_t ldb, T* X, int64_t ldx, int nrhs, bool trans = false) {
     const int n = (int)h->n;
     cudaStream_t st = h->s_main;
     const T* src = B;
     int64_t lds = ldb;
-    if ((const void*)B == (const void*)X) {
+    if ((const void*)B == (const void*)X && !trans) {
         // the row gather through the permutation is not an in-place operation: stage B
         int rc = ensure_rhs(h, nrhs);
         if (rc) return rc;
@@ -835,7 +873,7 @@ static int getrs_device(b200lu_handle* h, const T* B, int64_t ldb, T* X, int64_t
         src = (const T*)h->d_B;
         lds = n;
     }
-    return trsv_sweeps<T>(h, (const T*)h->dA, h->ldd, n, src, lds, X, ldx, nrhs);
+    return trsv_sweeps<T>(h, (const T*)h->dA, h->ldd, n, src, lds, X, ldx, nrhs, trans);
 }
 
 // MIXED: FP32 factors + FP64 residual refinement, one right-hand side at a time.
@@ -979,7 +1017,7 @@ void b200lu_destroy(b200lu_handle* h) {
     }
     free_dev(h->dA); free_dev(h->dA64); free_dev(h->d_ipiv); free_dev(h->d_perm);
     free_dev(h->d_info); free_dev(h->d_deverr); free_dev(h->d_plans); free_dev(h->d_panelsync); free_dev(h->d_split);
-    free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_wL); free_dev(h->d_wU); free_dev(h->d_tflags); free_dev(h->d_tticket); free_dev(h->d_t2items); free_dev(h->d_t2x); free_dev(h->d_t2p); free_dev(h->d_t2ticket);
+    free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_wL); free_dev(h->d_wU); free_dev(h->d_wLt); free_dev(h->d_wUt); free_dev(h->d_tflags); free_dev(h->d_tticket); free_dev(h->d_t2items); free_dev(h->d_t2x); free_dev(h->d_t2p); free_dev(h->d_t2ticket);
     free_dev(h->d_B); free_dev(h->d_X); free_dev(h->d_r); free_dev(h->d_r32); free_dev(h->d_scal);
     free_dev(h->dB_LU); free_dev(h->dB_ipiv); free_dev(h->dB_info); free_dev(h->dB_perm); free_dev(h->dB_in);
     free_dev(h->dB_rhs); free_dev(h->dB_x);
@@ -1105,6 +1143,7 @@ static int factor_resident(b200lu_handle* h, int64_t n, int64_t* info) {
     int rc;
     h->factored = false;
     h->solve_ready = false;
+    h->solve_ready_t = false;
     h->prof_used = 0;
     h->prof_flops = 0.0;
     CU_TRY(h, cudaEventRecord(h->ev_b, h->s_main));
@@ -1210,8 +1249,10 @@ int b200lu_factor_device(b200lu_handle* h, int64_t n, const void* A_dev, int64_t
 static int check_solve_args(b200lu_handle* h, char trans, int64_t nrhs, const void* B, int64_t ldb,
                             void* X, int64_t ldx) {
     if (!h) return -1;
-    if (trans != 'N' && trans != 'n')
-        return set_err(h, -2, "trans='%c' not implemented (only 'N')", trans);
+    const bool tr = (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c');   // real types: 'C' == 'T'
+    if (!tr && trans != 'N' && trans != 'n') return set_err(h, -2, "trans='%c' is not one of N, T, C", trans);
+    if (tr && h->dtype == B200LU_MIXED)
+        return set_err(h, -2, "transposed solves are not implemented for the mixed-precision handle");
     if (nrhs < 0) return set_err(h, -3, "nrhs < 0");
     if (!h->factored) return set_err(h, 3, "no factorization cached");
     if (h->info != 0) return set_err(h, 3, "cached factorization is singular (info=%lld)", (long long)h->info);
@@ -1242,9 +1283,9 @@ int b200lu_solve_device(b200lu_handle* h, char trans, int64_t nrhs, const void* 
     CU_TRY(h, cudaSetDevice(h->dev));
     CU_TRY(h, cudaEventRecord(h->ev_b, h->s_main));
     if (h->dtype == B200LU_F64)
-        rc = getrs_device<double>(h, (const double*)B_dev, ldb, (double*)X_dev, ldx, (int)nrhs);
+        rc = getrs_device<double>(h, (const double*)B_dev, ldb, (double*)X_dev, ldx, (int)nrhs, trans != 'N' && trans != 'n');
     else if (h->dtype == B200LU_F32)
-        rc = getrs_device<float>(h, (const float*)B_dev, ldb, (float*)X_dev, ldx, (int)nrhs);
+        rc = getrs_device<float>(h, (const float*)B_dev, ldb, (float*)X_dev, ldx, (int)nrhs, trans != 'N' && trans != 'n');
     else
         rc = refine_solve_device(h, (const double*)B_dev, ldb, (double*)X_dev, ldx, (int)nrhs);
     if (rc) return rc;
@@ -1276,9 +1317,9 @@ int b200lu_solve(b200lu_handle* h, char trans, int64_t nrhs, const void* B_host,
                                 (size_t)nrhs, cudaMemcpyHostToDevice, h->s_main));
     CU_TRY(h, cudaEventRecord(h->ev_b, h->s_main));
     if (h->dtype == B200LU_F64)
-        rc = getrs_device<double>(h, (const double*)dBs, n, (double*)dXs, n, (int)nrhs);
+        rc = getrs_device<double>(h, (const double*)dBs, n, (double*)dXs, n, (int)nrhs, trans != 'N' && trans != 'n');
     else if (h->dtype == B200LU_F32)
-        rc = getrs_device<float>(h, (const float*)dBs, n, (float*)dXs, n, (int)nrhs);
+        rc = getrs_device<float>(h, (const float*)dBs, n, (float*)dXs, n, (int)nrhs, trans != 'N' && trans != 'n');
     else
         rc = refine_solve_device(h, (const double*)dBs, n, (double*)dXs, n, (int)nrhs);
     if (rc) return rc;

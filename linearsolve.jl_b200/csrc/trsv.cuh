@@ -64,9 +64,10 @@ __global__ void __launch_bounds__(TRSV_TB) trtri_diag_kernel(const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) trsv_coupling_kernel(const T* __restrict__ A, long long lda,
                                                             int n, const T* __restrict__ dinv,
-                                                            T* __restrict__ wmat, int upper, int nblk) {
+                                                            T* __restrict__ wmat, int upper, int nblk,
+                                                            int trans) {
     constexpr int TB = TRSV_TB;
-    __shared__ T s_a[TB][TB + 1];   // A block [k][col]
+    __shared__ T s_a[TB][TB + 1];   // block [k][col]
     const int r = blockIdx.x;
     const int c = upper ? r + 1 : r - 1;
     T* out = wmat + (long long)r * TB * TB;
@@ -74,10 +75,17 @@ __global__ void __launch_bounds__(256) trsv_coupling_kernel(const T* __restrict_
         for (int i = threadIdx.x; i < TB * TB; i += 256) out[i] = T(0);
         return;
     }
+    // trans: the block of the TRANSPOSED triangular factor, T(r, c)(i, j) = A[c*TB + j, r*TB + i]
     for (int i = threadIdx.x; i < TB * TB; i += 256) {
-        const int row = i % TB, col = i / TB;
-        const int gr = r * TB + row, gc = c * TB + col;
-        s_a[row][col] = (gr < n && gc < n) ? A[(long long)gc * lda + gr] : T(0);
+        if (!trans) {
+            const int row = i % TB, col = i / TB;
+            const int gr = r * TB + row, gc = c * TB + col;
+            s_a[row][col] = (gr < n && gc < n) ? A[(long long)gc * lda + gr] : T(0);
+        } else {
+            const int col = i % TB, row = i / TB;   // col is contiguous in memory
+            const int gi = r * TB + row, gj = c * TB + col;
+            s_a[row][col] = (gi < n && gj < n) ? A[(long long)gi * lda + gj] : T(0);
+        }
     }
     __syncthreads();
     const T* dp = dinv + (long long)r * TB * TB;   // column-major: element (row, k) at k*TB + row
@@ -85,9 +93,16 @@ __global__ void __launch_bounds__(256) trsv_coupling_kernel(const T* __restrict_
         const int row = i % TB, col = i / TB;
         T acc = T(0);
 #pragma unroll 8
-        for (int k = 0; k < TB; ++k) acc = tfma(dp[k * TB + row], s_a[k][col], acc);
+        for (int k = 0; k < TB; ++k) acc = tfma(trans ? dp[row * TB + k] : dp[k * TB + row], s_a[k][col], acc);
         out[i] = acc;
     }
+}
+
+// x[perm[i]] = z[i]: the row interchanges of a transposed solve (A^T = U^T L^T P)
+template <typename T>
+__global__ void perm_scatter_kernel(const T* __restrict__ z, const int* __restrict__ perm, T* __restrict__ x, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[perm[i]] = z[i];
 }
 
 struct TrsvSync {
@@ -306,7 +321,7 @@ struct Trsv2Sync {
 
 constexpr int TRSV2_CH = 8;   // far blocks per partial item
 
-template <typename T, bool UPPER>
+template <typename T, bool UPPER, bool TRANS>
 __global__ void __launch_bounds__(256, 1) trsv2_kernel(const T* __restrict__ A, long long lda, int n,
                                                        const T* __restrict__ dinv, const T* __restrict__ wmat,
                                                        const T* __restrict__ B, const int* __restrict__ perm,
@@ -334,13 +349,24 @@ __global__ void __launch_bounds__(256, 1) trsv2_kernel(const T* __restrict__ A, 
         }
         __syncwarp();
     };
+    // block (r, c) of the triangular factor being solved with; TRANS: of its transpose,
+    // element (i, j) = A[c*TB + j, r*TB + i] — 16 contiguous values per thread
     auto load_blk = [&](int d, int grow, bool rok, T* dst) {
         const int c = UPPER ? (nblk - 1 - d) : d;
-        const T* ap = A + (long long)(c * TB + q * 16) * lda + grow;
+        if constexpr (!TRANS) {
+            const T* ap = A + (long long)(c * TB + q * 16) * lda + grow;
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-            const int gc = c * TB + q * 16 + jj;
-            dst[jj] = (rok && gc < n) ? ap[(long long)jj * lda] : T(0);
+            for (int jj = 0; jj < 16; ++jj) {
+                const int gc = c * TB + q * 16 + jj;
+                dst[jj] = (rok && gc < n) ? ap[(long long)jj * lda] : T(0);
+            }
+        } else {
+            const T* ap = A + (long long)grow * lda + (c * TB + q * 16);
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int gc = c * TB + q * 16 + jj;
+                dst[jj] = (rok && gc < n) ? ap[jj] : T(0);
+            }
         }
     };
 
@@ -405,14 +431,17 @@ __global__ void __launch_bounds__(256, 1) trsv2_kernel(const T* __restrict__ A, 
             T myb = T(0);
             if (tid < TB && rok) {
                 if (!UPPER && perm != nullptr) myb = B[perm[grow]];
+                else if (!UPPER && TRANS) myb = B[grow];
                 else myb = X[grow];
             }
             T dv[16], wv[16], av[16];
             {
-                const T* dp = dinv + (long long)r * TB * TB + (q * 16) * TB + row;
+                // TRANS: the inverse of the transposed diagonal block is the transpose of the inverse
+                const T* dp = TRANS ? dinv + (long long)r * TB * TB + row * TB + q * 16
+                                    : dinv + (long long)r * TB * TB + (q * 16) * TB + row;
                 const T* wp = wmat + (long long)r * TB * TB + (q * 16) * TB + row;
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) { dv[jj] = dp[jj * TB]; wv[jj] = wp[jj * TB]; }
+                for (int jj = 0; jj < 16; ++jj) { dv[jj] = TRANS ? dp[jj] : dp[jj * TB]; wv[jj] = wp[jj * TB]; }
             }
             if (t >= 2) load_blk(t - 2, grow, rok, av);
             // sum of the partial items, fixed order

@@ -315,10 +315,14 @@ def _check_residual_safety(cache, A_original, u):
     return np.linalg.norm(r) <= cache.abstol + cache.reltol * np.linalg.norm(cache.b)
 
 
-def solve_(cache: LinearCache, alg=None) -> LinearSolution:
+def solve_(cache: LinearCache, alg=None, adjoint: bool = False) -> LinearSolution:
     """`solve!(cache)` — protocol of src/openblas.jl:362-459: factor only when
     `cache.isfresh`; on info != 0 return ReturnCode.Failure and LEAVE isfresh
-    set; otherwise getrs from cache.b into cache.u."""
+    set; otherwise getrs from cache.b into cache.u.
+
+    `adjoint=True` mirrors `solve!(cache; adjoint = true)` (src/common.jl:1012-1027):
+    adjoint(A) u = b with the SAME cached factorization (getrs with trans = 'T'; the
+    element types here are real, so adjoint == transpose)."""
     alg = alg or cache.alg
     cv = cache.cacheval
     A = cache.A
@@ -339,10 +343,14 @@ def solve_(cache: LinearCache, alg=None) -> LinearSolution:
             return LinearSolution(cache.u, ReturnCode.Failure, alg)
         cache.isfresh = False
     if isinstance(A, BlockDiagonal):
+        if adjoint:
+            raise NotImplementedError("adjoint solves of BlockDiagonal problems")
         x = _solve_blockdiag(cache)
     else:
-        x = cv.handle.solve(np.asarray(cache.b))
+        x = cv.handle.solve(np.asarray(cache.b), trans="T" if adjoint else "N")
     cache.u[...] = x
+    if adjoint:
+        return LinearSolution(cache.u, ReturnCode.Success, alg)
     if check_safety and not _check_residual_safety(cache, A, cache.u):
         return LinearSolution(cache.u, ReturnCode.Failure, alg)
     return LinearSolution(cache.u, ReturnCode.Success, alg)

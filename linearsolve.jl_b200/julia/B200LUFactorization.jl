@@ -171,14 +171,23 @@ end
 end
 
 # getrs: same call shape as openblas_getrs! (src/openblas.jl:247-278); u may alias b
-@inline function _direct_lu_solve!(c::B200LUCache, u::StridedVecOrMat{T}, b::StridedVecOrMat{T}, alg) where {T}
+@inline function _direct_lu_solve!(c::B200LUCache, u::StridedVecOrMat{T}, b::StridedVecOrMat{T}, alg;
+        trans::Char = 'N') where {T}
     chkstride1(u, b)
     size(b, 1) == c.n || throw(DimensionMismatch("b has leading dimension $(size(b, 1)), but needs $(c.n)"))
     rc = ccall((:b200lu_solve, libb200lu[]), Cint,
         (Ptr{Cvoid}, UInt8, Int64, Ptr{T}, Int64, Ptr{T}, Int64),
-        c.handle, UInt8('N'), size(b, 2), b, max(1, stride(b, 2)), u, max(1, stride(u, 2)))
+        c.handle, UInt8(trans), size(b, 2), b, max(1, stride(b, 2)), u, max(1, stride(u, 2)))
     rc == 0 || _b200lu_error(c, rc)
     return u
+end
+
+# `solve!(cache; adjoint = true)` (src/common.jl:1012-1027) reuses the cached factorization:
+# the hooks of src/adjoint_factorization.jl:149-153.  Real element types: adjoint == transpose.
+_custom_can_reuse_adjoint_factorization(::B200LUFactorization, c::B200LUCache) = c.handle != C_NULL
+function _custom_adjoint_factorization_solve(alg::B200LUFactorization, c::B200LUCache, A, b)
+    u = similar(b)
+    return _direct_lu_solve!(c, u, b, alg; trans = 'T')
 end
 
 function SciMLBase.solve!(

@@ -164,3 +164,32 @@ def test_threads_independent_caches(gpu_required, ls):
     [t.join() for t in ts]
     for (A, b), u in zip(probs, out):
         np.testing.assert_allclose(A @ u, b, rtol=1e-10)
+
+
+@pytest.mark.parametrize("dtype,n", [(np.float64, 5), (np.float64, 64), (np.float64, 65), (np.float64, 300),
+                                     (np.float64, 1000), (np.float64, 2500), (np.float32, 700)])
+def test_adjoint_solve_reuses_factorization(gpu_required, ls, dtype, n):
+    """`solve!(cache; adjoint = true)` (reference src/common.jl:1012-1027, test/Core/adjoint.jl): the
+    cached factorization of A solves adjoint(A) u = b — getrs with trans = 'T' through the C ABI;
+    backward error of the transposed system <= 10 n eps; vector and matrix right-hand sides."""
+    rng = np.random.default_rng(400 + n)
+    A = np.asfortranarray(rng.random((n, n)).astype(dtype) + (0.5 * np.eye(n)).astype(dtype))
+    b = rng.random(n).astype(dtype)
+    cache = ls.init(ls.LinearProblem(A, b), ls.B200LUFactorization())
+    x = ls.solve_(cache).u.copy()
+    eps = np.finfo(dtype).eps
+    assert np.linalg.norm(A.astype(np.float64) @ x - b) / (np.linalg.norm(A) * np.linalg.norm(x)) <= 10 * n * eps
+    sol = ls.solve_(cache, adjoint=True)
+    assert sol.retcode == ls.ReturnCode.Success
+    xt = sol.u.copy()
+    r = A.T.astype(np.float64) @ xt - b
+    assert np.linalg.norm(r) / (np.linalg.norm(A) * np.linalg.norm(xt)) <= 10 * n * eps
+    # the factorization was reused, and a normal solve still works afterwards
+    assert not cache.isfresh
+    x2 = ls.solve_(cache).u
+    assert np.array_equal(x, x2)
+    # matrix right-hand side through the handle
+    B = np.asfortranarray(rng.random((n, 3)).astype(dtype))
+    Xt = cache.cacheval.handle.solve(B, trans="T")
+    R = A.T.astype(np.float64) @ Xt - B
+    assert np.linalg.norm(R) / (np.linalg.norm(A) * np.linalg.norm(Xt)) <= 10 * n * eps
