@@ -431,7 +431,14 @@ static int launch_panel_cluster_cfg(b200lu_handle* h, cudaStream_t st, PanelArgs
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CU_TRY(h, cudaLaunchKernelEx(&cfg, kern, p));
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+    if (le != cudaSuccess) {
+        // a cluster of this size cannot be placed on this device / partition (MIG, MPS limits):
+        // fall back to the L2-mailbox kernel for the rest of the handle's life
+        cudaGetLastError();
+        h->opt[B200LU_OPT_PANEL_MODE] = 1;
+        return -1000;
+    }
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -470,14 +477,17 @@ static int launch_panel_any(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda
     p.mail = nullptr;
     p.deverr = h->d_deverr;
     p.dbg = h->d_pdbg ? h->d_pdbg + 16 * (h->pdbg_n++ % 4096) : nullptr;
+    int rc;
     if constexpr (sizeof(T) == 8) {
-        if (bw > 16) return launch_panel_cluster_cfg<T, 32, 2>(h, st, p);
-        if (m <= PCL_ROWS2) return launch_panel_cluster_cfg<T, 16, 2>(h, st, p);
-        return launch_panel_cluster_cfg<T, 16, 4>(h, st, p);
+        if (bw > 16) rc = launch_panel_cluster_cfg<T, 32, 2>(h, st, p);
+        else if (m <= PCL_ROWS2) rc = launch_panel_cluster_cfg<T, 16, 2>(h, st, p);
+        else rc = launch_panel_cluster_cfg<T, 16, 4>(h, st, p);
     } else {
-        if (m <= PCL_ROWS2) return launch_panel_cluster_cfg<T, 32, 2>(h, st, p);
-        return launch_panel_cluster_cfg<T, 32, 4>(h, st, p);
+        if (m <= PCL_ROWS2) rc = launch_panel_cluster_cfg<T, 32, 2>(h, st, p);
+        else rc = launch_panel_cluster_cfg<T, 32, 4>(h, st, p);
     }
+    if (rc == -1000) return launch_panel_base<T>(h, st, A, lda, nrows, j0, wc, pc0, pc1);
+    return rc;
 }
 
 // ---------------------------------------------------------- recursive panel --

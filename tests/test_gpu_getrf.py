@@ -102,8 +102,10 @@ def test_singularity_info(gpu_required, ls, oracle):
     zero matrix => info == 1; NaN propagates"""
     rng = np.random.default_rng(11)
     h = _handle(ls)
-    for n in (10, 50, 130, 300):
-        for zc in (0, 3, n - 1):
+    # n = 1500: a 4-CTA cluster — the zero-pivot path then crosses CTAs (remote shared-memory stores
+    # of the row at position k + a cluster barrier), and a zero column inside the second 32-wide block
+    for n in (10, 50, 130, 300, 1500):
+        for zc in (0, 3, n - 1) + ((40, 700) if n == 1500 else ()):
             A = np.asfortranarray(rng.standard_normal((n, n)))
             A[:, zc] = 0.0
             _, info = h.factor(A)
@@ -119,6 +121,16 @@ def test_singularity_info(gpu_required, ls, oracle):
     An = np.asfortranarray(rng.standard_normal((30, 30)))
     An[1, 1] = np.nan
     h.factor(An)
+    assert np.isnan(h.get_factors()).any()
+    # zero matrix / all-NaN column on a multi-CTA cluster
+    Z = np.zeros((1100, 1100), order="F")
+    _, info = h.factor(Z)
+    assert info == 1
+    Ac = np.asfortranarray(rng.standard_normal((1100, 1100)))
+    Ac[:, 5] = np.nan
+    ipiv_c, _ = h.factor(Ac)
+    _, ipiv_ref_c, _ = oracle.lapack_getrf(Ac)
+    assert np.array_equal(np.asarray(ipiv_c)[:6], np.asarray(ipiv_ref_c)[:6])   # NaN never wins: kp = k at the NaN column
     assert np.isnan(h.get_factors()).any()
 
 
