@@ -99,7 +99,7 @@ enum {
     B200LU_OPT_SOLVE_NRHS_TILE = 4, /* right-hand sides per triangular sweep     */
     B200LU_OPT_PROFILE = 5,     /* 1: bracket every trailing GEMM with CUDA events */
     B200LU_OPT_PANEL_RPT = 6,   /* rows per thread in the base panel: 0 auto, 1, 2 */
-    B200LU_OPT_GEMM_CFG = 7,    /* FP64 trailing-update tile configuration 0..2      */
+    B200LU_OPT_GEMM_CFG = 7,    /* FP64 trailing-update tile configuration 0..2, 3 = auto (default) */
     B200LU_OPT_PANEL_MODE = 8,  /* base panel: 0 auto (cluster/DSMEM kernel when the panel fits
                                    16 CTAs, else L2 mailbox), 1 always L2 mailbox  */
     B200LU_OPT_SGEMM_MODE = 9,  /* FP32 trailing update: 0 auto (tcgen05 3xTF32 kernel for large

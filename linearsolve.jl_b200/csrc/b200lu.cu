@@ -267,7 +267,9 @@ static int launch_dgemm_cfg(b200lu_handle* h, cudaStream_t st, int M, int N, int
 static int launch_gemm(b200lu_handle* h, cudaStream_t st, int M, int N, int K, const double* A,
                        int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    switch ((int)h->opt[B200LU_OPT_GEMM_CFG]) {
+    int cfg = (int)h->opt[B200LU_OPT_GEMM_CFG];
+    if (cfg == 3) cfg = (h->n >= 12288) ? 1 : 0;   // auto: 8 warps of 32x32 win by ~1.3 % once the update dominates
+    switch (cfg) {
         case 1: return launch_dgemm_cfg<128, 64, 4, 2, 3, 2>(h, st, M, N, K, A, lda, B, ldb, C, ldc);
         case 2: return launch_dgemm_cfg<128, 128, 2, 4, 4, 1>(h, st, M, N, K, A, lda, B, ldb, C, ldc);
         default: return launch_dgemm_cfg<128, 64, 2, 2, 3, 2>(h, st, M, N, K, A, lda, B, ldb, C, ldc);
@@ -976,7 +978,7 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     h->opt[B200LU_OPT_SOLVE_NRHS_TILE] = 8;
     h->opt[B200LU_OPT_PROFILE] = 0;
     h->opt[B200LU_OPT_PANEL_RPT] = 0;
-    h->opt[B200LU_OPT_GEMM_CFG] = 0;
+    h->opt[B200LU_OPT_GEMM_CFG] = 3;
     h->opt[B200LU_OPT_PANEL_MODE] = 0;
     h->opt[B200LU_OPT_SGEMM_MODE] = 0;
     h->opt[B200LU_OPT_TRSV_MODE] = 0;
@@ -1136,7 +1138,7 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_PANEL_CTAS && (value < 1 || value > PANEL_GMAX)) return -3;
     if (option == B200LU_OPT_REFINE_MAXIT && value < 0) return -3;
     if (option == B200LU_OPT_PANEL_RPT && (value < 0 || value > 2)) return -3;
-    if (option == B200LU_OPT_GEMM_CFG && (value < 0 || value > 2)) return -3;
+    if (option == B200LU_OPT_GEMM_CFG && (value < 0 || value > 3)) return -3;
     if (option == B200LU_OPT_PANEL_MODE && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_SGEMM_MODE && (value < 0 || value > 2)) return -3;
     if (option == B200LU_OPT_TRSV_MODE && (value < 0 || value > 1)) return -3;
