@@ -66,7 +66,9 @@ __global__ void __launch_bounds__(batched_threads(NMAX)) getrf_batched_kernel(
         const T v = done ? T(0) : tabs(a[0]);                                                      \
         const int wl = pcl_warp_argmax(v, pos);                                                    \
         if (lane == wl) {                                                                          \
-            _Pragma("unroll") for (int c = 0; c < (LIVE); ++c) sh.cand_row[par][warp][c] = a[c];   \
+            if (NW == 1) {                                                                         \
+                _Pragma("unroll") for (int c = 0; c < (LIVE); ++c) sh.cand_row[par][0][c] = a[c];  \
+            }                                                                                      \
             sh.cand_val[par][warp] = v;                                                            \
             sh.cand_rinv[par][warp] = T(1) / a[0];   /* off the other threads' critical path */    \
             sh.cand_pos[par][warp] = pos;                                                          \
@@ -82,6 +84,14 @@ __global__ void __launch_bounds__(batched_threads(NMAX)) getrf_batched_kernel(
             const int op = sh.cand_pos[par][w];                                                    \
             if (ov > bv || (ov == bv && op < bp)) { bv = ov; bp = op; bw = w; }                    \
         }                                                                                          \
+        if (NW > 1) {                                                                              \
+            /* only the system's winner stages its row (half the shared-memory stores of staging */ \
+            /* every warp's candidate), at the price of a second barrier                         */ \
+            if (bv > T(0) && t == sh.cand_thr[par][bw]) {                                          \
+                _Pragma("unroll") for (int c = 0; c < (LIVE); ++c) sh.cand_row[par][0][c] = a[c];  \
+            }                                                                                      \
+            __syncthreads();                                                                       \
+        }                                                                                          \
         const bool none = !(bv > T(0));   /* all-zero / all-NaN subcolumn: kp = k */               \
         if (none) {                                                                                \
             /* the "pivot" row is the row at position k: a second, rare exchange */                \
@@ -95,7 +105,7 @@ __global__ void __launch_bounds__(batched_threads(NMAX)) getrf_batched_kernel(
             bw = 0;                                                                                \
             bp = k;                                                                                \
         }                                                                                          \
-        const T* prow = &sh.cand_row[par][bw][0];                                                  \
+        const T* prow = &sh.cand_row[par][0][0];                                                   \
         const int pthr = sh.cand_thr[par][bw];                                                     \
         const T pv = prow[0];                                                                      \
         /* the pivot row is frozen: all threads copy its staged entries into the tile */           \
