@@ -365,9 +365,16 @@ static int launch_gemm(b200lu_handle* h, cudaStream_t st, int M, int N, int K, c
     // The tcgen05 path owns one scratch set: main-stream updates only (the panel recursion's small
     // GEMMs run concurrently on the panel stream); K <= 256 by construction (K = panel width).
     const int64_t mode = h->opt[B200LU_OPT_SGEMM_MODE];   // 0 auto, 1 FFMA, 2 tcgen05 whenever legal (tests)
-    const bool tc = mode != 1 && st == h->s_main && K <= 256 && (ldc % 4) == 0 &&
+    const bool tc = mode != 1 && st == h->s_main && (ldc % 4) == 0 &&
                     (mode == 2 || (int64_t)M * N >= (int64_t)512 * 512);
-    if (tc) return launch_sgemm_tc(h, st, M, N, K, A, lda, B, ldb, C, ldc);
+    if (tc) {
+        // the split scratch holds 256 k-columns: deeper updates (the blocked TRSM of getrs) go in slabs
+        for (int k0 = 0; k0 < K; k0 += 256) {
+            const int rc = launch_sgemm_tc(h, st, M, N, std::min(256, K - k0), A + (int64_t)k0 * lda, lda, B + k0, ldb, C, ldc);
+            if (rc) return rc;
+        }
+        return 0;
+    }
     return launch_sgemm_ffma(h, st, M, N, K, A, lda, B, ldb, C, ldc);
 }
 
@@ -843,6 +850,60 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T
     int rc = ensure_trsv_groups(h, groups, NR);
     if (rc) return rc;
     TrsvSync sy{(unsigned long long*)h->d_tflags, h->d_tticket, h->d_deverr};
+    // ---- many right-hand sides: blocked TRSM.  Diagonal blocks of `db` rows are solved by the
+    // block-row kernel, everything off the diagonal is one tensor-core GEMM per block column
+    // (X_rest -= L_panel X_j / U_panel X_j): 2 n^2 nrhs flops on the trailing-update kernels
+    // instead of FMA mat-vecs.  (reference: getrs with a matrix right-hand side,
+    // src/openblas.jl:247-278; `_naive_lu_ldiv!` matrix branch, src/factorization.jl:480-488)
+    static const int db_env = getenv("B200LU_TRSM_DB") ? atoi(getenv("B200LU_TRSM_DB")) : 0;
+    const int db = db_env >= 64 ? (db_env / 64) * 64 : 1024;   // measured: 128/256/512/1024 -> 4.06/3.52/3.22/3.02 ms at n = 8192, 100 rhs
+    if (nrhs >= 16 && h->opt[B200LU_OPT_TRSV_MODE] == 0 && n > db && (ldx % 4) == 0 && (n % 4) == 0 &&
+        (reinterpret_cast<uintptr_t>(X) % 16) == 0) {   // 16-byte cp.async chunks of the GEMM operands
+        // P B -> X (B does not alias X here)
+        perm_gather_kernel<T><<<dim3(cdiv(n, 256), nrhs), 256, 0, st>>>(B, ldb, h->d_perm, X, ldx, n);
+        LAUNCH_CHECK(h);
+        const int nd = cdiv(n, db);
+        auto diag_solve = [&](int j, bool upper) -> int {
+            const int j0 = j * db, nj = std::min(db, n - j0), nb4 = cdiv(nj, TRSV_TB);
+            if (h->trsv_epoch > (1u << 30)) {
+                CU_TRY(h, cudaMemsetAsync(h->d_tflags, 0, h->cap_tflag_bytes, st));
+                h->trsv_epoch = 0;
+            }
+            const unsigned epoch = ++h->trsv_epoch;
+            const size_t boff = (size_t)(j0 / TRSV_TB) * TRSV_TB * TRSV_TB;
+            const T* Ad = A + (int64_t)j0 * lda + j0;
+            T* Xd = X + j0;
+            dim3 g(nb4 * groups);
+#define TRSV_SUB(NRV)                                                                             \
+    if (upper)                                                                                    \
+        trsv_block_kernel<T, NRV, true><<<g, 256, 0, st>>>(Ad, lda, nj, (const T*)h->d_dinvU + boff, (const T*)h->d_wU + boff, \
+                                                           nullptr, 0, nullptr, Xd, ldx, nrhs, sy, epoch, nb4); \
+    else                                                                                          \
+        trsv_block_kernel<T, NRV, false><<<g, 256, 0, st>>>(Ad, lda, nj, (const T*)h->d_dinvL + boff, (const T*)h->d_wL + boff, \
+                                                            nullptr, 0, nullptr, Xd, ldx, nrhs, sy, epoch, nb4);
+            if (NR == 4) { TRSV_SUB(4) } else { TRSV_SUB(8) }
+#undef TRSV_SUB
+            LAUNCH_CHECK(h);
+            return 0;
+        };
+        for (int j = 0; j < nd; ++j) {            // forward: L
+            if ((rc = diag_solve(j, false))) return rc;
+            const int j0 = j * db, j1 = std::min(n, j0 + db);
+            if (j1 < n) {
+                rc = launch_gemm(h, st, n - j1, nrhs, j1 - j0, A + (int64_t)j0 * lda + j1, lda, X + j0, ldx, X + j1, ldx);
+                if (rc) return rc;
+            }
+        }
+        for (int j = nd - 1; j >= 0; --j) {       // backward: U
+            if ((rc = diag_solve(j, true))) return rc;
+            const int j0 = j * db, j1 = std::min(n, j0 + db);
+            if (j0 > 0) {
+                rc = launch_gemm(h, st, j0, nrhs, j1 - j0, A + (int64_t)j0 * lda, lda, X + j0, ldx, X, ldx);
+                if (rc) return rc;
+            }
+        }
+        return 0;
+    }
     dim3 grid(nblk * groups);
     for (int upper = 0; upper < 2; ++upper) {
         if (h->trsv_epoch > (1u << 30)) {

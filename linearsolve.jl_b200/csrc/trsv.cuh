@@ -98,6 +98,15 @@ __global__ void __launch_bounds__(256) trsv_coupling_kernel(const T* __restrict_
     }
 }
 
+// X[i, c] = B[perm[i], c]: the row interchanges of getrs applied to a block of right-hand sides
+template <typename T>
+__global__ void perm_gather_kernel(const T* __restrict__ B, long long ldb, const int* __restrict__ perm,
+                                   T* __restrict__ X, long long ldx, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long c = blockIdx.y;
+    if (i < n) X[c * ldx + i] = B[c * ldb + perm[i]];
+}
+
 // x[perm[i]] = z[i]: the row interchanges of a transposed solve (A^T = U^T L^T P)
 template <typename T>
 __global__ void perm_scatter_kernel(const T* __restrict__ z, const int* __restrict__ perm, T* __restrict__ x, int n) {
