@@ -38,7 +38,7 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--n", "--size", dest="n", type=int, default=8192)   # use --size under torchrun (its parser abbreviates --n)
-    p.add_argument("--nrhs", type=int, default=100)
+    p.add_argument("--nrhs", type=int, default=None)   # config 2: 100; config 3 (mixed) names no count: 1
     p.add_argument("--workload", default="lu", choices=["lu", "batched", "mixed", "dist"])
     p.add_argument("--batch", type=int, default=65536)
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -49,7 +49,10 @@ def parse():
     p.add_argument("--gemm-cfg", type=int, default=-1)
     p.add_argument("--panel-mode", type=int, default=-1)
     p.add_argument("--sgemm-mode", type=int, default=-1)
-    return p.parse_args()
+    args = p.parse_args()
+    if args.nrhs is None:
+        args.nrhs = 1 if args.workload == "mixed" else 100
+    return args
 
 
 def lu_flops(n):
