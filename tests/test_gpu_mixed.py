@@ -47,3 +47,27 @@ def test_mixed_singular(gpu_required, ls):
     A = np.ones((50, 50))
     sol = ls.solve(ls.LinearProblem(A, np.ones(50)), ls.B200LU32MixedLUFactorization())
     assert sol.retcode == ls.ReturnCode.Failure
+
+
+def test_mixed_full_size_config3(gpu_required, ls):
+    """BASELINE config 3 at full size: FP32 factor (cluster panels of 16384 rows with 4 rows per thread,
+    tcgen05 / TMA / TMEM trailing update) + FP64 refinement at n = 16384, well-conditioned rand + 5 I
+    (reference idiom, test/Core/test_mixed_precision.jl:16-17).  Size-independent property: backward
+    error <= 10 n eps64, computed on the device."""
+    import torch
+    C = ls._capi
+    n = 16384
+    dev = torch.device("cuda", 0)
+    h = ls.Handle(C.MIXED)
+    A = torch.empty((n, n), dtype=torch.float64, device=dev)        # column-major: A[j, i] = entry (i, j)
+    b = torch.empty((1, n), dtype=torch.float64, device=dev)
+    x = torch.empty_like(b)
+    h.fill_uniform_device(A.data_ptr(), n, n, n, seed=31, diag_shift=5.0)
+    h.fill_uniform_device(b.data_ptr(), n, n, 1, seed=32)
+    assert h.factor_device(A.data_ptr(), n, n) == 0
+    h.solve_device(b.data_ptr(), n, x.data_ptr(), n, 1)
+    torch.cuda.synchronize()
+    r = A.T @ x[0] - b[0]
+    berr = (r.norm() / (A.norm() * x[0].norm())).item()
+    assert berr <= 10 * n * np.finfo(np.float64).eps, berr
+    assert h.counter(C.C_REFINE_ITERS) >= 1
