@@ -92,6 +92,9 @@ struct b200lu_handle {
     double* d_r = nullptr;     // residual (n)
     float* d_r32 = nullptr;    // residual cast / correction (n)
     double* d_scal = nullptr;  // [4] norms
+    double* d_cscal = nullptr; // [2 * cap_cscal] per-column norms of the matrix-RHS refinement
+    double* h_cscal = nullptr;
+    int cap_cscal = 0;
     double normA_F = 0.0;
     int last_refine_iters = 0;
     // pinned host staging
@@ -950,10 +953,83 @@ static int getrs_device(b200lu_handle* h, const T* B, int64_t ldb, T* X, int64_t
 }
 
 // MIXED: FP32 factors + FP64 residual refinement, one right-hand side at a time.
+// MIXED with a matrix right-hand side: all columns refined together — FP32 getrs of the whole
+// block (blocked TRSM on the tensor cores), residual R = B - A X as ONE FP64 GEMM on the DMMA
+// kernel (A is read once per 64 columns instead of once per column), per-column norms, stop when
+// the worst column has converged or stagnates.
+static int refine_solve_block_device(b200lu_handle* h, const double* B, int64_t ldb, double* X,
+                                     int64_t ldx, int nrhs) {
+    const int n = (int)h->n;
+    cudaStream_t st = h->s_main;
+    const int maxit = (int)h->opt[B200LU_OPT_REFINE_MAXIT];
+    const double eps = 2.220446049250313e-16;
+    if (nrhs > h->cap_cscal) {
+        CU_TRY(h, cudaStreamSynchronize(st));
+        free_dev(h->d_cscal);
+        if (h->h_cscal) cudaFreeHost(h->h_cscal);
+        CU_TRY(h, cudaMalloc((void**)&h->d_cscal, (size_t)2 * nrhs * sizeof(double)));
+        CU_TRY(h, cudaMallocHost((void**)&h->h_cscal, (size_t)2 * nrhs * sizeof(double)));
+        h->cap_cscal = nrhs;
+    }
+    // scratch (the lower halves of d_B / d_X are free here, see b200lu_solve): R (FP64), then
+    // two FP32 blocks W32 (rhs / correction input) and C32 (solution / correction output)
+    int rc = ensure_rhs(h, nrhs + 1);
+    if (rc) return rc;
+    const int64_t ldr = ((n + 3) / 4) * 4;
+    if ((size_t)ldr * nrhs * 8 > (size_t)h->cap_n * h->cap_rhs * 8) return set_err(h, 2, "refinement scratch too small");
+    double* R = (double*)h->d_B;
+    float* W32 = (float*)h->d_X;
+    float* C32 = W32 + (size_t)ldr * nrhs;
+    const dim3 g2(cdiv(n, 256), nrhs);
+    cast2d_kernel<double, float><<<g2, 256, 0, st>>>(B, ldb, W32, ldr, n, nrhs);
+    LAUNCH_CHECK(h);
+    rc = getrs_device<float>(h, W32, ldr, C32, ldr, nrhs);
+    if (rc) return rc;
+    cast2d_kernel<float, double><<<g2, 256, 0, st>>>(C32, ldr, X, ldx, n, nrhs);
+    LAUNCH_CHECK(h);
+    double prev = 1e300;
+    h->last_refine_iters = 0;
+    for (int it = 0; it < maxit; ++it) {
+        // R = B - A X
+        CU_TRY(h, cudaMemcpy2DAsync(R, (size_t)ldr * 8, B, (size_t)ldb * 8, (size_t)n * 8, nrhs, cudaMemcpyDeviceToDevice, st));
+        rc = launch_gemm(h, st, n, nrhs, n, h->dA64, h->ldd, X, ldx, R, ldr);
+        if (rc) return rc;
+        CU_TRY(h, cudaMemsetAsync(h->d_cscal, 0, (size_t)2 * nrhs * sizeof(double), st));
+        colsumsq_kernel<<<dim3(std::min(cdiv(n, 256), 64), nrhs), 256, 0, st>>>(R, ldr, n, h->d_cscal);
+        LAUNCH_CHECK(h);
+        colsumsq_kernel<<<dim3(std::min(cdiv(n, 256), 64), nrhs), 256, 0, st>>>(X, ldx, n, h->d_cscal + nrhs);
+        LAUNCH_CHECK(h);
+        CU_TRY(h, cudaMemcpyAsync(h->h_cscal, h->d_cscal, (size_t)2 * nrhs * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaStreamSynchronize(st));
+        double worst = 0.0;
+        for (int c = 0; c < nrhs; ++c) {
+            const double berr = sqrt(h->h_cscal[c]) / (h->normA_F * sqrt(h->h_cscal[nrhs + c]) + 1e-300);
+            if (!(berr == berr)) return set_err(h, 3, "refinement produced NaN");
+            worst = std::max(worst, berr);
+        }
+        h->last_refine_iters = std::max(h->last_refine_iters, it);
+        if (!(worst > 2.0 * eps) || !(worst < 0.5 * prev)) break;
+        prev = worst;
+        cast2d_kernel<double, float><<<g2, 256, 0, st>>>(R, ldr, W32, ldr, n, nrhs);
+        LAUNCH_CHECK(h);
+        rc = getrs_device<float>(h, W32, ldr, C32, ldr, nrhs);
+        if (rc) return rc;
+        axpy_f32_cols_kernel<<<g2, 256, 0, st>>>(X, ldx, C32, ldr, n);
+        LAUNCH_CHECK(h);
+        h->last_refine_iters = std::max(h->last_refine_iters, it + 1);
+    }
+    return 0;
+}
+
 static int refine_solve_device(b200lu_handle* h, const double* B, int64_t ldb, double* X,
                                int64_t ldx, int nrhs) {
     const int n = (int)h->n;
     cudaStream_t st = h->s_main;
+    // matrix right-hand side: refine the block as a whole when the GEMM operands are 16-byte aligned
+    // and B does not alias X (the residual needs the original B in every sweep)
+    if (nrhs >= 4 && 2 * nrhs <= n && (const void*)B != (const void*)X && (ldx % 2) == 0 && (n % 2) == 0 &&
+        (reinterpret_cast<uintptr_t>(X) % 16) == 0)
+        return refine_solve_block_device(h, B, ldb, X, ldx, nrhs);
     const int maxit = (int)h->opt[B200LU_OPT_REFINE_MAXIT];
     const double eps = 2.220446049250313e-16;
     int rc = ensure_rhs(h, 1);
@@ -1091,7 +1167,8 @@ void b200lu_destroy(b200lu_handle* h) {
     free_dev(h->dA); free_dev(h->dA64); free_dev(h->d_ipiv); free_dev(h->d_perm);
     free_dev(h->d_info); free_dev(h->d_deverr); free_dev(h->d_plans); free_dev(h->d_panelsync); free_dev(h->d_split);
     free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_wL); free_dev(h->d_wU); free_dev(h->d_wLt); free_dev(h->d_wUt); free_dev(h->d_tflags); free_dev(h->d_tticket); free_dev(h->d_t2items); free_dev(h->d_t2x); free_dev(h->d_t2p); free_dev(h->d_t2ticket);
-    free_dev(h->d_B); free_dev(h->d_X); free_dev(h->d_r); free_dev(h->d_r32); free_dev(h->d_scal);
+    free_dev(h->d_B); free_dev(h->d_X); free_dev(h->d_r); free_dev(h->d_r32); free_dev(h->d_scal); free_dev(h->d_cscal);
+    if (h->h_cscal) cudaFreeHost(h->h_cscal);
     free_dev(h->dB_LU); free_dev(h->dB_ipiv); free_dev(h->dB_info); free_dev(h->dB_perm); free_dev(h->dB_in);
     free_dev(h->dB_rhs); free_dev(h->dB_x);
     if (h->h_ipiv) cudaFreeHost(h->h_ipiv);

@@ -71,3 +71,22 @@ def test_mixed_full_size_config3(gpu_required, ls):
     berr = (r.norm() / (A.norm() * x[0].norm())).item()
     assert berr <= 10 * n * np.finfo(np.float64).eps, berr
     assert h.counter(C.C_REFINE_ITERS) >= 1
+
+
+@pytest.mark.parametrize("n,nrhs", [(1000, 20), (3000, 100), (1002, 7)])
+def test_mixed_matrix_rhs_block_refinement(gpu_required, ls, oracle, n, nrhs):
+    """MIXED with a matrix right-hand side: the whole block is refined together (FP32 blocked TRSM,
+    one FP64 GEMM residual per sweep); every column reaches backward error <= 10 n eps64."""
+    rng = np.random.default_rng(n + nrhs)
+    A = np.asfortranarray(rng.random((n, n)) + 5.0 * np.eye(n))
+    B = np.asfortranarray(rng.random((n, nrhs)))
+    h = ls.Handle(ls._capi.MIXED)
+    _, info = h.factor(A)
+    assert info == 0
+    X = h.solve(B)
+    eps = np.finfo(np.float64).eps
+    R = A @ X - B
+    nA = np.linalg.norm(A)
+    worst = max(np.linalg.norm(R[:, c]) / (nA * np.linalg.norm(X[:, c])) for c in range(nrhs))
+    assert worst <= 10 * n * eps, worst
+    assert worst <= 100 * eps, worst       # refinement gets to a few eps, not just under the bar
