@@ -20,7 +20,7 @@
 // CTA tile 128 x 256 (UMMA M = 128, N = 256, K = 8 per instruction), BK = 32, two stages of
 // 96 KB; persistent CTAs (one per SM) with TWO TMEM accumulators so the HBM-bound epilogue of a
 // tile overlaps the main loop of the next; warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
-// issuer, warps 2..5 = epilogue (TMEM -> registers, C += D with D = (-A) B by the instruction
+// issuer, warps 2.. = epilogue (TMEM -> registers, C += D with D = (-A) B by the instruction
 // descriptor's negate bit).
 #pragma once
 #include <cuda.h>   // CUtensorMap (types only; the encode entry point is fetched at run time)
@@ -28,12 +28,22 @@
 
 namespace b200lu {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 2;
+// BK = 16 (64-byte rows, 64-byte swizzle) x 4 stages of 48 KB: the producer runs three stages
+// (~1.2 us of tensor work) ahead of the MMA issuer — with BK = 32 x 2 stages of 96 KB the ring was one
+// stage deep and the tensor pipe idled on TMA latency (ncu: 35 % active).
+#ifndef TC_BK_CFG
+#define TC_BK_CFG 16
+#endif
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = TC_BK_CFG, TC_STAGES = (TC_BK_CFG == 16 ? 4 : 2);
+constexpr unsigned TC_SWIZZLE_BYTES = TC_BK * 4;                 // 64 or 128: one K-row of a stage
+constexpr unsigned TC_SBO = 8 * TC_SWIZZLE_BYTES;                // 8 rows of the swizzle atom
+constexpr unsigned long long TC_LAYOUT = (TC_BK_CFG == 16 ? 4ull : 2ull);   // UMMA layout type: SWIZZLE_64B / SWIZZLE_128B
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;              // 16 KB: one of A_hi / A_lo
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;              // 32 KB: one of B_hi / B_lo
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 96 KB
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;   // 197,888 B: one CTA per SM
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 4;                 // one warp per TMEM lane quarter (8 warps measured: no gain once C is prefetched into L2)
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 // hi = rn_tf32(x), lo = rn_tf32(x - hi) for a rows x cols column-major block
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ src, long long lds,
@@ -153,7 +163,7 @@ __device__ __forceinline__ void tc_commit(unsigned bar) {
 // shared-memory matrix descriptor, 128-byte swizzle, Blackwell version field = 1
 __device__ __forceinline__ unsigned long long tc_smem_desc(unsigned addr, unsigned lbo_bytes, unsigned sbo_bytes) {
     return (unsigned long long)((addr & 0x3FFFFu) >> 4) | ((unsigned long long)(lbo_bytes >> 4) << 16) |
-           ((unsigned long long)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+           ((unsigned long long)(sbo_bytes >> 4) << 32) | (1ull << 46) | (TC_LAYOUT << 61);
 }
 
 struct TcGemmParams {
@@ -198,7 +208,7 @@ sgemm3x_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             tc_mbar_init(bar_accf + 8 * a, 1);
-            tc_mbar_init(bar_acce + 8 * a, 4);   // one arrival per epilogue warp
+            tc_mbar_init(bar_acce + 8 * a, TC_EPI_WARPS);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tc_prefetch_tensormap(&tmAhi);
@@ -262,10 +272,10 @@ sgemm3x_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
                     const unsigned st = base + s * TC_STAGE_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < TC_BK / 8; ++ks) {
-                        const unsigned long long a_hi = tc_smem_desc(st + ks * 32, 16, 1024);
-                        const unsigned long long a_lo = tc_smem_desc(st + TC_A_BYTES + ks * 32, 16, 1024);
-                        const unsigned long long b_hi = tc_smem_desc(st + 2 * TC_A_BYTES + ks * 32, 16, 1024);
-                        const unsigned long long b_lo = tc_smem_desc(st + 2 * TC_A_BYTES + TC_B_BYTES + ks * 32, 16, 1024);
+                        const unsigned long long a_hi = tc_smem_desc(st + ks * 32, 16, TC_SBO);
+                        const unsigned long long a_lo = tc_smem_desc(st + TC_A_BYTES + ks * 32, 16, TC_SBO);
+                        const unsigned long long b_hi = tc_smem_desc(st + 2 * TC_A_BYTES + ks * 32, 16, TC_SBO);
+                        const unsigned long long b_lo = tc_smem_desc(st + 2 * TC_A_BYTES + TC_B_BYTES + ks * 32, 16, TC_SBO);
                         tc_mma_tf32(tacc, a_hi, b_lo, IDESC, (kb | ks) != 0 ? 1u : 0u);
                         tc_mma_tf32(tacc, a_lo, b_hi, IDESC, 1u);
                         tc_mma_tf32(tacc, a_hi, b_hi, IDESC, 1u);
@@ -276,19 +286,34 @@ sgemm3x_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
             }
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        // ===== epilogue: warps 2.., TMEM lane quarter = warp % 4, column slice = (warp - 2) / 4 =====
         const int q = warp & 3;
+        constexpr int CPW = TC_BN / (TC_EPI_WARPS / 4);   // columns per epilogue warp
+        const int cbase = ((warp - 2) >> 2) * CPW;
         int j = 0;
         for (int tile = tile0; tile < tile1; ++tile, ++j) {
             const int m0 = (tile % tiles_m) * TC_BM, n0 = (tile / tiles_m) * TC_BN;
             const int acc = j & 1;
             const unsigned aph = (unsigned)(j >> 1) & 1u;
             const int row = m0 + 32 * q + lane;
+            // The epilogue is latency-bound (32 loads in flight per thread, 8 dependent chunks per tile:
+            // ~12 us against a 9 us main loop).  While the main loop of THIS tile runs, pull the warp's
+            // 256 lines of C (one 128-byte line per column) into L2.
+            if (m0 + 32 * q < p.M) {
+#pragma unroll
+                for (int jj = 0; jj < CPW / 32; ++jj) {
+                    const int col = n0 + cbase + lane + 32 * jj;
+                    if (col < p.N) {
+                        const float* pf = p.C + (long long)col * p.ldc + (m0 + 32 * q);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                    }
+                }
+            }
             const bool ok = tc_mbar_wait(bar_accf + 8 * acc, aph);
             if (!ok) { if (lane == 0) atomicExch(p.deverr, DEV_ERR_GEMM_TIMEOUT); break; }
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < TC_BN / 32; ++c) {
+            for (int c = cbase / 32; c < (cbase + CPW) / 32; ++c) {
                 float cv[32];
                 float* cp = p.C + (long long)(n0 + c * 32) * p.ldc + row;
 #pragma unroll
