@@ -43,6 +43,7 @@ def parse():
     p.add_argument("--batch", type=int, default=65536)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-comparator", action="store_true")
     p.add_argument("--nb", type=int, default=0)
     p.add_argument("--lookahead", type=int, default=-1)
     p.add_argument("--rpt", type=int, default=-1)
@@ -312,7 +313,10 @@ def main():
         tc_peak = bf16 / 2.0 / 3.0
         roofline = {
             "bound": "tensor", "kernel": "sgemm3x_tc_kernel (tcgen05 kind::tf32, TMA-fed, TMEM accumulator, 3xTF32)",
-            "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": None,
+            "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak,
+            # dram bytes of ONE launch from the committed ncu capture (profiles/r01_ncu_sgemm3x_tc_details.txt:
+            # M=16128 N=15872 K=256, first trailing update at n=16384): 1.265e9 read + 0.984e9 written
+            "traffic": 2.2485e9, "traffic_algorithmic": 2 * 16128 * 15872 * 4 + 2 * (16128 + 15872) * 256 * 4,
             "peak_source": "measured bf16 burst %.0f TFLOP/s / 2 (tf32 rate) / 3 (MMAs per FP32-accurate product); "
                            "achieved counts 2MNK useful flops" % bf16,
             "launches_profiled": int(g_n), "gemm_share_of_getrf": (g_ms / 2) / t_fact_prof if t_fact_prof else None,
@@ -350,6 +354,28 @@ def main():
         "getrf_gflops": lu_flops(n) / ((tf / args.steps) * 1e-3) / 1e9,
         "backward_error": berr, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }
+
+    # ---------------- on-box GPU comparator (library code, reported for context only) ---------
+    if args.workload == "lu" and world == 1 and not args.no_comparator:
+        try:
+            Am = A_dev.t().contiguous()          # row-major copy of the math matrix for torch
+            torch.linalg.lu_factor(Am)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = 1e30
+            for _ in range(3):
+                e0.record()
+                torch.linalg.lu_factor(Am)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            line["comparators"] = {"torch_linalg_lu_factor_ms": best,
+                                   "torch_linalg_lu_factor_gflops": lu_flops(n) / (best * 1e-3) / 1e9,
+                                   "note": "cuSOLVER/MAGMA getrf behind torch.linalg.lu_factor on the same matrix, "
+                                           "device-resident, min of 3; not part of the product path"}
+            del Am
+        except Exception as ex:   # comparator only
+            line["comparators"] = {"error": str(ex)[:200]}
 
     # ---------------- e2e through the public API with pinned host buffers -----------------
     if not args.no_e2e:
