@@ -259,6 +259,10 @@ def main():
         h.solve_device(B_dev.data_ptr(), n, X_dev.data_ptr(), n, nrhs)
         return info, t_f, h.timing(C.T_SOLVE)
 
+    # roofline yardstick, probed BEFORE the load (cool GPU) and again after it: the larger one is the peak
+    # (after a long DMMA-heavy run the probe has read 20 % low while the timed region itself showed
+    # full clocks — a denominator measured in a worse power state would inflate the fraction)
+    peak_dmma_before = h.probe_peak(C.PEAK_FP64_DMMA)
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local)
@@ -295,7 +299,8 @@ def main():
         g_ms += h.timing(C.T_GEMM); g_fl += h.counter(C.C_GEMM_FLOPS); g_n += h.counter(C.C_GEMM_LAUNCHES)
         t_fact_prof = h.timing(C.T_FACTOR)
     h.set_option(C.OPT_PROFILE, 0)
-    peak_dmma = h.probe_peak(C.PEAK_FP64_DMMA)
+    peak_dmma_after = h.probe_peak(C.PEAK_FP64_DMMA)
+    peak_dmma = max(peak_dmma_before, peak_dmma_after)
     peak_dfma = h.probe_peak(C.PEAK_FP64_DFMA)
     hbm_copy = h.probe_peak(C.PEAK_HBM_COPY)
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
@@ -333,6 +338,7 @@ def main():
             "peak_source": "library DMMA.8x8x4 register-resident probe on this GPU (no FP64 entry in MEASURED_PEAKS.json)",
             "launches_profiled": int(g_n), "gemm_share_of_getrf": (g_ms / 2) / t_fact_prof if t_fact_prof else None,
             "dfma_probe_tflops": peak_dfma, "hbm_copy_probe_gbs": hbm_copy,
+            "peak_probe_before": peak_dmma_before, "peak_probe_after": peak_dmma_after,
             "getrf_frac_of_fp64_peak": (lu_flops(n) / ((tf / args.steps) * 1e-3) / 1e12) / peak_dmma if peak_dmma else None,
         }
     roofline["getrs"] = {"bound": "hbm",
