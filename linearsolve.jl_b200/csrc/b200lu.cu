@@ -418,8 +418,9 @@ static int launch_laswp(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda, in
 }
 
 // ------------------------------------------------------ cluster base panel --
-template <typename T, int W, int RPT>
+template <typename T, int W, int RPT, int NTV = PCL_NT>
 static int launch_panel_cluster_cfg(b200lu_handle* h, cudaStream_t st, PanelArgs<T> p) {
+    constexpr int PCL_NT = NTV;   // threads per CTA of this instantiation
     auto kern = panel_cluster_kernel<T, W, RPT, PCL_NT>;
     static bool attr_set = false;
     if (!attr_set) {
