@@ -66,7 +66,8 @@ enum {
 /* phases for b200lu_last_timing (milliseconds, CUDA-event measured) */
 enum {
     B200LU_T_H2D = 0,      /* host -> device copy of A (factor) or B (solve)   */
-    B200LU_T_FACTOR = 1,   /* getrf on the device                              */
+    B200LU_T_FACTOR = 1,   /* getrf on the device (with B200LU_OPT_STREAM_H2D the
+                              upload runs underneath it: H2D and FACTOR overlap) */
     B200LU_T_SOLVE = 2,    /* getrs (+ refinement) on the device               */
     B200LU_T_D2H = 3,      /* device -> host copy of ipiv/info or X            */
     B200LU_T_GEMM = 4,     /* of FACTOR: sum of trailing-update GEMM launches;
@@ -104,9 +105,17 @@ enum {
                                    16 CTAs, else L2 mailbox), 1 always L2 mailbox  */
     B200LU_OPT_SGEMM_MODE = 9,  /* FP32 trailing update: 0 auto (tcgen05 3xTF32 kernel for large
                                    updates, FFMA otherwise), 1 always FFMA          */
-    B200LU_OPT_TRSV_MODE = 10,  /* single-RHS getrs: 0 = 2-D work items on a persistent grid,
-                                   1 = one CTA per block row                        */
-    B200LU_OPT_COUNT = 11
+    B200LU_OPT_TRSV_MODE = 10,  /* single-RHS getrs: 0 auto (n >= 6144: mode 3, else mode 2;
+                                   transposed solves: mode 2), 1 = one CTA per block row,
+                                   2 = 2-D work items on a persistent grid, 3 = the dependency
+                                   chain in one thread-block cluster over DSMEM + worker CTAs
+                                   on the far blocks (n >= 1024)                          */
+    B200LU_OPT_STREAM_H2D = 11, /* b200lu_factor from a HOST matrix (F64/F32, n >= 2048): 1 (default)
+                                   = upload A in column chunks on a copy stream and start
+                                   factoring as soon as the first chunk has landed (late chunks
+                                   are caught up left-looking when they arrive); 0 = copy all of
+                                   A, then factor.  The factors are the same either way.  */
+    B200LU_OPT_COUNT = 12
 };
 
 /* library/ABI version: major*10000 + minor*100 + patch */

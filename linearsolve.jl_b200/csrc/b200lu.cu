@@ -25,6 +25,7 @@
 #include "panel_cluster.cuh"
 #include "trsm.cuh"
 #include "trsv.cuh"
+#include "trsv_cluster.cuh"
 #include "util_kernels.cuh"
 
 namespace b200lu {
@@ -38,10 +39,13 @@ using namespace b200lu;
 struct b200lu_handle {
     int dtype = 0;
     int dev = 0;
-    cudaStream_t s_main = nullptr, s_panel = nullptr;
+    cudaStream_t s_main = nullptr, s_panel = nullptr, s_copy = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_next = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_next = nullptr, ev_h2d = nullptr;
     std::vector<cudaEvent_t> ev_panel;
+    // streamed upload of A (B200LU_OPT_STREAM_H2D): column chunks in flight on s_copy
+    std::vector<cudaEvent_t> ev_chunk;   // chunk c has landed
+    std::vector<int> chunk_end;          // one past its last column (multiples of nb; last = n)
     char err[512] = {0};
     double timing[B200LU_T_COUNT] = {0};
     int64_t opt[B200LU_OPT_COUNT];
@@ -85,6 +89,15 @@ struct b200lu_handle {
     int* d_t2ticket = nullptr;
     int t2_nblk = 0, t2_nitems = 0, t2_kmax = 0, t2_grid = 0;
     unsigned t2_epoch = 0;
+    // single-RHS TRSV v3 (chain in one cluster over DSMEM, workers on the far blocks)
+    Trsv2Item* d_t3items = nullptr;
+    unsigned long long* d_t3x = nullptr;
+    unsigned long long* d_t3p = nullptr;
+    int* d_t3ticket = nullptr;
+    int t3_nblk = 0, t3_nitems = 0, t3_kmax = 0, t3_clusters = 0;
+    long long* d_t3dbg = nullptr;
+    int t3_ok = -1;            // -1 not probed, 0 cluster launch not possible (v2 is used), 1 ok
+    unsigned t3_epoch = 0;
     void* d_B = nullptr;       // staging for host solves / permuted rhs
     void* d_X = nullptr;
     int64_t cap_rhs = 0;
@@ -547,10 +560,15 @@ static int ensure_events(b200lu_handle* h, int count) {
     return 0;
 }
 
-// getrf of the n x n matrix in `A` (device, leading dim lda): columns [0, ncols)
-// are local.  Single-GPU: ncols == n.
+// getrf of the n x n matrix in `A` (device, leading dim lda).
+// nchunks > 0: A is still being uploaded in column chunks (h->chunk_end / h->ev_chunk, recorded
+// on the copy stream).  A chunk is admitted when it has landed (host-side event query, the host
+// is paced one panel behind the device while chunks are outstanding) or at the latest when the
+// next panel needs its columns; on admission the chunk is caught up left-looking: interchanges
+// of every finished panel, the U block rows by TRSM, one deep GEMM below them.  Each element
+// sees the same arithmetic in the same order as in the resident factorization.
 template <typename T>
-static int getrf_device(b200lu_handle* h, T* A, int64_t lda, int n) {
+static int getrf_device(b200lu_handle* h, T* A, int64_t lda, int n, int nchunks = 0) {
     const int nb = (int)h->opt[B200LU_OPT_NB];
     const bool la = h->opt[B200LU_OPT_LOOKAHEAD] != 0;
     const int nblk = cdiv(n, nb);
@@ -558,10 +576,47 @@ static int getrf_device(b200lu_handle* h, T* A, int64_t lda, int n) {
     if (rc) return rc;
     cudaStream_t sm = h->s_main;
     cudaStream_t sp = la ? h->s_panel : h->s_main;
+    int adm = nchunks > 0 ? 0 : n;   // columns [0, adm) are on the device
+    static const bool sdbg = getenv("B200LU_STREAM_DBG") != nullptr;
+    int next_chunk = 0;
+    // admit the next chunk; panels [0, kdone) are finished and applied to everything admitted so far
+    auto admit = [&](int kdone) -> int {
+        const int c0 = adm, c1 = h->chunk_end[next_chunk];
+        CU_TRY(h, cudaStreamWaitEvent(sm, h->ev_chunk[next_chunk], 0));
+        ++next_chunk;
+        adm = c1;
+        if (kdone == 0) return 0;
+        int r;
+        for (int j = 0; j < kdone; ++j) {
+            r = launch_laswp<T>(h, sm, A, lda, c0, c1, h->d_plans + j);
+            if (r) return r;
+        }
+        const int kd = kdone * nb;
+        for (int j = 0; j < kdone; ++j) {
+            const int r0 = j * nb, r1 = r0 + nb;
+            r = launch_trsm<T>(h, sm, A + (int64_t)r0 * lda + r0, lda, A + (int64_t)c0 * lda + r0, lda, nb, c1 - c0);
+            if (r) return r;
+            if (r1 < kd) {
+                r = launch_gemm(h, sm, kd - r1, c1 - c0, nb, A + (int64_t)r0 * lda + r1, lda,
+                                A + (int64_t)c0 * lda + r0, lda, A + (int64_t)c0 * lda + r1, lda);
+                if (r) return r;
+            }
+        }
+        if (kd < n) {
+            r = launch_gemm_prof<T>(h, sm, n - kd, c1 - c0, kd, A + kd, lda, A + (int64_t)c0 * lda, lda,
+                                    A + (int64_t)c0 * lda + kd, lda);
+            if (r) return r;
+        }
+        return 0;
+    };
 
     CU_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), sm));
     iota_kernel<<<cdiv(n, 256), 256, 0, sm>>>(h->d_perm, n);
     LAUNCH_CHECK(h);
+    while (next_chunk < nchunks && adm < std::min(nb, n)) {
+        rc = admit(0);
+        if (rc) return rc;
+    }
     if (la) {
         CU_TRY(h, cudaEventRecord(h->ev_fork, sm));
         CU_TRY(h, cudaStreamWaitEvent(sp, h->ev_fork, 0));
@@ -581,6 +636,14 @@ static int getrf_device(b200lu_handle* h, T* A, int64_t lda, int n) {
         const LaswpPlan* plan = h->d_plans + k;
         if (la) CU_TRY(h, cudaStreamWaitEvent(sm, h->ev_panel[k], 0));
         const int jb2 = std::min(nb, n - j1);
+        // a chunk the next panel needs is admitted (and waited for) now; chunks that have merely
+        // landed are admitted below, after the next panel has been handed to the panel stream,
+        // so that their catch-up never delays the panel chain
+        while (next_chunk < nchunks && j1 + jb2 > adm) {
+            if (sdbg) fprintf(stderr, "[stream] step %d admits chunk %d (needed)\n", k, next_chunk);
+            rc = admit(k);
+            if (rc) return rc;
+        }
         // interchanges: the next panel's columns first (they gate the look-ahead), the rest
         // of the matrix after the next panel has been handed to the panel stream
         if (j1 < n) {
@@ -611,18 +674,32 @@ static int getrf_device(b200lu_handle* h, T* A, int64_t lda, int n) {
         laswp_plan_kernel<<<1, 2 * LASWP_MAXSW, 0, sp>>>(h->d_ipiv, j1, jb2, h->d_plans + (k + 1));
         LAUNCH_CHECK(h);
         if (la) CU_TRY(h, cudaEventRecord(h->ev_panel[k + 1], sp));
+        if (next_chunk < nchunks) {
+            // the host stays one panel behind the device while chunks are outstanding, so that
+            // the arrival query is fresh
+            CU_TRY(h, cudaEventSynchronize(h->ev_panel[k]));
+            while (next_chunk < nchunks) {
+                if (cudaEventQuery(h->ev_chunk[next_chunk]) != cudaSuccess) {
+                    (void)cudaGetLastError();   // cudaErrorNotReady
+                    break;
+                }
+                if (sdbg) fprintf(stderr, "[stream] step %d admits chunk %d (landed)\n", k, next_chunk);
+                rc = admit(k);
+                if (rc) return rc;
+            }
+        }
         // the remaining interchanges of panel k, then the rest of the trailing matrix
         rc = launch_laswp<T>(h, sm, A, lda, 0, j0, plan);
         if (rc) return rc;
         rc = launch_laswp<int>(h, sm, h->d_perm, n, 0, 1, plan);
         if (rc) return rc;
         const int c2 = j1 + jb2;
-        rc = launch_laswp<T>(h, sm, A, lda, c2, n, plan);
-        if (rc) return rc;
-        if (c2 < n) {
-            rc = launch_trsm<T>(h, sm, L11, lda, A + (int64_t)c2 * lda + j0, lda, jb, n - c2);
+        if (c2 < adm) {
+            rc = launch_laswp<T>(h, sm, A, lda, c2, adm, plan);
             if (rc) return rc;
-            rc = launch_gemm_prof<T>(h, sm, n - j1, n - c2, jb, L21, lda, A + (int64_t)c2 * lda + j0, lda,
+            rc = launch_trsm<T>(h, sm, L11, lda, A + (int64_t)c2 * lda + j0, lda, jb, adm - c2);
+            if (rc) return rc;
+            rc = launch_gemm_prof<T>(h, sm, n - j1, adm - c2, jb, L21, lda, A + (int64_t)c2 * lda + j0, lda,
                                      A + (int64_t)c2 * lda + j1, lda);
             if (rc) return rc;
         }
@@ -696,8 +773,8 @@ static int ensure_capacity(b200lu_handle* h, int64_t n) {
     const int nblk = cdiv(n, TRSV_TB);
     CU_TRY(h, cudaMalloc(&h->d_dinvL, (size_t)nblk * TRSV_TB * TRSV_TB * es));
     CU_TRY(h, cudaMalloc(&h->d_dinvU, (size_t)nblk * TRSV_TB * TRSV_TB * es));
-    CU_TRY(h, cudaMalloc(&h->d_wL, (size_t)nblk * TRSV_TB * TRSV_TB * es));
-    CU_TRY(h, cudaMalloc(&h->d_wU, (size_t)nblk * TRSV_TB * TRSV_TB * es));
+    CU_TRY(h, cudaMalloc(&h->d_wL, (size_t)TRSV3_NEAR_MAX * nblk * TRSV_TB * TRSV_TB * es));   // coupling planes
+    CU_TRY(h, cudaMalloc(&h->d_wU, (size_t)TRSV3_NEAR_MAX * nblk * TRSV_TB * TRSV_TB * es));
     free_dev(h->d_tflags);
     free_dev(h->d_tticket);
     h->cap_tgroups = 0;
@@ -739,6 +816,101 @@ static int ensure_trsv_groups(b200lu_handle* h, int groups, int NR) {
     return 0;
 }
 
+// getrs, one right-hand side, version 3 (trsv_cluster.cuh): both sweeps.  Returns -1000 when the
+// cluster launch is not possible on this device (the caller falls back to version 2).
+template <typename T, int NEAR, int CS>
+static int trsv3_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T* B, T* X, int nblk) {
+    cudaStream_t st = h->s_main;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = trsv3_smem_bytes<T, NEAR>();
+    cfg.stream = st;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    auto kl = trsv3_kernel<T, false, NEAR, CS>;
+    auto ku = trsv3_kernel<T, true, NEAR, CS>;
+    if (h->t3_ok < 0 || h->t3_nblk != nblk) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CU_TRY(h, cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, trsv3_smem_bytes<T, NEAR>()));
+            CU_TRY(h, cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, trsv3_smem_bytes<T, NEAR>()));
+            if (CS > 8) {
+                CU_TRY(h, cudaFuncSetAttribute(kl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                CU_TRY(h, cudaFuncSetAttribute(ku, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            }
+            attr_set = true;
+        }
+        int ncl_l = 0, ncl_u = 0;
+        cfg.gridDim = dim3(CS * 2);
+        cudaError_t e1 = cudaOccupancyMaxActiveClusters(&ncl_l, kl, &cfg);
+        cudaError_t e2 = cudaOccupancyMaxActiveClusters(&ncl_u, ku, &cfg);
+        const int ncl = std::min(ncl_l, ncl_u);
+        if (getenv("B200LU_TRSV_DBG")) fprintf(stderr, "[trsv3] NEAR=%d CS=%d: %d co-resident clusters\n", NEAR, CS, ncl);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || ncl < 2) {
+            (void)cudaGetLastError();
+            h->t3_ok = 0;
+            return -1000;
+        }
+        CU_TRY(h, cudaStreamSynchronize(st));
+        free_dev(h->d_t3items); free_dev(h->d_t3x); free_dev(h->d_t3p);
+        std::vector<Trsv2Item> items;
+        int kmax = 1;
+        for (int t = NEAR + 1; t < nblk; ++t) {
+            const int nch = cdiv(t - NEAR, TRSV3_CH);
+            kmax = std::max(kmax, nch);
+            for (int k = 0; k < nch; ++k) items.push_back(Trsv2Item{t, k});
+        }
+        CU_TRY(h, cudaMalloc((void**)&h->d_t3items, items.size() * sizeof(Trsv2Item)));
+        CU_TRY(h, cudaMemcpy(h->d_t3items, items.data(), items.size() * sizeof(Trsv2Item), cudaMemcpyHostToDevice));
+        const size_t xb = (size_t)nblk * TRSV_TB * 2 * sizeof(unsigned long long);
+        const size_t pb = (size_t)nblk * kmax * TRSV_TB * 2 * sizeof(unsigned long long);
+        CU_TRY(h, cudaMalloc((void**)&h->d_t3x, xb));
+        CU_TRY(h, cudaMemset(h->d_t3x, 0, xb));
+        CU_TRY(h, cudaMalloc((void**)&h->d_t3p, pb));
+        CU_TRY(h, cudaMemset(h->d_t3p, 0, pb));
+        if (!h->d_t3ticket) {
+            CU_TRY(h, cudaMalloc((void**)&h->d_t3ticket, 64));
+            CU_TRY(h, cudaMemset(h->d_t3ticket, 0, 64));
+        }
+        if (getenv("B200LU_TRSV_DBG") && !h->d_t3dbg) {
+            CU_TRY(h, cudaMalloc((void**)&h->d_t3dbg, 16 * 8 * sizeof(long long)));
+            CU_TRY(h, cudaMemset(h->d_t3dbg, 0, 16 * 8 * sizeof(long long)));
+        }
+        h->t3_clusters = ncl;   // every cluster resident: the chain and the tickets cannot deadlock
+        h->t3_nblk = nblk;
+        h->t3_nitems = (int)items.size();
+        h->t3_kmax = kmax;
+        h->t3_epoch = 0;
+        h->t3_ok = 1;
+    }
+    // one cluster for the chain, workers up to one item each
+    const int clusters = std::max(2, std::min(h->t3_clusters, 1 + cdiv(h->t3_nitems, CS)));
+    cfg.gridDim = dim3(clusters * CS);
+    for (int upper = 0; upper < 2; ++upper) {
+        if (h->t3_epoch > (1u << 30)) {
+            CU_TRY(h, cudaMemsetAsync(h->d_t3x, 0, (size_t)nblk * TRSV_TB * 2 * sizeof(unsigned long long), st));
+            CU_TRY(h, cudaMemsetAsync(h->d_t3p, 0, (size_t)nblk * h->t3_kmax * TRSV_TB * 2 * sizeof(unsigned long long), st));
+            h->t3_epoch = 0;
+        }
+        const unsigned epoch = ++h->t3_epoch;
+        Trsv3Sync sy{h->d_t3x, h->d_t3p, h->d_t3ticket, h->d_deverr, h->d_t3items, h->t3_nitems, h->t3_kmax, h->d_t3dbg,
+                     getenv("B200LU_TRSV_DBGFLAGS") ? atoi(getenv("B200LU_TRSV_DBGFLAGS")) : 0};
+        const T* nullT = nullptr;
+        const int* nullI = nullptr;
+        if (upper)
+            CU_TRY(h, cudaLaunchKernelEx(&cfg, ku, A, (long long)lda, n, (const T*)h->d_dinvU, (const T*)h->d_wU,
+                                         nullT, nullI, X, sy, epoch, nblk));
+        else
+            CU_TRY(h, cudaLaunchKernelEx(&cfg, kl, A, (long long)lda, n, (const T*)h->d_dinvL, (const T*)h->d_wL,
+                                         B, (const int*)h->d_perm, X, sy, epoch, nblk));
+        B200LU_COUNT_LAUNCH();
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------- getrs --
 // X = U \ (L \ (P B)).  B must not alias X here (the lower sweep gathers B rows
 // through the permutation); getrs_device stages an aliased right-hand side.
@@ -759,9 +931,9 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T
         LAUNCH_CHECK(h);
         trtri_diag_kernel<T><<<nblk, TRSV_TB, tsm, st>>>(A, lda, n, (T*)h->d_dinvU, 1);
         LAUNCH_CHECK(h);
-        trsv_coupling_kernel<T><<<nblk, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvL, (T*)h->d_wL, 0, nblk, 0);
+        trsv_coupling_kernel<T><<<dim3(nblk, TRSV3_NEAR_MAX), 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvL, (T*)h->d_wL, 0, nblk, 0);
         LAUNCH_CHECK(h);
-        trsv_coupling_kernel<T><<<nblk, 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvU, (T*)h->d_wU, 1, nblk, 0);
+        trsv_coupling_kernel<T><<<dim3(nblk, TRSV3_NEAR_MAX), 256, 0, st>>>(A, lda, n, (const T*)h->d_dinvU, (T*)h->d_wU, 1, nblk, 0);
         LAUNCH_CHECK(h);
         h->solve_ready = true;
     }
@@ -777,7 +949,19 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T
         LAUNCH_CHECK(h);
         h->solve_ready_t = true;
     }
-    if (trans || (nrhs == 1 && h->opt[B200LU_OPT_TRSV_MODE] == 0 && nblk >= 4)) {
+    if (!trans && nrhs == 1 && h->t3_ok != 0 &&
+        (h->opt[B200LU_OPT_TRSV_MODE] == 3 || (h->opt[B200LU_OPT_TRSV_MODE] == 0 && nblk >= 96)) && nblk >= 16) {
+        // ---- version 3: the dependency chain in one cluster over DSMEM, workers on the far blocks ----
+        static const int near_cfg = getenv("B200LU_TRSV3_NEAR") ? atoi(getenv("B200LU_TRSV3_NEAR")) : 4;
+        static const int cs_cfg = getenv("B200LU_TRSV3_CS") ? atoi(getenv("B200LU_TRSV3_CS")) : 8;
+        int rc3;
+        if (near_cfg == 6 && cs_cfg == 16) rc3 = trsv3_sweeps<T, 6, 16>(h, A, lda, n, B, X, nblk);
+        else if (near_cfg == 6) rc3 = trsv3_sweeps<T, 6, 8>(h, A, lda, n, B, X, nblk);
+        else if (cs_cfg == 16) rc3 = trsv3_sweeps<T, 4, 16>(h, A, lda, n, B, X, nblk);
+        else rc3 = trsv3_sweeps<T, 4, 8>(h, A, lda, n, B, X, nblk);
+        if (rc3 != -1000) return rc3;   // -1000: cluster launch not possible here, version 2 takes over
+    }
+    if (trans || (nrhs == 1 && h->opt[B200LU_OPT_TRSV_MODE] != 1 && nblk >= 4)) {
         // ---- version 2: 2-D work items on a persistent, fully resident grid ----
         if (h->t2_nblk != nblk) {
             CU_TRY(h, cudaStreamSynchronize(st));
@@ -1124,10 +1308,13 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     h->opt[B200LU_OPT_PANEL_MODE] = 0;
     h->opt[B200LU_OPT_SGEMM_MODE] = 0;
     h->opt[B200LU_OPT_TRSV_MODE] = 0;
+    h->opt[B200LU_OPT_STREAM_H2D] = 1;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) == cudaSuccess;
     ok = ok && cudaStreamCreateWithPriority(&h->s_panel, cudaStreamNonBlocking, hi) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&h->ev_h2d) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev_a) == cudaSuccess && cudaEventCreate(&h->ev_b) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev_c) == cudaSuccess && cudaEventCreate(&h->ev_d) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
@@ -1157,6 +1344,7 @@ void b200lu_destroy(b200lu_handle* h) {
     cudaSetDevice(h->dev);
     if (h->s_main) cudaStreamSynchronize(h->s_main);
     if (h->s_panel) cudaStreamSynchronize(h->s_panel);
+    if (h->s_copy) cudaStreamSynchronize(h->s_copy);
     if (h->d_pdbg) {
         const int cnt = std::min(h->pdbg_n, 4096);
         std::vector<long long> t((size_t)cnt * 16);
@@ -1169,9 +1357,20 @@ void b200lu_destroy(b200lu_handle* h) {
         }
         cudaFree(h->d_pdbg);
     }
+    if (h->d_t3dbg) {
+        long long t[16 * 8];
+        cudaMemcpy(t, h->d_t3dbg, sizeof(t), cudaMemcpyDeviceToHost);
+        for (int r = 0; r < 16; ++r)
+            if (t[r * 8 + 4])
+                fprintf(stderr, "[trsv3] chain CTA %d: %lld rows; cycles per row: far sums+operands %lld | dinv + older x %lld | wait x(t-1) %lld | step %lld | issue next %lld ; loop %lld cycles in %lld ns = %.0f MHz\n",
+                        r, t[r * 8 + 4], t[r * 8] / t[r * 8 + 4], t[r * 8 + 1] / t[r * 8 + 4], t[r * 8 + 2] / t[r * 8 + 4], t[r * 8 + 3] / t[r * 8 + 4],
+                        t[r * 8 + 5] / t[r * 8 + 4], t[r * 8 + 6], t[r * 8 + 7], 1e3 * (double)t[r * 8 + 6] / (double)std::max(1LL, t[r * 8 + 7]));
+        cudaFree(h->d_t3dbg);
+    }
     free_dev(h->dA); free_dev(h->dA64); free_dev(h->d_ipiv); free_dev(h->d_perm);
     free_dev(h->d_info); free_dev(h->d_deverr); free_dev(h->d_plans); free_dev(h->d_panelsync); free_dev(h->d_split);
     free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_wL); free_dev(h->d_wU); free_dev(h->d_wLt); free_dev(h->d_wUt); free_dev(h->d_tflags); free_dev(h->d_tticket); free_dev(h->d_t2items); free_dev(h->d_t2x); free_dev(h->d_t2p); free_dev(h->d_t2ticket);
+    free_dev(h->d_t3items); free_dev(h->d_t3x); free_dev(h->d_t3p); free_dev(h->d_t3ticket);
     free_dev(h->d_B); free_dev(h->d_X); free_dev(h->d_r); free_dev(h->d_r32); free_dev(h->d_scal); free_dev(h->d_cscal);
     if (h->h_cscal) cudaFreeHost(h->h_cscal);
     free_dev(h->dB_LU); free_dev(h->dB_ipiv); free_dev(h->dB_info); free_dev(h->dB_perm); free_dev(h->dB_in);
@@ -1182,12 +1381,14 @@ void b200lu_destroy(b200lu_handle* h) {
     if (h->hB_ipiv) cudaFreeHost(h->hB_ipiv);
     if (h->hB_info) cudaFreeHost(h->hB_info);
     for (cudaEvent_t e : h->ev_panel) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
-    cudaEvent_t evs[] = {h->ev_a, h->ev_b, h->ev_c, h->ev_d, h->ev_fork, h->ev_next};
+    cudaEvent_t evs[] = {h->ev_a, h->ev_b, h->ev_c, h->ev_d, h->ev_fork, h->ev_next, h->ev_h2d};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     if (h->s_main) cudaStreamDestroy(h->s_main);
     if (h->s_panel) cudaStreamDestroy(h->s_panel);
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
     delete h;
 }
 
@@ -1284,7 +1485,8 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_GEMM_CFG && (value < 0 || value > 3)) return -3;
     if (option == B200LU_OPT_PANEL_MODE && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_SGEMM_MODE && (value < 0 || value > 2)) return -3;
-    if (option == B200LU_OPT_TRSV_MODE && (value < 0 || value > 1)) return -3;
+    if (option == B200LU_OPT_TRSV_MODE && (value < 0 || value > 3)) return -3;
+    if (option == B200LU_OPT_STREAM_H2D && (value < 0 || value > 1)) return -3;
     h->opt[option] = value;
     return 0;
 }
@@ -1294,7 +1496,7 @@ int64_t b200lu_get_option(const b200lu_handle* h, int option) {
 }
 
 // factor whatever already sits in h->dA (and dA64 for MIXED)
-static int factor_resident(b200lu_handle* h, int64_t n, int64_t* info) {
+static int factor_resident(b200lu_handle* h, int64_t n, int64_t* info, int nchunks = 0) {
     int rc;
     h->factored = false;
     h->solve_ready = false;
@@ -1303,7 +1505,7 @@ static int factor_resident(b200lu_handle* h, int64_t n, int64_t* info) {
     h->prof_flops = 0.0;
     CU_TRY(h, cudaEventRecord(h->ev_b, h->s_main));
     if (h->dtype == B200LU_F64) {
-        rc = getrf_device<double>(h, (double*)h->dA, h->ldd, (int)n);
+        rc = getrf_device<double>(h, (double*)h->dA, h->ldd, (int)n, nchunks);
     } else {
         if (h->dtype == B200LU_MIXED) {
             CU_TRY(h, cudaMemsetAsync(h->d_scal, 0, 4 * sizeof(double), h->s_main));
@@ -1314,7 +1516,7 @@ static int factor_resident(b200lu_handle* h, int64_t n, int64_t* info) {
                 h->dA64, h->ldd, (float*)h->dA, h->ldd, (int)n, (int)n);
             LAUNCH_CHECK(h);
         }
-        rc = getrf_device<float>(h, (float*)h->dA, h->ldd, (int)n);
+        rc = getrf_device<float>(h, (float*)h->dA, h->ldd, (int)n, nchunks);
     }
     if (rc) return rc;
     CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
@@ -1363,12 +1565,45 @@ int b200lu_factor(b200lu_handle* h, int64_t n, const void* A_host, int64_t lda, 
     const size_t is = iface_size(h);
     void* dst = (h->dtype == B200LU_MIXED) ? (void*)h->dA64 : h->dA;
     CU_TRY(h, cudaEventRecord(h->ev_a, h->s_main));
-    CU_TRY(h, cudaMemcpy2DAsync(dst, (size_t)h->ldd * is, A_host, (size_t)lda * is, (size_t)n * is,
-                                (size_t)n, cudaMemcpyHostToDevice, h->s_main));
-    rc = factor_resident(h, n, info);
-    if (rc) return rc;
+    // streamed upload: column chunks on the copy stream, the factorization starts under them
+    const int nb = (int)h->opt[B200LU_OPT_NB];
+    int nchunks = 0;
+    if (h->opt[B200LU_OPT_STREAM_H2D] && h->opt[B200LU_OPT_LOOKAHEAD] && h->dtype != B200LU_MIXED && n >= 2048) {
+        static const int want = getenv("B200LU_H2D_CHUNKS") ? std::max(2, atoi(getenv("B200LU_H2D_CHUNKS"))) : 8;
+        const int cw = cdiv(cdiv((int)n, want), nb) * nb;
+        const int first = std::min(cw, 2 * nb);   // a short first chunk: the first panel starts early
+        nchunks = 1 + cdiv((int)n - first, cw);
+        if (nchunks < 2) nchunks = 0;
+        else {
+            h->chunk_end.resize(nchunks);
+            while ((int)h->ev_chunk.size() < nchunks) {
+                cudaEvent_t e;
+                CU_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->ev_chunk.push_back(e);
+            }
+            CU_TRY(h, cudaStreamWaitEvent(h->s_copy, h->ev_a, 0));
+            for (int c = 0; c < nchunks; ++c) {
+                const int64_t c0 = c == 0 ? 0 : first + (int64_t)(c - 1) * cw;
+                const int64_t c1 = c == 0 ? first : std::min<int64_t>(n, c0 + cw);
+                h->chunk_end[c] = (int)c1;
+                CU_TRY(h, cudaMemcpy2DAsync((char*)dst + (size_t)c0 * h->ldd * is, (size_t)h->ldd * is,
+                                            (const char*)A_host + (size_t)c0 * lda * is, (size_t)lda * is,
+                                            (size_t)n * is, (size_t)(c1 - c0), cudaMemcpyHostToDevice, h->s_copy));
+                CU_TRY(h, cudaEventRecord(h->ev_chunk[c], h->s_copy));
+            }
+            CU_TRY(h, cudaEventRecord(h->ev_h2d, h->s_copy));
+        }
+    }
+    if (nchunks == 0)
+        CU_TRY(h, cudaMemcpy2DAsync(dst, (size_t)h->ldd * is, A_host, (size_t)lda * is, (size_t)n * is,
+                                    (size_t)n, cudaMemcpyHostToDevice, h->s_main));
+    rc = factor_resident(h, n, info, nchunks);
+    if (rc) {
+        if (nchunks) cudaStreamSynchronize(h->s_copy);   // the caller's buffer must not be read after we return
+        return rc;
+    }
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+    cudaEventElapsedTime(&ms, h->ev_a, nchunks ? h->ev_h2d : h->ev_b);
     h->timing[B200LU_T_H2D] = ms;
     if (ipiv_out) {
         rc = b200lu_get_ipiv(h, ipiv_out);

@@ -57,10 +57,12 @@ __global__ void __launch_bounds__(TRSV_TB) trtri_diag_kernel(const T* __restrict
     for (int c = 0; c < TRSV_TB; ++c) out[c * TRSV_TB + j] = Ys[j][c];
 }
 
-// Coupling blocks W_r = dinv_r * A[r, r-1] (lower) or dinv_r * A[r, r+1] (upper),
-// 64x64 each, column-major like dinv.  With them the only work a block row has to
-// do AFTER its last dependency arrives is one 64x64 mat-vec:
+// Coupling blocks W^m_r = dinv_r * A[r, r-m] (lower) or dinv_r * A[r, r+m] (upper), m = 1 +
+// blockIdx.y, 64x64 each, column-major like dinv; plane m-1 of `wmat` holds the nblk blocks of
+// offset m.  With them the only work a block row has to do AFTER its last dependency arrives is
+// one 64x64 mat-vec:
 //     x_r = dinv_r (b_r - sum_{c not adjacent} A_rc x_c)  -  W_r x_adjacent .
+// (trsv_block_kernel / trsv2_kernel use plane 0; the cluster chain of trsv_cluster.cuh planes 0..3)
 template <typename T>
 __global__ void __launch_bounds__(256) trsv_coupling_kernel(const T* __restrict__ A, long long lda,
                                                             int n, const T* __restrict__ dinv,
@@ -69,8 +71,9 @@ __global__ void __launch_bounds__(256) trsv_coupling_kernel(const T* __restrict_
     constexpr int TB = TRSV_TB;
     __shared__ T s_a[TB][TB + 1];   // block [k][col]
     const int r = blockIdx.x;
-    const int c = upper ? r + 1 : r - 1;
-    T* out = wmat + (long long)r * TB * TB;
+    const int off = 1 + (int)blockIdx.y;
+    const int c = upper ? r + off : r - off;
+    T* out = wmat + ((long long)blockIdx.y * nblk + r) * TB * TB;
     if (c < 0 || c >= nblk) {
         for (int i = threadIdx.x; i < TB * TB; i += 256) out[i] = T(0);
         return;

@@ -265,3 +265,59 @@ def test_l2_mailbox_fallback_panels(gpu_required, ls):
     r = A0.T @ x[0] - b[0]
     berr = (r.norm() / (A0.norm() * x[0].norm())).item()
     assert berr <= 10 * n * np.finfo(np.float64).eps, berr
+
+
+@pytest.mark.parametrize("dtype,n,pad", [(np.float64, 2048, 0), (np.float64, 3000, 7), (np.float64, 4096, 0),
+                                         (np.float32, 3000, 0)])
+def test_streamed_upload_matches_resident(gpu_required, ls, oracle, dtype, n, pad):
+    """b200lu_factor from a host matrix uploads A in column chunks and factors underneath the copy
+    (B200LU_OPT_STREAM_H2D, default on for n >= 2048); late chunks are caught up left-looking.  Every
+    element sees the same arithmetic in the same order as in the copy-then-factor path: FP64 factors
+    and pivots are bitwise equal (FP32 may take the FFMA instead of the tcgen05 kernel for a small
+    catch-up block, so it is checked through the residual instead)."""
+    rng = np.random.default_rng(4100 + n)
+    P = np.asfortranarray(rng.standard_normal((n + pad, n)).astype(dtype))
+    A = P[:n, :]
+    h0 = _handle(ls, dtype, OPT_STREAM_H2D=0)
+    h1 = _handle(ls, dtype, OPT_STREAM_H2D=1)
+    ipiv0, info0 = h0.factor(A)
+    ipiv1, info1 = h1.factor(A)
+    assert info0 == 0 and info1 == 0
+    LU1 = h1.get_factors()
+    if dtype == np.float64:
+        assert np.array_equal(np.asarray(ipiv0), np.asarray(ipiv1))
+        assert np.array_equal(h0.get_factors(), LU1)
+    assert oracle.scaled_residual(A.copy(order="F"), LU1, ipiv1) < 20
+    # twice on the same handle: chunk events and plans are reused
+    ipiv2, _ = h1.factor(A)
+    assert np.array_equal(np.asarray(ipiv1), np.asarray(ipiv2))
+    assert np.array_equal(LU1, h1.get_factors())
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_single_rhs_getrs_all_paths(gpu_required, ls, oracle, dtype):
+    """The three single-right-hand-side getrs kernels on the same factors: the cluster chain over
+    DSMEM (mode 3; the default from n = 6144), the 2-D work items, one CTA per block row.  Each meets the
+    backward-error bar and agrees with LAPACK getrs; ragged last blocks (n not a multiple of 64),
+    general (not diagonally dominant) matrices, repeated solves (ring / epoch reuse)."""
+    rng = np.random.default_rng(606)
+    eps = np.finfo(dtype).eps
+    C = ls._capi
+    for n in (1024, 1500, 2048, 4097, 6200):
+        A = np.asfortranarray(rng.standard_normal((n, n)).astype(dtype))
+        lu_ref, ipiv_ref, _ = oracle.lapack_getrf(A)
+        xs = []
+        for mode in (3, 2, 1, 0):
+            h = _handle(ls, dtype, OPT_TRSV_MODE=mode)
+            _, info = h.factor(A)
+            assert info == 0
+            for rep in range(3):
+                b = rng.standard_normal(n).astype(dtype)
+                x = h.solve(b)
+                assert oracle.backward_error(A, x, b) <= 10 * n * eps, (n, mode, rep)
+            x_ref = oracle.lapack_getrs(lu_ref, ipiv_ref, b)
+            scale = np.linalg.norm(x_ref, np.inf)
+            assert np.linalg.norm(x - x_ref, np.inf) <= 1e4 * n * eps * scale, (n, mode)
+            xs.append(x)
+            # deterministic: the same solve again gives the same bits
+            assert np.array_equal(x, h.solve(b)), (n, mode)
