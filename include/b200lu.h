@@ -115,7 +115,11 @@ enum {
                                    factoring as soon as the first chunk has landed (late chunks
                                    are caught up left-looking when they arrive); 0 = copy all of
                                    A, then factor.  The factors are the same either way.  */
-    B200LU_OPT_COUNT = 12
+    B200LU_OPT_MAPPED_RHS = 12, /* b200lu_solve with ONE right-hand side (F64/F32, trans = 'N', n >= 256):
+                                   1 (default) = b and x travel through a page-locked, device-mapped
+                                   staging buffer that the getrs kernels read and write directly over
+                                   PCIe (no copy-engine launches); 0 = H2D / D2H copies             */
+    B200LU_OPT_COUNT = 13
 };
 
 /* library/ABI version: major*10000 + minor*100 + patch */

@@ -110,6 +110,10 @@ struct b200lu_handle {
     int cap_cscal = 0;
     double normA_F = 0.0;
     int last_refine_iters = 0;
+    // page-locked, device-mapped staging of one right-hand side and its solution (2 * cap_hrhs * 8 bytes)
+    char* h_rhs = nullptr;
+    char* d_rhs_map = nullptr;
+    int64_t cap_hrhs = 0;
     // pinned host staging
     long long* h_ipiv = nullptr;
     int64_t cap_hipiv = 0;
@@ -896,8 +900,7 @@ static int trsv3_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const 
             h->t3_epoch = 0;
         }
         const unsigned epoch = ++h->t3_epoch;
-        Trsv3Sync sy{h->d_t3x, h->d_t3p, h->d_t3ticket, h->d_deverr, h->d_t3items, h->t3_nitems, h->t3_kmax, h->d_t3dbg,
-                     getenv("B200LU_TRSV_DBGFLAGS") ? atoi(getenv("B200LU_TRSV_DBGFLAGS")) : 0};
+        Trsv3Sync sy{h->d_t3x, h->d_t3p, h->d_t3ticket, h->d_deverr, h->d_t3items, h->t3_nitems, h->t3_kmax, h->d_t3dbg};
         const T* nullT = nullptr;
         const int* nullI = nullptr;
         if (upper)
@@ -952,13 +955,8 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T
     if (!trans && nrhs == 1 && h->t3_ok != 0 &&
         (h->opt[B200LU_OPT_TRSV_MODE] == 3 || (h->opt[B200LU_OPT_TRSV_MODE] == 0 && nblk >= 96)) && nblk >= 16) {
         // ---- version 3: the dependency chain in one cluster over DSMEM, workers on the far blocks ----
-        static const int near_cfg = getenv("B200LU_TRSV3_NEAR") ? atoi(getenv("B200LU_TRSV3_NEAR")) : 4;
-        static const int cs_cfg = getenv("B200LU_TRSV3_CS") ? atoi(getenv("B200LU_TRSV3_CS")) : 8;
-        int rc3;
-        if (near_cfg == 6 && cs_cfg == 16) rc3 = trsv3_sweeps<T, 6, 16>(h, A, lda, n, B, X, nblk);
-        else if (near_cfg == 6) rc3 = trsv3_sweeps<T, 6, 8>(h, A, lda, n, B, X, nblk);
-        else if (cs_cfg == 16) rc3 = trsv3_sweeps<T, 4, 16>(h, A, lda, n, B, X, nblk);
-        else rc3 = trsv3_sweeps<T, 4, 8>(h, A, lda, n, B, X, nblk);
+        // measured and dropped: NEAR = 6 and 16-CTA clusters (see trsv_cluster.cuh)
+        const int rc3 = trsv3_sweeps<T, 4, 8>(h, A, lda, n, B, X, nblk);
         if (rc3 != -1000) return rc3;   // -1000: cluster launch not possible here, version 2 takes over
     }
     if (trans || (nrhs == 1 && h->opt[B200LU_OPT_TRSV_MODE] != 1 && nblk >= 4)) {
@@ -1309,6 +1307,7 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     h->opt[B200LU_OPT_SGEMM_MODE] = 0;
     h->opt[B200LU_OPT_TRSV_MODE] = 0;
     h->opt[B200LU_OPT_STREAM_H2D] = 1;
+    h->opt[B200LU_OPT_MAPPED_RHS] = 1;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) == cudaSuccess;
@@ -1376,6 +1375,7 @@ void b200lu_destroy(b200lu_handle* h) {
     free_dev(h->dB_LU); free_dev(h->dB_ipiv); free_dev(h->dB_info); free_dev(h->dB_perm); free_dev(h->dB_in);
     free_dev(h->dB_rhs); free_dev(h->dB_x);
     if (h->h_ipiv) cudaFreeHost(h->h_ipiv);
+    if (h->h_rhs) cudaFreeHost(h->h_rhs);
     if (h->h_small) cudaFreeHost(h->h_small);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     if (h->hB_ipiv) cudaFreeHost(h->hB_ipiv);
@@ -1487,6 +1487,7 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_SGEMM_MODE && (value < 0 || value > 2)) return -3;
     if (option == B200LU_OPT_TRSV_MODE && (value < 0 || value > 3)) return -3;
     if (option == B200LU_OPT_STREAM_H2D && (value < 0 || value > 1)) return -3;
+    if (option == B200LU_OPT_MAPPED_RHS && (value < 0 || value > 1)) return -3;
     h->opt[option] = value;
     return 0;
 }
@@ -1694,6 +1695,38 @@ int b200lu_solve(b200lu_handle* h, char trans, int64_t nrhs, const void* B_host,
     if (rc) return rc;
     if (h->n == 0 || nrhs == 0) return 0;
     CU_TRY(h, cudaSetDevice(h->dev));
+    const bool tr = !(trans == 'N' || trans == 'n');
+    if (nrhs == 1 && !tr && h->dtype != B200LU_MIXED && h->n >= 256 && h->opt[B200LU_OPT_MAPPED_RHS]) {
+        // one right-hand side: the getrs kernels read b and write x in mapped host memory themselves
+        const int64_t n = h->n;
+        const size_t is = iface_size(h);
+        if (n > h->cap_hrhs) {
+            CU_TRY(h, cudaStreamSynchronize(h->s_main));
+            if (h->h_rhs) cudaFreeHost(h->h_rhs);
+            h->h_rhs = nullptr;
+            h->cap_hrhs = 0;
+            CU_TRY(h, cudaHostAlloc((void**)&h->h_rhs, (size_t)2 * h->cap_n * 8, cudaHostAllocMapped));
+            CU_TRY(h, cudaHostGetDevicePointer((void**)&h->d_rhs_map, h->h_rhs, 0));
+            h->cap_hrhs = h->cap_n;
+        }
+        memcpy(h->h_rhs, B_host, (size_t)n * is);
+        char* dB = h->d_rhs_map;
+        char* dX = h->d_rhs_map + (size_t)h->cap_hrhs * 8;
+        CU_TRY(h, cudaEventRecord(h->ev_b, h->s_main));
+        if (h->dtype == B200LU_F64) rc = getrs_device<double>(h, (const double*)dB, n, (double*)dX, n, 1, false);
+        else rc = getrs_device<float>(h, (const float*)dB, n, (float*)dX, n, 1, false);
+        if (rc) return rc;
+        CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
+        rc = finish_solve(h);
+        if (rc) return rc;
+        memcpy(X_host, h->h_rhs + (size_t)h->cap_hrhs * 8, (size_t)n * is);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_b, h->ev_c);
+        h->timing[B200LU_T_SOLVE] = ms;
+        h->timing[B200LU_T_H2D] = 0.0;   // no copies: the kernels touch the mapped buffer
+        h->timing[B200LU_T_D2H] = 0.0;
+        return 0;
+    }
     // d_B/d_X are also scratch of the in-place / refinement paths: keep the host
     // staging in the upper half of a 2*nrhs allocation
     rc = ensure_rhs(h, 2 * nrhs + 2);

@@ -40,7 +40,7 @@
 
 namespace b200lu {
 
-constexpr int TRSV3_NEAR_MAX = 6; // coupling planes kept per factorization (block columns t-1 .. t-6)
+constexpr int TRSV3_NEAR_MAX = 4; // coupling planes kept per factorization (block columns t-1 .. t-4)
 constexpr int TRSV3_RING = 16;   // solved segments kept in every chain CTA's shared memory
 constexpr int TRSV3_CH = 8;      // far blocks per partial item
 
@@ -52,7 +52,6 @@ struct Trsv3Sync {
     const Trsv2Item* items;      // partial items only, t-major
     int nitems, kmax;
     long long* dbg;              // B200LU_TRSV_DBG: per chain CTA, cycles spent in each wait
-    int dbgflags;                // experiments only: 1 = the chain does not wait for the far sums (WRONG results)
 };
 
 template <typename T, int NEAR>
@@ -261,7 +260,7 @@ __global__ void __launch_bounds__(256, 1) trsv3_kernel(const T* __restrict__ A, 
                 // both of their words) in flight per thread; fixed assignment and order: deterministic
                 T sum = T(0);
                 const unsigned long long* src = sy.pll + ((size_t)(t * sy.kmax) * TB + row) * WN;
-                for (int k0 = q; k0 < ((sy.dbgflags & 1) ? 0 : nch); k0 += 16) {
+                for (int k0 = q; k0 < nch; k0 += 16) {
                     unsigned long long v[4][WN];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {

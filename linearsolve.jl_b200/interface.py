@@ -347,8 +347,15 @@ def solve_(cache: LinearCache, alg=None, adjoint: bool = False) -> LinearSolutio
             raise NotImplementedError("adjoint solves of BlockDiagonal problems")
         x = _solve_blockdiag(cache)
     else:
-        x = cv.handle.solve(np.asarray(cache.b), trans="T" if adjoint else "N")
-    cache.u[...] = x
+        u, b = cache.u, np.asarray(cache.b)
+        # vector right-hand side into a plain vector u: getrs writes straight into cache.u
+        direct = (isinstance(u, np.ndarray) and u.ndim == 1 and b.ndim == 1 and u.shape == b.shape and
+                  u.flags.c_contiguous and u.dtype == cv.handle.np_dtype and not np.shares_memory(u, b))
+        x = cv.handle.solve(b, out=u if direct else None, trans="T" if adjoint else "N")
+        if direct:
+            x = None   # getrs wrote straight into cache.u
+    if x is not None:
+        cache.u[...] = x
     if adjoint:
         return LinearSolution(cache.u, ReturnCode.Success, alg)
     if check_safety and not _check_residual_safety(cache, A, cache.u):

@@ -321,3 +321,6 @@ def test_single_rhs_getrs_all_paths(gpu_required, ls, oracle, dtype):
             xs.append(x)
             # deterministic: the same solve again gives the same bits
             assert np.array_equal(x, h.solve(b)), (n, mode)
+            # ... and so does the copy-engine path (default: b and x in device-mapped host memory)
+            h.set_option(C.OPT_MAPPED_RHS, 0)
+            assert np.array_equal(x, h.solve(b)), (n, mode)
