@@ -31,7 +31,8 @@
 // getrs: 232 us vs 240 us (n = 8192), 620 vs 685 us (n = 16384); below n = 6144 version 2 is as
 // fast or faster and stays the default.  A chain CTA also has to pull (NEAR + 1) x 32 KiB of
 // operands per row (~3200 cycles to issue), which is why NEAR = 6 and 16-CTA clusters (7 instead
-// of 15 co-resident clusters: fewer workers) measured no better.
+// of 15 co-resident clusters: fewer workers) measured no better; taking the near terms before the
+// far sums measured worse (232 -> 260 us), as did a single polling lane per warp (232 -> 268 us).
 #pragma once
 #include "common.cuh"
 #include "panel.cuh"           // LL packets
