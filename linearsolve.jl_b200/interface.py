@@ -348,9 +348,10 @@ def solve_(cache: LinearCache, alg=None, adjoint: bool = False) -> LinearSolutio
         x = _solve_blockdiag(cache)
     else:
         u, b = cache.u, np.asarray(cache.b)
-        # vector right-hand side into a plain vector u: getrs writes straight into cache.u
-        direct = (isinstance(u, np.ndarray) and u.ndim == 1 and b.ndim == 1 and u.shape == b.shape and
-                  u.flags.c_contiguous and u.dtype == cv.handle.np_dtype and not np.shares_memory(u, b))
+        # a plain vector u, or a column-major matrix u: getrs writes straight into cache.u
+        direct = (isinstance(u, np.ndarray) and u.shape == b.shape and u.dtype == cv.handle.np_dtype and
+                  ((u.ndim == 1 and u.flags.c_contiguous) or (u.ndim == 2 and u.flags.f_contiguous)) and
+                  not np.shares_memory(u, b))
         x = cv.handle.solve(b, out=u if direct else None, trans="T" if adjoint else "N")
         if direct:
             x = None   # getrs wrote straight into cache.u
