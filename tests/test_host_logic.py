@@ -65,6 +65,22 @@ def test_bad_arguments_do_not_need_a_device(ls):
     assert lib.b200lu_set_option(None, 0, 64) == -1
 
 
+def test_header_enums_match_the_python_binding(ls):
+    """include/b200lu.h is the contract: every B200LU_OPT_* / element-type constant the ctypes
+    binding uses has the value the header declares, and the header's OPT_COUNT covers them all."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "b200lu.h")).read()
+    enums = {m.group(1): int(m.group(2)) for m in re.finditer(r"\bB200LU_([A-Z0-9_]+)\s*=\s*(\d+)", hdr)}
+    C = ls._capi
+    opts = [k for k in enums if k.startswith("OPT_") and k != "OPT_COUNT"]
+    assert len(opts) == enums["OPT_COUNT"] and sorted(enums[k] for k in opts) == list(range(enums["OPT_COUNT"]))
+    for k in opts:
+        assert getattr(C, k) == enums[k], k
+    for k in ("F64", "F32", "MIXED"):
+        assert getattr(C, k) == enums[k], k
+
+
 def test_default_algorithm_bands_unchanged(ls):
     """reference test/Core/default_algs.jl:4-66 with and without the new arm"""
     C = ls.DefaultAlgorithmChoice
