@@ -166,8 +166,9 @@ int b200lu_factor(b200lu_handle* h, int64_t n, const void* A_host, int64_t lda,
  * the cached factorization is singular (info > 0) or absent.  'T'/'C' (the
  * reference's `solve!(cache; adjoint = true)`, src/common.jl:1012-1027; LAPACK
  * getrs trans argument, src/openblas.jl:247-278) reuse the same factors:
- * U^T y = b, L^T z = y, x = P^T z; supported for F64 and F32 handles (status -2
- * for MIXED).
+ * U^T y = b, L^T z = y, x = P^T z; every handle type (B200LU_MIXED refines the
+ * transposed system: FP32 transposed sweeps + FP64 residual b - A^T x, one
+ * right-hand side at a time).
  */
 int b200lu_solve(b200lu_handle* h, char trans, int64_t nrhs,
                  const void* B_host, int64_t ldb, void* X_host, int64_t ldx);
@@ -198,12 +199,21 @@ int b200lu_factor_batched(b200lu_handle* h, int64_t batch, int64_t n,
 int b200lu_solve_batched(b200lu_handle* h, int64_t nrhs,
                          const void* B_host, int64_t ldb, int64_t strideB,
                          void* X_host, int64_t ldx, int64_t strideX);
+/* The same getrs with op(A_i) = A_i^T ('T'/'C'; 'N' is b200lu_solve_batched): the adjoint
+ * solve of a BlockDiagonal problem with the cached per-block factors
+ * (`solve!(cache; adjoint = true)`, src/common.jl:1012-1027). */
+int b200lu_solve_batched_trans(b200lu_handle* h, char trans, int64_t nrhs,
+                               const void* B_host, int64_t ldb, int64_t strideB,
+                               void* X_host, int64_t ldx, int64_t strideX);
 int b200lu_factor_batched_device(b200lu_handle* h, int64_t batch, int64_t n,
                                  const void* A_dev, int64_t lda, int64_t strideA,
                                  int64_t* any_info);
 int b200lu_solve_batched_device(b200lu_handle* h, int64_t nrhs,
                                 const void* B_dev, int64_t ldb, int64_t strideB,
                                 void* X_dev, int64_t ldx, int64_t strideX);
+int b200lu_solve_batched_trans_device(b200lu_handle* h, char trans, int64_t nrhs,
+                                      const void* B_dev, int64_t ldb, int64_t strideB,
+                                      void* X_dev, int64_t ldx, int64_t strideX);
 int b200lu_get_factors_batched(b200lu_handle* h, void* LU_host, int64_t lda,
                                int64_t strideA, int64_t* ipiv_out, int64_t* info_out);
 

@@ -29,6 +29,8 @@ from .interface import (
     block_cyclic_columns,
     defaultalg,
     init,
+    pad_blocks,
+    plan_blockdiag,
     reduce_info,
     reinit,
     shard_batch,

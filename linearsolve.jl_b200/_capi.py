@@ -31,6 +31,7 @@ SYMBOLS = [
     "b200lu_get_factors", "b200lu_get_ipiv",
     "b200lu_factor_batched", "b200lu_solve_batched", "b200lu_factor_batched_device",
     "b200lu_solve_batched_device", "b200lu_get_factors_batched",
+    "b200lu_solve_batched_trans", "b200lu_solve_batched_trans_device",
     "b200lu_comm_unique_id", "b200lu_comm_init", "b200lu_dist_local_cols",
     "b200lu_factor_dist", "b200lu_solve_dist", "b200lu_fill_uniform_device",
 ]
@@ -80,6 +81,8 @@ def load():
     P("b200lu_solve_batched", ci, [vp, i64, vp, i64, i64, vp, i64, i64])
     P("b200lu_factor_batched_device", ci, [vp, i64, i64, vp, i64, i64, pi64])
     P("b200lu_solve_batched_device", ci, [vp, i64, vp, i64, i64, vp, i64, i64])
+    P("b200lu_solve_batched_trans", ci, [vp, ctypes.c_char, i64, vp, i64, i64, vp, i64, i64])
+    P("b200lu_solve_batched_trans_device", ci, [vp, ctypes.c_char, i64, vp, i64, i64, vp, i64, i64])
     P("b200lu_get_factors_batched", ci, [vp, vp, i64, i64, vp, vp])
     P("b200lu_comm_unique_id", ci, [vp])
     P("b200lu_comm_init", ci, [vp, vp, ci, ci])
@@ -276,16 +279,23 @@ class Handle:
         self.b_batch, self.b_n = batch, n
         return ipiv, info
 
-    def solve_batched(self, B):
-        """B: (batch, n) or (batch, nrhs, n) (each right-hand side contiguous)."""
+    def solve_batched(self, B, trans="N"):
+        """B: (batch, n) or (batch, nrhs, n) (each right-hand side contiguous).
+        trans = 'T'/'C': op(A_i) = A_i^T with the same cached factors."""
         B = np.ascontiguousarray(B)
+        if B.dtype != self.np_dtype:
+            raise TypeError(f"expected {self.np_dtype}, got {B.dtype}")
         vec = B.ndim == 2
         Bm = B.reshape(self.b_batch, 1, self.b_n) if vec else B
         nrhs = Bm.shape[1]
         X = np.empty_like(Bm)
         n = self.b_n
-        self._check(self.lib.b200lu_solve_batched(self._h, nrhs, Bm.ctypes.data, n, n * nrhs,
-                                                  X.ctypes.data, n, n * nrhs))
+        if trans in ("N", "n"):
+            self._check(self.lib.b200lu_solve_batched(self._h, nrhs, Bm.ctypes.data, n, n * nrhs,
+                                                      X.ctypes.data, n, n * nrhs))
+        else:
+            self._check(self.lib.b200lu_solve_batched_trans(self._h, trans.encode(), nrhs, Bm.ctypes.data, n,
+                                                            n * nrhs, X.ctypes.data, n, n * nrhs))
         return X.reshape(B.shape)
 
     def get_factors_batched(self):
@@ -306,7 +316,12 @@ class Handle:
         self.b_batch, self.b_n = batch, n
         return int(bad.value)
 
-    def solve_batched_device(self, b_ptr, x_ptr, nrhs=1):
+    def solve_batched_device(self, b_ptr, x_ptr, nrhs=1, trans="N"):
         n = self.b_n
-        self._check(self.lib.b200lu_solve_batched_device(self._h, nrhs, ctypes.c_void_p(b_ptr), n, n * nrhs,
-                                                         ctypes.c_void_p(x_ptr), n, n * nrhs))
+        if trans in ("N", "n"):
+            self._check(self.lib.b200lu_solve_batched_device(self._h, nrhs, ctypes.c_void_p(b_ptr), n, n * nrhs,
+                                                             ctypes.c_void_p(x_ptr), n, n * nrhs))
+        else:
+            self._check(self.lib.b200lu_solve_batched_trans_device(self._h, trans.encode(), nrhs,
+                                                                   ctypes.c_void_p(b_ptr), n, n * nrhs,
+                                                                   ctypes.c_void_p(x_ptr), n, n * nrhs))

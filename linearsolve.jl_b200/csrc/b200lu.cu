@@ -1208,20 +1208,24 @@ static int refine_solve_block_device(b200lu_handle* h, const double* B, int64_t 
     return 0;
 }
 
+// trans: op(A) = A^T — the same loop with the transposed FP32 sweeps (U^T, L^T, P^T scatter) and the
+// residual r = b - A^T x (one contiguous dot product per column of A), one right-hand side at a time.
 static int refine_solve_device(b200lu_handle* h, const double* B, int64_t ldb, double* X,
-                               int64_t ldx, int nrhs) {
+                               int64_t ldx, int nrhs, bool trans = false) {
     const int n = (int)h->n;
     cudaStream_t st = h->s_main;
     // matrix right-hand side: refine the block as a whole when the GEMM operands are 16-byte aligned
     // and B does not alias X (the residual needs the original B in every sweep)
-    if (nrhs >= 4 && 2 * nrhs <= n && (const void*)B != (const void*)X && (ldx % 2) == 0 && (n % 2) == 0 &&
+    if (!trans && nrhs >= 4 && 2 * nrhs <= n && (const void*)B != (const void*)X && (ldx % 2) == 0 && (n % 2) == 0 &&
         (reinterpret_cast<uintptr_t>(X) % 16) == 0)
         return refine_solve_block_device(h, B, ldb, X, ldx, nrhs);
     const int maxit = (int)h->opt[B200LU_OPT_REFINE_MAXIT];
     const double eps = 2.220446049250313e-16;
-    int rc = ensure_rhs(h, 1);
+    int rc = ensure_rhs(h, trans ? 2 : 1);
     if (rc) return rc;
     float* w32 = (float*)h->d_X;  // n floats of scratch
+    // the copy of b: column 0 of d_B, or column 1 when the transposed sweeps use column 0 for x = P^T z
+    double* const bcopy = (double*)h->d_B + (trans ? h->cap_n : 0);
     h->last_refine_iters = 0;
     for (int c = 0; c < nrhs; ++c) {
         const double* b = B + (int64_t)c * ldb;
@@ -1229,10 +1233,9 @@ static int refine_solve_device(b200lu_handle* h, const double* B, int64_t ldb, d
         // x0 = fl64( solve32( fl32(b) ) )
         cast2d_kernel<double, float><<<dim3(cdiv(n, 256), 1), 256, 0, st>>>(b, n, h->d_r32, n, n, 1);
         LAUNCH_CHECK(h);
-        rc = getrs_device<float>(h, h->d_r32, n, w32, n, 1);
+        rc = getrs_device<float>(h, h->d_r32, n, w32, n, 1, trans);
         if (rc) return rc;
         // b may alias x: keep a copy of b in d_r's sibling (d_B, FP64)
-        double* bcopy = (double*)h->d_B;
         CU_TRY(h, cudaMemcpyAsync(bcopy, b, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
         cast2d_kernel<float, double><<<dim3(cdiv(n, 256), 1), 256, 0, st>>>(w32, n, x, n, n, 1);
         LAUNCH_CHECK(h);
@@ -1241,8 +1244,11 @@ static int refine_solve_device(b200lu_handle* h, const double* B, int64_t ldb, d
             // r = b - A x in FP64
             CU_TRY(h, cudaMemcpyAsync(h->d_r, bcopy, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
             const int cchunk = 512;
-            residual_gemv_kernel<double><<<dim3(cdiv(n, 256), cdiv(n, cchunk)), 256, 0, st>>>(
-                h->dA64, h->ldd, n, x, h->d_r, cchunk);
+            if (trans)
+                residual_gemvT_kernel<double><<<cdiv(n, 8), 256, 0, st>>>(h->dA64, h->ldd, n, x, h->d_r);
+            else
+                residual_gemv_kernel<double><<<dim3(cdiv(n, 256), cdiv(n, cchunk)), 256, 0, st>>>(
+                    h->dA64, h->ldd, n, x, h->d_r, cchunk);
             LAUNCH_CHECK(h);
             CU_TRY(h, cudaMemsetAsync(h->d_scal, 0, 4 * sizeof(double), st));
             sumsq_kernel<<<std::min(cdiv(n, 256), 1024), 256, 0, st>>>(h->d_r, n, h->d_scal + 0);
@@ -1263,7 +1269,7 @@ static int refine_solve_device(b200lu_handle* h, const double* B, int64_t ldb, d
             prev = berr;
             cast2d_kernel<double, float><<<dim3(cdiv(n, 256), 1), 256, 0, st>>>(h->d_r, n, h->d_r32, n, n, 1);
             LAUNCH_CHECK(h);
-            rc = getrs_device<float>(h, h->d_r32, n, w32, n, 1);
+            rc = getrs_device<float>(h, h->d_r32, n, w32, n, 1, trans);
             if (rc) return rc;
             axpy_f32_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, w32, n);
             LAUNCH_CHECK(h);
@@ -1642,8 +1648,6 @@ static int check_solve_args(b200lu_handle* h, char trans, int64_t nrhs, const vo
     if (!h) return -1;
     const bool tr = (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c');   // real types: 'C' == 'T'
     if (!tr && trans != 'N' && trans != 'n') return set_err(h, -2, "trans='%c' is not one of N, T, C", trans);
-    if (tr && h->dtype == B200LU_MIXED)
-        return set_err(h, -2, "transposed solves are not implemented for the mixed-precision handle");
     if (nrhs < 0) return set_err(h, -3, "nrhs < 0");
     if (!h->factored) return set_err(h, 3, "no factorization cached");
     if (h->info != 0) return set_err(h, 3, "cached factorization is singular (info=%lld)", (long long)h->info);
@@ -1678,7 +1682,7 @@ int b200lu_solve_device(b200lu_handle* h, char trans, int64_t nrhs, const void* 
     else if (h->dtype == B200LU_F32)
         rc = getrs_device<float>(h, (const float*)B_dev, ldb, (float*)X_dev, ldx, (int)nrhs, trans != 'N' && trans != 'n');
     else
-        rc = refine_solve_device(h, (const double*)B_dev, ldb, (double*)X_dev, ldx, (int)nrhs);
+        rc = refine_solve_device(h, (const double*)B_dev, ldb, (double*)X_dev, ldx, (int)nrhs, trans != 'N' && trans != 'n');
     if (rc) return rc;
     CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
     rc = finish_solve(h);
@@ -1744,7 +1748,7 @@ int b200lu_solve(b200lu_handle* h, char trans, int64_t nrhs, const void* B_host,
     else if (h->dtype == B200LU_F32)
         rc = getrs_device<float>(h, (const float*)dBs, n, (float*)dXs, n, (int)nrhs, trans != 'N' && trans != 'n');
     else
-        rc = refine_solve_device(h, (const double*)dBs, n, (double*)dXs, n, (int)nrhs);
+        rc = refine_solve_device(h, (const double*)dBs, n, (double*)dXs, n, (int)nrhs, trans != 'N' && trans != 'n');
     if (rc) return rc;
     CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
     CU_TRY(h, cudaMemcpy2DAsync(X_host, (size_t)ldx * is, dXs, (size_t)n * is, (size_t)n * is,
@@ -1840,7 +1844,7 @@ static int batched_factor_launch(b200lu_handle* h, const T* A, int64_t lda, int6
 
 template <typename T>
 static int batched_solve_launch(b200lu_handle* h, int nrhs, const T* B, int64_t ldb, int64_t strideB,
-                                T* X, int64_t ldx, int64_t strideX) {
+                                T* X, int64_t ldx, int64_t strideX, bool trans = false) {
     const int n = (int)h->b_n;
     const int64_t batch = h->b_batch;
     const T* LU = (const T*)h->dB_LU;
@@ -1848,10 +1852,16 @@ static int batched_solve_launch(b200lu_handle* h, int nrhs, const T* B, int64_t 
     // WPC systems (warps) per CTA: about 32 KB of staged factors per CTA
 #define GETRS_B(NMAXV, WPCV)                                                                      \
     {                                                                                             \
-        const size_t smem = (size_t)(WPCV) * (NMAXV) * (NMAXV) * sizeof(T);                        \
         const unsigned grid = (unsigned)((batch + (WPCV) - 1) / (WPCV));                           \
-        getrs_batched_kernel<T, NMAXV, WPCV><<<grid, 32 * (WPCV), smem, st>>>(                     \
-            LU, n, (int64_t)n * n, h->dB_perm, B, ldb, strideB, X, ldx, strideX, n, nrhs, batch);  \
+        if (trans) {                                                                              \
+            const size_t smem = (size_t)(WPCV) * (NMAXV) * ((NMAXV) + 1) * sizeof(T);              \
+            getrs_batched_trans_kernel<T, NMAXV, WPCV><<<grid, 32 * (WPCV), smem, st>>>(           \
+                LU, n, (int64_t)n * n, h->dB_perm, B, ldb, strideB, X, ldx, strideX, n, nrhs, batch); \
+        } else {                                                                                  \
+            const size_t smem = (size_t)(WPCV) * (NMAXV) * (NMAXV) * sizeof(T);                    \
+            getrs_batched_kernel<T, NMAXV, WPCV><<<grid, 32 * (WPCV), smem, st>>>(                 \
+                LU, n, (int64_t)n * n, h->dB_perm, B, ldb, strideB, X, ldx, strideX, n, nrhs, batch); \
+        }                                                                                         \
     }
     if (n <= 16) GETRS_B(16, 8)
     else if (n <= 32) GETRS_B(32, 4)
@@ -1911,9 +1921,14 @@ int b200lu_factor_batched_device(b200lu_handle* h, int64_t batch, int64_t n, con
     return 0;
 }
 
-int b200lu_solve_batched_device(b200lu_handle* h, int64_t nrhs, const void* B_dev, int64_t ldb,
-                                int64_t strideB, void* X_dev, int64_t ldx, int64_t strideX) {
-    if (!h) return -1;
+static int parse_trans(b200lu_handle* h, char trans, bool* tr) {
+    *tr = (trans == 'T' || trans == 't' || trans == 'C' || trans == 'c');   // real element types: 'C' == 'T'
+    if (!*tr && trans != 'N' && trans != 'n') return set_err(h, -2, "trans='%c' is not one of N, T, C", trans);
+    return 0;
+}
+
+static int solve_batched_device_impl(b200lu_handle* h, bool trans, int64_t nrhs, const void* B_dev, int64_t ldb,
+                                     int64_t strideB, void* X_dev, int64_t ldx, int64_t strideX) {
     if (!h->b_factored) return set_err(h, 3, "no batched factorization cached");
     if (nrhs < 0) return set_err(h, -2, "nrhs < 0");
     if (h->b_batch == 0 || h->b_n == 0 || nrhs == 0) return 0;
@@ -1923,9 +1938,9 @@ int b200lu_solve_batched_device(b200lu_handle* h, int64_t nrhs, const void* B_de
     int rc;
     CU_TRY(h, cudaEventRecord(h->ev_b, h->s_main));
     if (h->dtype == B200LU_F64)
-        rc = batched_solve_launch<double>(h, (int)nrhs, (const double*)B_dev, ldb, strideB, (double*)X_dev, ldx, strideX);
+        rc = batched_solve_launch<double>(h, (int)nrhs, (const double*)B_dev, ldb, strideB, (double*)X_dev, ldx, strideX, trans);
     else
-        rc = batched_solve_launch<float>(h, (int)nrhs, (const float*)B_dev, ldb, strideB, (float*)X_dev, ldx, strideX);
+        rc = batched_solve_launch<float>(h, (int)nrhs, (const float*)B_dev, ldb, strideB, (float*)X_dev, ldx, strideX, trans);
     if (rc) return rc;
     CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
     CU_TRY(h, cudaStreamSynchronize(h->s_main));
@@ -1933,6 +1948,21 @@ int b200lu_solve_batched_device(b200lu_handle* h, int64_t nrhs, const void* B_de
     cudaEventElapsedTime(&ms, h->ev_b, h->ev_c);
     h->timing[B200LU_T_SOLVE] = ms;
     return 0;
+}
+
+int b200lu_solve_batched_device(b200lu_handle* h, int64_t nrhs, const void* B_dev, int64_t ldb,
+                                int64_t strideB, void* X_dev, int64_t ldx, int64_t strideX) {
+    if (!h) return -1;
+    return solve_batched_device_impl(h, false, nrhs, B_dev, ldb, strideB, X_dev, ldx, strideX);
+}
+
+int b200lu_solve_batched_trans_device(b200lu_handle* h, char trans, int64_t nrhs, const void* B_dev, int64_t ldb,
+                                      int64_t strideB, void* X_dev, int64_t ldx, int64_t strideX) {
+    if (!h) return -1;
+    bool tr = false;
+    int rc = parse_trans(h, trans, &tr);
+    if (rc) return rc;
+    return solve_batched_device_impl(h, tr, nrhs, B_dev, ldb, strideB, X_dev, ldx, strideX);
 }
 
 int b200lu_factor_batched(b200lu_handle* h, int64_t batch, int64_t n, const void* A_host, int64_t lda,
@@ -2001,9 +2031,8 @@ int b200lu_get_factors_batched(b200lu_handle* h, void* LU_host, int64_t lda, int
     return 0;
 }
 
-int b200lu_solve_batched(b200lu_handle* h, int64_t nrhs, const void* B_host, int64_t ldb,
-                         int64_t strideB, void* X_host, int64_t ldx, int64_t strideX) {
-    if (!h) return -1;
+static int solve_batched_impl(b200lu_handle* h, bool trans, int64_t nrhs, const void* B_host, int64_t ldb,
+                              int64_t strideB, void* X_host, int64_t ldx, int64_t strideX) {
     if (!h->b_factored) return set_err(h, 3, "no batched factorization cached");
     if (nrhs < 0) return set_err(h, -2, "nrhs < 0");
     const int64_t batch = h->b_batch, n = h->b_n;
@@ -2031,7 +2060,7 @@ int b200lu_solve_batched(b200lu_handle* h, int64_t nrhs, const void* B_host, int
                                         (const char*)B_host + (size_t)(i * strideB) * is, (size_t)ldb * is,
                                         (size_t)n * is, (size_t)nrhs, cudaMemcpyHostToDevice, h->s_main));
     }
-    int rc = b200lu_solve_batched_device(h, nrhs, h->dB_rhs, n, n * nrhs, h->dB_x, n, n * nrhs);
+    int rc = solve_batched_device_impl(h, trans, nrhs, h->dB_rhs, n, n * nrhs, h->dB_x, n, n * nrhs);
     if (rc) return rc;
     const bool compactX = (ldx == n) && (strideX == n * nrhs || batch == 1);
     CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
@@ -2049,6 +2078,21 @@ int b200lu_solve_batched(b200lu_handle* h, int64_t nrhs, const void* B_host, int
     cudaEventElapsedTime(&ms, h->ev_c, h->ev_d);
     h->timing[B200LU_T_D2H] = ms;
     return 0;
+}
+
+int b200lu_solve_batched(b200lu_handle* h, int64_t nrhs, const void* B_host, int64_t ldb,
+                         int64_t strideB, void* X_host, int64_t ldx, int64_t strideX) {
+    if (!h) return -1;
+    return solve_batched_impl(h, false, nrhs, B_host, ldb, strideB, X_host, ldx, strideX);
+}
+
+int b200lu_solve_batched_trans(b200lu_handle* h, char trans, int64_t nrhs, const void* B_host, int64_t ldb,
+                               int64_t strideB, void* X_host, int64_t ldx, int64_t strideX) {
+    if (!h) return -1;
+    bool tr = false;
+    int rc = parse_trans(h, trans, &tr);
+    if (rc) return rc;
+    return solve_batched_impl(h, tr, nrhs, B_host, ldb, strideB, X_host, ldx, strideX);
 }
 
 // --------------------------------------------------------------- synthetic --

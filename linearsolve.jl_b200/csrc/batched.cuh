@@ -244,4 +244,80 @@ __global__ void __launch_bounds__(32 * WPC) getrs_batched_kernel(
     }
 }
 
+// getrs with op(A) = A^T on the cached batched factors (the reference's `solve!(cache; adjoint = true)`,
+// src/common.jl:1012-1027, for BlockDiagonal problems): P A = L U  =>  A^T = U^T L^T P, so
+// U^T y = b (lower, divide by the diagonal), L^T z = y (unit upper), x = P^T z (x[perm[p]] = z[p]).
+// Same mapping as getrs_batched_kernel (one warp per system, lane l holds rows l and l + 32,
+// chains on shuffles); the factors are staged ROW-major with a padded leading dimension
+// (s_t[r * (NMAX + 1) + c] = LU[r, c]) so that the column-oriented sweeps of the transposed
+// triangles read consecutive shared-memory words.
+template <typename T, int NMAX, int WPC>
+__global__ void __launch_bounds__(32 * WPC) getrs_batched_trans_kernel(
+    const T* __restrict__ LU, long long ldlu, long long strideLU, const int* __restrict__ perm,
+    const T* __restrict__ B, long long ldb, long long strideB, T* __restrict__ X, long long ldx,
+    long long strideX, int n, int nrhs, long long batch) {
+    constexpr int RPL = (NMAX + 31) / 32;
+    constexpr int LDS = NMAX + 1;
+    extern __shared__ __align__(16) unsigned char getrs_bt_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long sys = (long long)blockIdx.x * WPC + warp;
+    if (sys >= batch) return;
+    T* s_t = reinterpret_cast<T*>(getrs_bt_smem) + (size_t)warp * NMAX * LDS;
+    const T* Lb = LU + sys * strideLU;
+    for (int i = lane; i < n * n; i += 32) {
+        const int c = i / n, r = i - c * n;
+        s_t[r * LDS + c] = Lb[(long long)c * ldlu + r];
+    }
+    __syncwarp();
+    int dst[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int row = r * 32 + lane;
+        dst[r] = row < n ? perm[sys * n + row] : 0;
+    }
+    for (int rhs = 0; rhs < nrhs; ++rhs) {
+        T b[RPL];
+#pragma unroll
+        for (int r = 0; r < RPL; ++r)
+            b[r] = (r * 32 + lane < n) ? B[sys * strideB + (long long)rhs * ldb + r * 32 + lane] : T(0);
+        // forward: U^T y = b; (U^T)[row, k] = U[k, row] = s_t[k * LDS + row] for row > k
+#pragma unroll
+        for (int kr = 0; kr < RPL; ++kr) {
+            const int kend = min(32, n - kr * 32);
+#pragma unroll 4
+            for (int kk = 0; kk < kend; ++kk) {
+                const int k = kr * 32 + kk;
+                if (lane == kk) b[kr] = b[kr] / s_t[k * LDS + k];
+                const T xk = __shfl_sync(0xffffffffu, b[kr], kk);
+#pragma unroll
+                for (int r = kr; r < RPL; ++r) {
+                    const int row = r * 32 + lane;
+                    if (row > k && row < n) b[r] = tfma(-s_t[k * LDS + row], xk, b[r]);
+                }
+            }
+        }
+        // backward: L^T z = y, unit diagonal; (L^T)[row, k] = L[k, row] = s_t[k * LDS + row] for row < k
+#pragma unroll
+        for (int kr = RPL - 1; kr >= 0; --kr) {
+            const int kend = min(32, n - kr * 32);
+#pragma unroll 4
+            for (int kk = kend - 1; kk >= 0; --kk) {
+                const int k = kr * 32 + kk;
+                const T xk = __shfl_sync(0xffffffffu, b[kr], kk);
+#pragma unroll
+                for (int r = 0; r <= kr; ++r) {
+                    const int row = r * 32 + lane;
+                    if (row < k) b[r] = tfma(-s_t[k * LDS + row], xk, b[r]);
+                }
+            }
+        }
+        // x = P^T z: the entry at position p belongs to original row perm[p] (all loads of this
+        // right-hand side are done, so X may alias B)
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < RPL; ++r)
+            if (r * 32 + lane < n) X[sys * strideX + (long long)rhs * ldx + dst[r]] = b[r];
+    }
+}
+
 }  // namespace b200lu

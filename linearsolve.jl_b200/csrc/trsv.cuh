@@ -557,4 +557,30 @@ __global__ void __launch_bounds__(256) residual_gemv_kernel(const TA* __restrict
     atomicAdd(y + row, -((s0 + s1) + (s2 + s3)));
 }
 
+// y -= A^T x (the residual of the transposed system, MIXED refinement with trans = 'T'): one warp per
+// COLUMN of the column-major A — a contiguous dot product, 256 bytes per warp request, four
+// independent accumulators, shuffle tree, ONE writer per y[c] (no atomics: deterministic).
+template <typename TA>
+__global__ void __launch_bounds__(256) residual_gemvT_kernel(const TA* __restrict__ A, long long lda,
+                                                             int n, const double* __restrict__ x,
+                                                             double* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= n) return;   // whole warps leave together
+    const TA* ap = A + (long long)c * lda;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int r = lane;
+    for (; r + 96 < n; r += 128) {
+        s0 = fma((double)ap[r], x[r], s0);
+        s1 = fma((double)ap[r + 32], x[r + 32], s1);
+        s2 = fma((double)ap[r + 64], x[r + 64], s2);
+        s3 = fma((double)ap[r + 96], x[r + 96], s3);
+    }
+    for (; r < n; r += 32) s0 = fma((double)ap[r], x[r], s0);
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) y[c] -= s;
+}
+
 }  // namespace b200lu

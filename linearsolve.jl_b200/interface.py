@@ -161,7 +161,8 @@ class _B200LUCache:
         self.handle = None
         self.ipiv = None
         self.info = 0
-        self.groups = None  # BlockDiagonal: list of (handle, block indices, n)
+        self.groups = None  # BlockDiagonal: list of (kind, handle, block indices, padded size)
+        self.group_sizes = None
 
 
 class LinearCache:
@@ -254,57 +255,100 @@ def _configure(handle, alg):
         handle.set_option(_capi.OPT_REFINE_MAXIT, alg.maxiters if alg.refine else 0)
 
 
+# kernel classes of the batched getrf/getrs (template NMAX in csrc/batched.cuh); larger blocks take
+# the single-system path, one handle each
+_BATCHED_CLASSES = (16, 32, 64)
+
+
+def plan_blockdiag(sizes):
+    """Launch plan for a BlockDiagonal with blocks of `sizes` (ragged allowed, the reference's
+    `[2, 3, 4]` case and the variable-size supernode blocks of SURVEY §8(f)3): every block of up
+    to 64 rows joins the batched launch of its kernel class, embedded in the class's largest
+    member size m as diag(B, I) — at most three launches however ragged the sizes are; blocks
+    above 64 are factored one by one.  Returns [(kind, block indices, m)], kind in
+    {"batched", "single"}; empty blocks appear nowhere."""
+    by_class = {}
+    singles = []
+    for i, n in enumerate(sizes):
+        if n == 0:
+            continue
+        cls = next((c for c in _BATCHED_CLASSES if n <= c), None)
+        if cls is None:
+            singles.append(i)
+        else:
+            by_class.setdefault(cls, []).append(i)
+    plan = [("batched", idx, max(sizes[i] for i in idx)) for _, idx in sorted(by_class.items())]
+    plan += [("single", [i], sizes[i]) for i in singles]
+    return plan
+
+
+def pad_blocks(blocks, idx, m, dtype):
+    """Stack blocks[idx] as (len(idx), m, m) column-major systems, block B embedded as diag(B, I).
+    Partial pivoting never looks at the padding: in column k < n the padding rows hold exact zeros
+    (an all-zero subcolumn keeps kp = k, like the unpadded block), their multipliers are 0 and the
+    rank-1 updates leave them untouched, and for k >= n the pivot is the unit diagonal.  So
+    ipiv[:n], info and the leading n x n factors are those of B itself, bit for bit."""
+    stack = np.zeros((len(idx), m, m), dtype=dtype)
+    pad = np.arange(m)
+    for s, i in enumerate(idx):
+        B = blocks[i]
+        n = B.shape[0]
+        stack[s, :n, :n] = B.T          # [s, col, row]
+        stack[s, pad[n:], pad[n:]] = 1
+    return stack
+
+
 def _factor_blockdiag(cache, alg):
-    """Blockwise LU (ext/LinearSolveBlockDiagonalsExt.jl:119-125): blocks of equal
-    size <= 64 go through ONE batched launch; larger blocks one by one.
+    """Blockwise LU (ext/LinearSolveBlockDiagonalsExt.jl:119-125): see plan_blockdiag.
     success = all(issuccess) (:121-124)."""
     A = cache.A
     cv = cache.cacheval
-    by_size = {}
-    for i, B in enumerate(A.blocks):
-        by_size.setdefault(B.shape[0], []).append(i)
-    sig = [(n, len(by_size[n])) for n in sorted(by_size)]
-    if cv.groups is None or [(g[2], len(g[1])) for g in cv.groups] != sig:
+    if not A.all_square():
+        raise ValueError("B200LUFactorization needs square diagonal blocks")
+    sizes = [B.shape[0] for B in A.blocks]
+    dt = alg.handle_dtype(A.dtype)
+    if cv.groups is None or cv.group_sizes != (sizes, dt):
         cv.groups = []
-        for n in sorted(by_size):
-            # n <= 64: one handle caches the whole batch; larger blocks: one handle each
-            cnt = 1 if n <= 64 else len(by_size[n])
-            hs = []
-            for _ in range(cnt):
-                h = _capi.Handle(alg.handle_dtype(A.dtype), alg.device)
-                _configure(h, alg)
-                hs.append(h)
-            cv.groups.append([hs, by_size[n], n])
+        for kind, idx, m in plan_blockdiag(sizes):
+            h = _capi.Handle(dt, alg.device)
+            _configure(h, alg)
+            cv.groups.append((kind, h, idx, m))
+        cv.group_sizes = (sizes, dt)
     ok = True
-    for hs, idx, n in cv.groups:
-        if n <= 64:
-            stack = np.stack([np.asfortranarray(A.blocks[i]).T for i in idx])  # [s, col, row]
-            _, info = hs[0].factor_batched(np.ascontiguousarray(stack))
+    for kind, h, idx, m in cv.groups:
+        if kind == "batched":
+            _, info = h.factor_batched(pad_blocks(A.blocks, idx, m, h.np_dtype))
             ok = ok and not np.any(info != 0)
         else:
-            for hh, i in zip(hs, idx):
-                _, info = hh.factor(np.asfortranarray(A.blocks[i]), want_ipiv=False)
-                ok = ok and info == 0
+            _, info = h.factor(np.asfortranarray(A.blocks[idx[0]], dtype=h.np_dtype), want_ipiv=False)
+            ok = ok and info == 0
     cv.info = 0 if ok else 1
     return cv.info
 
 
-def _solve_blockdiag(cache):
+def _solve_blockdiag(cache, adjoint=False):
+    """per-block ldiv! on views of b (ext/LinearSolveBlockDiagonalsExt.jl:183-205); `adjoint`: the
+    transposed blocks with the same factors (block-diagonal structure is its own transpose)"""
     A, cv = cache.A, cache.cacheval
     b = np.asarray(cache.b)
     vec = b.ndim == 1
     Bm = b.reshape(b.shape[0], -1)
     X = np.empty_like(Bm)
-    for hs, idx, n in cv.groups:
-        if n <= 64:
-            # (batch, nrhs, n): each right-hand side contiguous
-            rhs = np.stack([Bm[A.offsets[i]:A.offsets[i] + n, :].T for i in idx])
-            sol = hs[0].solve_batched(np.ascontiguousarray(rhs))
+    trans = "T" if adjoint else "N"
+    for kind, h, idx, m in cv.groups:
+        if kind == "batched":
+            # (batch, nrhs, m): each right-hand side contiguous, zero in the padding rows
+            rhs = np.zeros((len(idx), Bm.shape[1], m), dtype=h.np_dtype)
             for s, i in enumerate(idx):
-                X[A.offsets[i]:A.offsets[i] + n, :] = sol[s].T
+                o, n = A.offsets[i], A.blocks[i].shape[0]
+                rhs[s, :, :n] = Bm[o:o + n, :].T
+            sol = h.solve_batched(rhs, trans=trans)
+            for s, i in enumerate(idx):
+                o, n = A.offsets[i], A.blocks[i].shape[0]
+                X[o:o + n, :] = sol[s, :, :n].T
         else:
-            for hh, i in zip(hs, idx):
-                X[A.offsets[i]:A.offsets[i] + n, :] = hh.solve(np.asfortranarray(Bm[A.offsets[i]:A.offsets[i] + n, :]))
+            o, n = A.offsets[idx[0]], m
+            X[o:o + n, :] = h.solve(np.asfortranarray(Bm[o:o + n, :], dtype=h.np_dtype), trans=trans)
     return X[:, 0] if vec else X
 
 
@@ -343,9 +387,7 @@ def solve_(cache: LinearCache, alg=None, adjoint: bool = False) -> LinearSolutio
             return LinearSolution(cache.u, ReturnCode.Failure, alg)
         cache.isfresh = False
     if isinstance(A, BlockDiagonal):
-        if adjoint:
-            raise NotImplementedError("adjoint solves of BlockDiagonal problems")
-        x = _solve_blockdiag(cache)
+        x = _solve_blockdiag(cache, adjoint)
     else:
         u, b = cache.u, np.asarray(cache.b)
         # a plain vector u, or a column-major matrix u: getrs writes straight into cache.u

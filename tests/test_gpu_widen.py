@@ -1,0 +1,117 @@
+"""Rows SURVEY §8 marks "next", at the same parity bar as the hot path: adjoint solves for
+every handle type (`solve!(cache; adjoint = true)`, reference src/common.jl:1012-1027 and
+test/Core/adjoint.jl) and ragged BlockDiagonal problems in one batched launch per kernel class
+(ext/LinearSolveBlockDiagonalsExt.jl:119-125,183-205; test/Core/basictests.jl:1168-1223)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+EPS = np.finfo(np.float64).eps
+
+
+def _berr(M, x, b):
+    return np.linalg.norm(M @ x - b) / (np.linalg.norm(M) * np.linalg.norm(x))
+
+
+@pytest.mark.parametrize("n", [100, 1000, 2500])
+def test_mixed_adjoint_refines_transposed_system(gpu_required, ls, n):
+    """FP32 factors of A + FP64 refinement of A^T x = b: transposed FP32 sweeps, residual
+    b - A^T x in FP64; backward error of the TRANSPOSED system <= 10 n eps64 (north-star bar)."""
+    rng = np.random.default_rng(900 + n)
+    A = np.asfortranarray(rng.random((n, n)) + 5.0 * np.eye(n))
+    b = rng.random(n)
+    cache = ls.init(ls.LinearProblem(A, b), ls.B200LU32MixedLUFactorization())
+    x = ls.solve_(cache).u.copy()
+    assert _berr(A, x, b) <= 10 * n * EPS
+    sol = ls.solve_(cache, adjoint=True)
+    assert sol.retcode == ls.ReturnCode.Success and not cache.isfresh
+    xt = sol.u.copy()
+    assert _berr(A.T, xt, b) <= 10 * n * EPS
+    assert _berr(A.T, xt, b) <= 50 * EPS          # refinement reaches a few eps
+    # matrix right-hand side, column by column
+    B = np.asfortranarray(rng.random((n, 3)))
+    Xt = cache.cacheval.handle.solve(B, trans="T")
+    for c in range(3):
+        assert _berr(A.T, Xt[:, c], B[:, c]) <= 10 * n * EPS
+    # the untransposed solve still works afterwards (not bitwise: its residual kernel sums column
+    # chunks with atomics)
+    x2 = ls.solve_(cache).u
+    assert _berr(A, x2, b) <= 10 * n * EPS
+    np.testing.assert_allclose(x2, x, rtol=1e-9)
+    # without refinement: the reference's *32Mixed accuracy class for the transposed system
+    h = ls.Handle(ls._capi.MIXED)
+    h.set_option(ls._capi.OPT_REFINE_MAXIT, 0)
+    _, info = h.factor(A)
+    assert info == 0
+    x32 = h.solve(b, trans="T")
+    assert np.linalg.norm(x32 - xt) / np.linalg.norm(xt) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [1, 3, 16, 17, 32, 33, 50, 64])
+def test_batched_transposed_solve(gpu_required, ls, dtype, n):
+    rng = np.random.default_rng(70 + n)
+    batch = 19
+    A = (rng.random((batch, n, n)) + 0.5 * n * np.eye(n)).astype(dtype)    # [s, col, row]: matrix s is A[s].T
+    h = ls.Handle(ls._capi.F64 if dtype == np.float64 else ls._capi.F32)
+    _, info = h.factor_batched(A)
+    assert not info.any()
+    eps = np.finfo(dtype).eps
+    for nrhs in (1, 3):
+        b = rng.random((batch, nrhs, n)).astype(dtype)
+        xt = h.solve_batched(b, trans="T")
+        x = h.solve_batched(b)
+        for s in range(batch):
+            M = A[s].T.astype(np.float64)
+            for r in range(nrhs):
+                assert _berr(M.T, xt[s, r].astype(np.float64), b[s, r]) <= 10 * n * eps, (s, r)
+                assert _berr(M, x[s, r].astype(np.float64), b[s, r]) <= 10 * n * eps, (s, r)
+    # 'C' == 'T' for real element types; a bad trans is an argument error, not a crash
+    assert np.array_equal(h.solve_batched(b, trans="C"), xt)
+    with pytest.raises(ls.B200LUError):
+        h.solve_batched(b, trans="X")
+
+
+@pytest.mark.parametrize("sizes", [[2, 3, 4], [5, 64, 17, 33, 70, 16, 1], [3, 3, 3, 3], [40, 9, 130]])
+def test_ragged_blockdiagonal_one_launch_per_class(gpu_required, ls, oracle, sizes):
+    rng = np.random.default_rng(sum(sizes))
+    blocks = [rng.random((k, k)) + k * np.eye(k) for k in sizes]
+    A = ls.BlockDiagonal(blocks)
+    n = sum(sizes)
+    D = A.to_dense()
+    cache = ls.init(ls.LinearProblem(A, rng.random(n)), ls.B200LUFactorization())
+    before = ls.launch_count()
+    sol = ls.solve_(cache)
+    assert sol.retcode == ls.ReturnCode.Success
+    np.testing.assert_allclose(sol.u, np.linalg.solve(D, cache.b), rtol=1e-10)
+    plan = ls.plan_blockdiag(sizes)
+    assert len(cache.cacheval.groups) == len(plan) <= 3 + sum(k > 64 for k in sizes)
+    n_batched = sum(kind == "batched" for kind, *_ in plan)
+    if all(k <= 64 for k in sizes):
+        assert ls.launch_count() - before == 2 * n_batched     # one getrf + one getrs launch per class
+    # pivots of the padded systems are the pivots of the blocks themselves (LAPACK, up to ties)
+    for kind, h, idx, m in cache.cacheval.groups:
+        if kind != "batched":
+            continue
+        _, ipiv, info = h.get_factors_batched()
+        assert not info.any()
+        for s, i in enumerate(idx):
+            k = sizes[i]
+            _, ipiv_ref, _ = oracle.lapack_getrf(blocks[i])
+            assert oracle.compare_ipiv(blocks[i], ipiv[s, :k], ipiv_ref)[1] in ("exact", "tie")
+            assert np.array_equal(ipiv[s, k:], np.arange(k + 1, m + 1))
+    # matrix right-hand side, re-solve only
+    B = rng.random((n, 3))
+    cache.b = B
+    cache.u = np.zeros_like(B)
+    np.testing.assert_allclose(ls.solve_(cache).u, np.linalg.solve(D, B), rtol=1e-10)
+    # adjoint with the same per-block factors
+    sol = ls.solve_(cache, adjoint=True)
+    assert sol.retcode == ls.ReturnCode.Success and not cache.isfresh
+    np.testing.assert_allclose(sol.u, np.linalg.solve(D.T, B), rtol=1e-10)
+    # a singular block anywhere => Failure, isfresh stays set (retcode protocol, src/openblas.jl:362-459)
+    bad = [b.copy() for b in blocks]
+    bad[1][:, 0] = 0.0
+    cache.A = ls.BlockDiagonal(bad)
+    assert ls.solve_(cache).retcode == ls.ReturnCode.Failure and cache.isfresh

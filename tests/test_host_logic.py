@@ -146,6 +146,48 @@ def test_block_diagonal_container(ls):
     assert list(bd.offsets) == [0, 2, 5]
 
 
+def test_blockdiag_plan_classes(ls):
+    """ragged BlockDiagonal blocks (reference case [2, 3, 4], test/Core/basictests.jl:1168-1223, and the
+    variable-size supernode blocks of SURVEY 8(f)3): blocks <= 64 share the batched launch of their
+    kernel class, padded to its largest member; larger blocks go one by one; empty blocks vanish"""
+    assert ls.plan_blockdiag([3, 3, 3, 3]) == [("batched", [0, 1, 2, 3], 3)]
+    assert ls.plan_blockdiag([2, 3, 4]) == [("batched", [0, 1, 2], 4)]
+    plan = ls.plan_blockdiag([64, 5, 0, 70, 17, 33, 16, 32, 1000])
+    assert plan == [("batched", [1, 6], 16), ("batched", [4, 7], 32), ("batched", [0, 5], 64),
+                    ("single", [3], 70), ("single", [8], 1000)]
+    assert ls.plan_blockdiag([]) == [] and ls.plan_blockdiag([0, 0]) == []
+    # uniform sizes are never padded
+    assert ls.plan_blockdiag([64] * 7) == [("batched", list(range(7)), 64)]
+
+
+def test_blockdiag_padding_is_exact(ls, oracle):
+    """diag(B, I) has the pivots, info and leading factors of B itself, bit for bit, and solving it
+    with a zero-padded right-hand side gives B's solution — checked with the oracle's per-block
+    lu!/ldiv! restatement (ext/LinearSolveBlockDiagonalsExt.jl:119-125,183-205)"""
+    rng = np.random.default_rng(7)
+    sizes = [2, 3, 4, 7, 1, 4]
+    blocks = [rng.standard_normal((k, k)) for k in sizes]
+    blocks[3][:, 2] = 0.0                              # singular block: zero column 3 => info = 3
+    blocks[5] = np.eye(4)[[2, 0, 3, 1], :]             # permutation block
+    (kind, idx, m), = ls.plan_blockdiag(sizes)
+    assert kind == "batched" and m == 7
+    P = ls.pad_blocks(blocks, idx, m, np.float64)
+    assert P.shape == (6, 7, 7)
+    rhs = np.zeros((6, m))
+    for s, k in enumerate(sizes):
+        rhs[s, :k] = rng.random(k)
+    Fp, ipiv_p, info_p, x_p = oracle.ref_batched(P, rhs)
+    for s, k in enumerate(sizes):
+        Bs = np.ascontiguousarray(blocks[s].T)[None]   # [1, col, row]
+        F, ipiv, info, x = oracle.ref_batched(Bs, rhs[s:s + 1, :k].copy())
+        assert np.array_equal(ipiv_p[s, :k], ipiv[0]) and info_p[s] == info[0]
+        assert np.array_equal(Fp[s, :k, :k], F[0])
+        assert np.array_equal(ipiv_p[s, k:], np.arange(k + 1, m + 1))      # the padding never interchanges
+        if info[0] == 0:
+            assert np.array_equal(x_p[s, :k], x[0]) and not x_p[s, k:].any()
+    assert info_p[3] == 3 and not info_p[[0, 1, 2, 4, 5]].any()
+
+
 def test_bench_reference_arm_runs_on_cpu():
     import json
     import subprocess
