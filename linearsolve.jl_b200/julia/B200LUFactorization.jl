@@ -184,8 +184,11 @@ end
 
 # `solve!(cache; adjoint = true)` (src/common.jl:1012-1027) reuses the cached factorization:
 # the hooks of src/adjoint_factorization.jl:149-153.  Real element types: adjoint == transpose.
-_custom_can_reuse_adjoint_factorization(::B200LUFactorization, c::B200LUCache) = c.handle != C_NULL
-function _custom_adjoint_factorization_solve(alg::B200LUFactorization, c::B200LUCache, A, b)
+# The mixed-precision handle refines the TRANSPOSED system (FP32 transposed sweeps + FP64 residual
+# b - A'x), so both algorithms reuse their factors.
+const _B200LUAlgs = Union{B200LUFactorization, B200LU32MixedLUFactorization}
+_custom_can_reuse_adjoint_factorization(::_B200LUAlgs, c::B200LUCache) = c.handle != C_NULL
+function _custom_adjoint_factorization_solve(alg::_B200LUAlgs, c::B200LUCache, A, b)
     u = similar(b)
     return _direct_lu_solve!(c, u, b, alg; trans = 'T')
 end
@@ -222,21 +225,43 @@ function SciMLBase.solve!(
     )
 end
 
-# BlockDiagonal surface (ext/LinearSolveBlockDiagonalsExt.jl:119-125,183-205): equal
-# square blocks of size <= 64 go through ONE batched call.
+# BlockDiagonal surface (ext/LinearSolveBlockDiagonalsExt.jl:119-125,183-205).  Blocks of up to 64
+# rows go through ONE batched call per kernel class (<= 16, <= 32, <= 64 rows) however ragged their
+# sizes are: block B is embedded in the class's largest member size m as diag(B, I).  Partial
+# pivoting never looks at the padding (exact zeros below B, unit pivots after it), so ipiv[1:n],
+# info and the leading n x n factors are those of B itself (tests/test_host_logic.py::
+# test_blockdiag_padding_is_exact checks this bit for bit against the per-block lu!).  Larger
+# blocks take `_direct_lu_factorize!`, one cache each.  Python twin: interface.py::plan_blockdiag,
+# pad_blocks, _factor_blockdiag, _solve_blockdiag.
 function _b200lu_factor_blocks!(c::B200LUCache, blocks::Vector{Matrix{T}}, alg) where {T}
-    n = size(first(blocks), 1)
+    m = maximum(B -> size(B, 1), blocks)              # all blocks of one kernel class
     batch = length(blocks)
     _b200lu_ensure_handle!(c, alg)
-    packed = Array{T, 3}(undef, n, n, batch)          # column-major blocks back to back
+    packed = zeros(T, m, m, batch)                    # column-major systems back to back
     for (s, B) in enumerate(blocks)
-        copyto!(view(packed, :, :, s), B)
+        n = size(B, 1)
+        copyto!(view(packed, 1:n, 1:n, s), B)
+        for d in (n + 1):m
+            packed[d, d, s] = one(T)
+        end
     end
-    ipiv = Vector{BlasInt}(undef, n * batch)
+    ipiv = Vector{BlasInt}(undef, m * batch)
     info = Vector{BlasInt}(undef, batch)
     rc = ccall((:b200lu_factor_batched, libb200lu[]), Cint,
         (Ptr{Cvoid}, Int64, Int64, Ptr{T}, Int64, Int64, Ptr{BlasInt}, Ptr{BlasInt}),
-        c.handle, batch, n, packed, n, n * n, ipiv, info)
+        c.handle, batch, m, packed, m, m * m, ipiv, info)
     rc == 0 || _b200lu_error(c, rc)
+    c.n = m
     return all(iszero, info)                           # success = all(issuccess), :121-124
+end
+
+# per-block ldiv! on views of b (:183-205); rhs[:, :, s] is the zero-padded m x nrhs block of b that
+# belongs to system s.  trans = 'T': `solve!(cache; adjoint = true)` with the same factors.
+function _b200lu_solve_blocks!(c::B200LUCache, x::Array{T, 3}, rhs::Array{T, 3}; trans::Char = 'N') where {T}
+    m, nrhs, batch = size(rhs)
+    rc = ccall((:b200lu_solve_batched_trans, libb200lu[]), Cint,
+        (Ptr{Cvoid}, UInt8, Int64, Ptr{T}, Int64, Int64, Ptr{T}, Int64, Int64),
+        c.handle, UInt8(trans), nrhs, rhs, m, m * nrhs, x, m, m * nrhs)
+    rc == 0 || _b200lu_error(c, rc)
+    return x
 end
