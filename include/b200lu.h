@@ -188,7 +188,8 @@ int b200lu_get_ipiv(b200lu_handle* h, int64_t* ipiv_out);
 
 /*
  * Many independent small systems (BlockDiagonal surface): `batch` matrices of
- * n x n (n <= 64), matrix i at A + i*strideA elements, column-major with
+ * n x n (n <= 160: register kernels up to 64 rows, a shared-memory kernel above),
+ * matrix i at A + i*strideA elements, column-major with
  * leading dimension lda.  ipiv: batch*n (1-based), info: batch entries.
  * The factors stay on the device; solve_batched applies them to B
  * (n x nrhs per system, system i at B + i*strideB).

@@ -1832,7 +1832,17 @@ static int batched_factor_launch(b200lu_handle* h, const T* A, int64_t lda, int6
     const int64_t batch = h->b_batch;
     T* LU = (T*)h->dB_LU;
     cudaStream_t st = h->s_main;
-    if (n <= 16)
+    if (n > 64) {
+        // 65 ... BATCHED_SMEM_NMAX rows: the system lives in shared memory, one CTA each
+        const size_t smem = (size_t)n * (n | 1) * sizeof(T);
+        static bool attr_set = false;
+        if (!attr_set) {
+            CU_TRY(h, cudaFuncSetAttribute(getrf_batched_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)((size_t)BATCHED_SMEM_NMAX * (BATCHED_SMEM_NMAX | 1) * sizeof(T))));
+            attr_set = true;
+        }
+        getrf_batched_smem_kernel<T><<<(unsigned)batch, BATCHED_SMEM_NT, smem, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_perm, h->dB_info, n);
+    } else if (n <= 16)
         getrf_batched_kernel<T, 16><<<(unsigned)batch, 32, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_perm, h->dB_info, n);
     else if (n <= 32)
         getrf_batched_kernel<T, 32><<<(unsigned)batch, 32, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_perm, h->dB_info, n);
@@ -1853,6 +1863,16 @@ static int batched_solve_launch(b200lu_handle* h, int nrhs, const T* B, int64_t 
 #define GETRS_B(NMAXV, WPCV)                                                                      \
     {                                                                                             \
         const unsigned grid = (unsigned)((batch + (WPCV) - 1) / (WPCV));                           \
+        if ((NMAXV) > 64) {   /* more than 48 KB of dynamic shared memory: opt in once */          \
+            static bool attr_set = false;                                                         \
+            if (!attr_set) {                                                                      \
+                CU_TRY(h, cudaFuncSetAttribute(getrs_batched_kernel<T, NMAXV, WPCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)((size_t)(WPCV) * (NMAXV) * (NMAXV) * sizeof(T)))); \
+                CU_TRY(h, cudaFuncSetAttribute(getrs_batched_trans_kernel<T, NMAXV, WPCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)((size_t)(WPCV) * (NMAXV) * ((NMAXV) + 1) * sizeof(T)))); \
+                attr_set = true;                                                                  \
+            }                                                                                     \
+        }                                                                                         \
         if (trans) {                                                                              \
             const size_t smem = (size_t)(WPCV) * (NMAXV) * ((NMAXV) + 1) * sizeof(T);              \
             getrs_batched_trans_kernel<T, NMAXV, WPCV><<<grid, 32 * (WPCV), smem, st>>>(           \
@@ -1863,7 +1883,8 @@ static int batched_solve_launch(b200lu_handle* h, int nrhs, const T* B, int64_t 
                 LU, n, (int64_t)n * n, h->dB_perm, B, ldb, strideB, X, ldx, strideX, n, nrhs, batch); \
         }                                                                                         \
     }
-    if (n <= 16) GETRS_B(16, 8)
+    if (n > 64) GETRS_B(BATCHED_SMEM_NMAX, 1)
+    else if (n <= 16) GETRS_B(16, 8)
     else if (n <= 32) GETRS_B(32, 4)
     else if (sizeof(T) == 4) GETRS_B(64, 2)
     else GETRS_B(64, 1)
@@ -1879,7 +1900,7 @@ static int check_batched_args(b200lu_handle* h, int64_t batch, int64_t n, const 
     if (!h) return -1;
     if (h->dtype == B200LU_MIXED) return set_err(h, -1, "batched mode supports F64 and F32 handles");
     if (batch < 0) return set_err(h, -2, "batch < 0");
-    if (n < 0 || n > 64) return set_err(h, -3, "batched n must be in [0, 64]");
+    if (n < 0 || n > BATCHED_SMEM_NMAX) return set_err(h, -3, "batched n must be in [0, %d]", BATCHED_SMEM_NMAX);
     if (batch > 0 && n > 0) {
         if (!A) return set_err(h, -4, "A is NULL");
         if (lda < n) return set_err(h, -5, "lda < n");

@@ -1,4 +1,5 @@
-// batched.cuh — many independent small systems (n <= 64), the reference's
+// batched.cuh — many independent small systems (n <= 64 in registers, 65 ... 160 in shared memory,
+// see getrf_batched_smem_kernel at the end), the reference's
 // BlockDiagonal surface: per-block `lu!(B; check=false)` + per-block `ldiv!`
 // (ext/LinearSolveBlockDiagonalsExt.jl:119-125,183-205).  Pivot/info semantics
 // as src/blocked_lufact.jl:38-54,58-90.
@@ -318,6 +319,118 @@ __global__ void __launch_bounds__(32 * WPC) getrs_batched_trans_kernel(
         for (int r = 0; r < RPL; ++r)
             if (r * 32 + lane < n) X[sys * strideX + (long long)rhs * ldx + dst[r]] = b[r];
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Blocks of 65 ... BATCHED_SMEM_NMAX rows (variable-size BlockDiagonal / supernode blocks, SURVEY
+// 8(f)3): one CTA per system, the whole system in shared memory (column-major, odd leading
+// dimension), unblocked right-looking getrf with the same arithmetic contract as the register
+// kernel above — amax from 0 with strict '>', lowest row on ties (NaN never wins), kp = k and
+// info = k on an all-zero subcolumn with the rank-1 update still run, multipliers scaled by the
+// reciprocal of the pivot, FMA updates.  Three CTA barriers per column: after the pivot search,
+// after the row interchange, after the rank-1 update (which reads the UNSCALED column k; the scaled
+// multipliers are written behind that barrier by warp 0, and nothing reads them before the next
+// interchange, which sits behind the next search barrier).
+constexpr int BATCHED_SMEM_NMAX = 160;   // 160 x 161 FP64 words = 206,080 bytes of the 227 KB
+constexpr int BATCHED_SMEM_NT = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(BATCHED_SMEM_NT) getrf_batched_smem_kernel(
+    const T* __restrict__ A, long long lda, long long strideA, T* __restrict__ LU, long long ldlu,
+    long long strideLU, int* __restrict__ ipiv, int* __restrict__ perm, int* __restrict__ info, int n) {
+    constexpr int NT = BATCHED_SMEM_NT, NW = NT / 32, QMAX = (BATCHED_SMEM_NMAX + 31) / 32;
+    extern __shared__ __align__(16) unsigned char bsm_dyn[];
+    T* s = reinterpret_cast<T*>(bsm_dyn);
+    __shared__ T c_val[NW];
+    __shared__ int c_pos[NW];
+    __shared__ int s_perm[BATCHED_SMEM_NMAX];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long sys = blockIdx.x;
+    const int ld = n | 1;
+    const T* Ab = A + sys * strideA;
+    for (int i = tid; i < n * n; i += NT) {
+        const int c = i / n, r = i - c * n;
+        s[r + c * ld] = Ab[(long long)c * lda + r];
+    }
+    for (int i = tid; i < n; i += NT) s_perm[i] = i;
+    int myinfo = 0;   // thread 0
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        // 1. pivot search over rows k .. n-1 of column k (n - k <= 160 < NT rows: one per thread)
+        T v = T(0);
+        int pos = INT_MAX;
+        if (k + tid < n) {
+            v = tabs(s[k + tid + k * ld]);
+            pos = k + tid;
+            if (!(v > T(0))) { v = T(0); pos = INT_MAX; }   // zeros and NaNs are no candidates
+        }
+        const int wl = pcl_warp_argmax(v, pos);
+        if (lane == wl) { c_val[warp] = v; c_pos[warp] = pos; }
+        if (wl < 0 && lane == 0) { c_val[warp] = T(0); c_pos[warp] = INT_MAX; }
+        __syncthreads();
+        T bv = c_val[0];
+        int bp = c_pos[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) {
+            const T ov = c_val[w];
+            const int op = c_pos[w];
+            if (ov > bv || (ov == bv && op < bp)) { bv = ov; bp = op; }
+        }
+        const int piv = (bv > T(0)) ? bp : k;   // all-zero / all-NaN subcolumn: kp = k
+        // 2. interchange of rows k and piv over ALL columns (LAPACK: left and right of the panel)
+        if (piv != k) {
+            for (int c = tid; c < n; c += NT) {
+                const T x = s[k + c * ld];
+                s[k + c * ld] = s[piv + c * ld];
+                s[piv + c * ld] = x;
+            }
+        }
+        if (tid == 0) {
+            ipiv[sys * n + k] = piv;
+            if (piv != k) { const int x = s_perm[k]; s_perm[k] = s_perm[piv]; s_perm[piv] = x; }
+        }
+        __syncthreads();
+        const T pv = s[k + k * ld];
+        const bool scale = pv != T(0);
+        if (tid == 0 && !scale && myinfo == 0) myinfo = k + 1;
+        const T rinv = T(1) / pv;
+        // 3. rank-1 update of the trailing block: lane <-> row (mod 32), warp <-> column (mod NW)
+        T l[QMAX];
+#pragma unroll
+        for (int q = 0; q < QMAX; ++q) {
+            const int r = k + 1 + lane + 32 * q;
+            l[q] = T(0);
+            if (r < n) {
+                l[q] = s[r + k * ld];
+                if (scale) l[q] *= rinv;
+            }
+        }
+        for (int c = k + 1 + warp; c < n; c += NW) {
+            const T u = s[k + c * ld];
+#pragma unroll
+            for (int q = 0; q < QMAX; ++q) {
+                const int r = k + 1 + lane + 32 * q;
+                if (r < n) s[r + c * ld] = tfma(-l[q], u, s[r + c * ld]);
+            }
+        }
+        __syncthreads();
+        // 4. the scaled multipliers of column k
+        if (warp == 0) {
+#pragma unroll
+            for (int q = 0; q < QMAX; ++q) {
+                const int r = k + 1 + lane + 32 * q;
+                if (r < n) s[r + k * ld] = l[q];
+            }
+        }
+    }
+    __syncthreads();
+    T* Lb = LU + sys * strideLU;
+    for (int i = tid; i < n * n; i += NT) {
+        const int c = i / n, r = i - c * n;
+        Lb[(long long)c * ldlu + r] = s[r + c * ld];
+    }
+    for (int i = tid; i < n; i += NT) perm[sys * n + i] = s_perm[i];
+    if (tid == 0) info[sys] = myinfo;
 }
 
 }  // namespace b200lu

@@ -255,17 +255,18 @@ def _configure(handle, alg):
         handle.set_option(_capi.OPT_REFINE_MAXIT, alg.maxiters if alg.refine else 0)
 
 
-# kernel classes of the batched getrf/getrs (template NMAX in csrc/batched.cuh); larger blocks take
-# the single-system path, one handle each
-_BATCHED_CLASSES = (16, 32, 64)
+# size classes of the batched getrf/getrs: up to 64 rows the register kernels (template NMAX in
+# csrc/batched.cuh), 65 ... 160 rows the shared-memory kernel (any n, classes only bound the padding);
+# larger blocks take the single-system path, one handle each
+_BATCHED_CLASSES = (16, 32, 64, 96, 128, 160)
 
 
 def plan_blockdiag(sizes):
     """Launch plan for a BlockDiagonal with blocks of `sizes` (ragged allowed, the reference's
     `[2, 3, 4]` case and the variable-size supernode blocks of SURVEY §8(f)3): every block of up
-    to 64 rows joins the batched launch of its kernel class, embedded in the class's largest
-    member size m as diag(B, I) — at most three launches however ragged the sizes are; blocks
-    above 64 are factored one by one.  Returns [(kind, block indices, m)], kind in
+    to 160 rows joins the batched launch of its size class, embedded in the class's largest
+    member size m as diag(B, I) — at most six launches however ragged the sizes are; blocks
+    above 160 are factored one by one.  Returns [(kind, block indices, m)], kind in
     {"batched", "single"}; empty blocks appear nowhere."""
     by_class = {}
     singles = []

@@ -225,8 +225,8 @@ function SciMLBase.solve!(
     )
 end
 
-# BlockDiagonal surface (ext/LinearSolveBlockDiagonalsExt.jl:119-125,183-205).  Blocks of up to 64
-# rows go through ONE batched call per kernel class (<= 16, <= 32, <= 64 rows) however ragged their
+# BlockDiagonal surface (ext/LinearSolveBlockDiagonalsExt.jl:119-125,183-205).  Blocks of up to 160
+# rows go through ONE batched call per size class (<= 16, 32, 64, 96, 128, 160 rows) however ragged their
 # sizes are: block B is embedded in the class's largest member size m as diag(B, I).  Partial
 # pivoting never looks at the padding (exact zeros below B, unit pivots after it), so ipiv[1:n],
 # info and the leading n x n factors are those of B itself (tests/test_host_logic.py::

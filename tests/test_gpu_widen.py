@@ -73,7 +73,7 @@ def test_batched_transposed_solve(gpu_required, ls, dtype, n):
         h.solve_batched(b, trans="X")
 
 
-@pytest.mark.parametrize("sizes", [[2, 3, 4], [5, 64, 17, 33, 70, 16, 1], [3, 3, 3, 3], [40, 9, 130]])
+@pytest.mark.parametrize("sizes", [[2, 3, 4], [5, 64, 17, 33, 70, 16, 1], [3, 3, 3, 3], [40, 9, 130], [100, 161, 97, 300]])
 def test_ragged_blockdiagonal_one_launch_per_class(gpu_required, ls, oracle, sizes):
     rng = np.random.default_rng(sum(sizes))
     blocks = [rng.random((k, k)) + k * np.eye(k) for k in sizes]
@@ -86,9 +86,9 @@ def test_ragged_blockdiagonal_one_launch_per_class(gpu_required, ls, oracle, siz
     assert sol.retcode == ls.ReturnCode.Success
     np.testing.assert_allclose(sol.u, np.linalg.solve(D, cache.b), rtol=1e-10)
     plan = ls.plan_blockdiag(sizes)
-    assert len(cache.cacheval.groups) == len(plan) <= 3 + sum(k > 64 for k in sizes)
+    assert len(cache.cacheval.groups) == len(plan) <= 6 + sum(k > 160 for k in sizes)
     n_batched = sum(kind == "batched" for kind, *_ in plan)
-    if all(k <= 64 for k in sizes):
+    if all(k <= 160 for k in sizes):
         assert ls.launch_count() - before == 2 * n_batched     # one getrf + one getrs launch per class
     # pivots of the padded systems are the pivots of the blocks themselves (LAPACK, up to ties)
     for kind, h, idx, m in cache.cacheval.groups:
@@ -115,3 +115,48 @@ def test_ragged_blockdiagonal_one_launch_per_class(gpu_required, ls, oracle, siz
     bad[1][:, 0] = 0.0
     cache.A = ls.BlockDiagonal(bad)
     assert ls.solve_(cache).retcode == ls.ReturnCode.Failure and cache.isfresh
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [65, 70, 96, 100, 128, 131, 159, 160])
+def test_batched_shared_memory_class(gpu_required, ls, oracle, dtype, n):
+    """blocks of 65 ... 160 rows: one CTA per system with the system in shared memory — the same
+    parity bar as the register kernels (tests/test_gpu_batched.py): pivots equal to LAPACK's up to
+    ties, info, scaled residual < 20, backward error <= 10 n eps, transposed solves"""
+    rng = np.random.default_rng(1000 + n)
+    batch = 11
+    A = rng.random((batch, n, n)).astype(dtype)                  # [s, col, row]
+    A[3] = ls.pad_blocks([np.eye(n)[rng.permutation(n), :]], [0], n, dtype)[0]   # a permutation matrix
+    A[5].T[:, 6] = 0.0                                           # zero column 7 => info of LAPACK
+    A[7] = 0.0                                                   # zero matrix => info 1
+    h = ls.Handle(ls._capi.F64 if dtype == np.float64 else ls._capi.F32)
+    ipiv, info = h.factor_batched(A)
+    LU, ipiv2, info2 = h.get_factors_batched()
+    assert np.array_equal(ipiv, ipiv2) and np.array_equal(info, info2)
+    eps = np.finfo(dtype).eps
+    for s in range(batch):
+        M = np.asfortranarray(A[s].T)
+        lu_ref, ipiv_ref, info_ref = oracle.lapack_getrf(M)
+        assert info[s] == info_ref, s
+        if s == 7:
+            assert info[s] == 1 and np.array_equal(ipiv[s], np.arange(1, n + 1))
+            continue
+        if s == 5:
+            assert info[s] == 7 and np.array_equal(ipiv[s, :6], ipiv_ref[:6])
+            continue
+        assert oracle.compare_ipiv(M, ipiv[s], ipiv_ref)[1] in ("exact", "tie"), s
+        if s == 3:
+            assert np.array_equal(ipiv[s], ipiv_ref) and np.array_equal(LU[s].T, lu_ref)
+        assert oracle.scaled_residual(M, LU[s].T, ipiv[s]) < 20
+    # solves on a non-singular batch
+    A = (rng.random((batch, n, n)) + 0.25 * n * np.eye(n)).astype(dtype)
+    _, info = h.factor_batched(A)
+    assert not info.any()
+    b = rng.random((batch, 2, n)).astype(dtype)
+    x = h.solve_batched(b)
+    xt = h.solve_batched(b, trans="T")
+    for s in range(batch):
+        M = A[s].T.astype(np.float64)
+        for r in range(2):
+            assert _berr(M, x[s, r].astype(np.float64), b[s, r]) <= 10 * n * eps, (s, r)
+            assert _berr(M.T, xt[s, r].astype(np.float64), b[s, r]) <= 10 * n * eps, (s, r)

@@ -148,13 +148,13 @@ def test_block_diagonal_container(ls):
 
 def test_blockdiag_plan_classes(ls):
     """ragged BlockDiagonal blocks (reference case [2, 3, 4], test/Core/basictests.jl:1168-1223, and the
-    variable-size supernode blocks of SURVEY 8(f)3): blocks <= 64 share the batched launch of their
-    kernel class, padded to its largest member; larger blocks go one by one; empty blocks vanish"""
+    variable-size supernode blocks of SURVEY 8(f)3): blocks <= 160 share the batched launch of their
+    size class, padded to its largest member; blocks above 160 rows go one by one; empty blocks vanish"""
     assert ls.plan_blockdiag([3, 3, 3, 3]) == [("batched", [0, 1, 2, 3], 3)]
     assert ls.plan_blockdiag([2, 3, 4]) == [("batched", [0, 1, 2], 4)]
-    plan = ls.plan_blockdiag([64, 5, 0, 70, 17, 33, 16, 32, 1000])
+    plan = ls.plan_blockdiag([64, 5, 0, 70, 17, 33, 16, 32, 1000, 96, 130, 161])
     assert plan == [("batched", [1, 6], 16), ("batched", [4, 7], 32), ("batched", [0, 5], 64),
-                    ("single", [3], 70), ("single", [8], 1000)]
+                    ("batched", [3, 9], 96), ("batched", [10], 130), ("single", [8], 1000), ("single", [11], 161)]
     assert ls.plan_blockdiag([]) == [] and ls.plan_blockdiag([0, 0]) == []
     # uniform sizes are never padded
     assert ls.plan_blockdiag([64] * 7) == [("batched", list(range(7)), 64)]
