@@ -119,7 +119,12 @@ enum {
                                    1 (default) = b and x travel through a page-locked, device-mapped
                                    staging buffer that the getrs kernels read and write directly over
                                    PCIe (no copy-engine launches); 0 = H2D / D2H copies             */
-    B200LU_OPT_COUNT = 13
+    B200LU_OPT_KEEP_A = 13,     /* 1 = b200lu_factor / b200lu_factor_device keep a device copy of A (F64/F32 handles;
+                                   +n^2 elements of HBM, one device-to-device copy, and the host upload
+                                   is no longer streamed under the factorization) so that
+                                   b200lu_residual_norms can check a solution on the device; default 0.
+                                   MIXED handles always hold A in FP64.                              */
+    B200LU_OPT_COUNT = 14
 };
 
 /* library/ABI version: major*10000 + minor*100 + patch */
@@ -180,6 +185,16 @@ int b200lu_factor_device(b200lu_handle* h, int64_t n, const void* A_dev, int64_t
                          int64_t* info);
 int b200lu_solve_device(b200lu_handle* h, char trans, int64_t nrhs,
                         const void* B_dev, int64_t ldb, void* X_dev, int64_t ldx);
+
+/*
+ * The a-posteriori residual check of the reference (`_check_residual_safety`,
+ * src/factorization.jl:127-156: ||A u - b|| <= abstol + reltol ||b||) on the device:
+ * resid_out[c] = ||B[:, c] - A X[:, c]||_2 and bnorm_out[c] = ||B[:, c]||_2, accumulated
+ * in FP64, for host B and X (n x nrhs, interface element type).  Needs the matrix itself:
+ * B200LU_OPT_KEEP_A switched on at factor time for F64/F32 handles (status 3 otherwise).
+ */
+int b200lu_residual_norms(b200lu_handle* h, int64_t nrhs, const void* B_host, int64_t ldb,
+                          const void* X_host, int64_t ldx, double* resid_out, double* bnorm_out);
 
 /* Copy factors (L\U packed like LAPACK) / pivots of the cached factorization
  * to the host: parity tests, adjoint reuse (src/adjoint_factorization.jl). */

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libb200lu.so")
 
 F64, F32, MIXED = 0, 1, 2
 T_H2D, T_FACTOR, T_SOLVE, T_D2H, T_GEMM = range(5)
-OPT_NB, OPT_LOOKAHEAD, OPT_REFINE_MAXIT, OPT_PANEL_CTAS, OPT_SOLVE_NRHS_TILE, OPT_PROFILE, OPT_PANEL_RPT, OPT_GEMM_CFG, OPT_PANEL_MODE, OPT_SGEMM_MODE, OPT_TRSV_MODE, OPT_STREAM_H2D, OPT_MAPPED_RHS = range(13)
+OPT_NB, OPT_LOOKAHEAD, OPT_REFINE_MAXIT, OPT_PANEL_CTAS, OPT_SOLVE_NRHS_TILE, OPT_PROFILE, OPT_PANEL_RPT, OPT_GEMM_CFG, OPT_PANEL_MODE, OPT_SGEMM_MODE, OPT_TRSV_MODE, OPT_STREAM_H2D, OPT_MAPPED_RHS, OPT_KEEP_A = range(14)
 C_GEMM_FLOPS, C_GEMM_LAUNCHES, C_REFINE_ITERS = range(3)
 PEAK_FP64_DMMA, PEAK_FP64_DFMA, PEAK_HBM_COPY = range(3)
 
@@ -28,7 +28,7 @@ SYMBOLS = [
     "b200lu_last_error", "b200lu_last_timing", "b200lu_last_counter", "b200lu_probe_peak", "b200lu_debug_gemm_sub",
     "b200lu_set_option", "b200lu_get_option",
     "b200lu_factor", "b200lu_solve", "b200lu_factor_device", "b200lu_solve_device",
-    "b200lu_get_factors", "b200lu_get_ipiv",
+    "b200lu_get_factors", "b200lu_get_ipiv", "b200lu_residual_norms",
     "b200lu_factor_batched", "b200lu_solve_batched", "b200lu_factor_batched_device",
     "b200lu_solve_batched_device", "b200lu_get_factors_batched",
     "b200lu_solve_batched_trans", "b200lu_solve_batched_trans_device",
@@ -75,6 +75,7 @@ def load():
     P("b200lu_solve", ci, [vp, ctypes.c_char, i64, vp, i64, vp, i64])
     P("b200lu_factor_device", ci, [vp, i64, vp, i64, pi64])
     P("b200lu_solve_device", ci, [vp, ctypes.c_char, i64, vp, i64, vp, i64])
+    P("b200lu_residual_norms", ci, [vp, i64, vp, i64, vp, i64, vp, vp])
     P("b200lu_get_factors", ci, [vp, vp, i64])
     P("b200lu_get_ipiv", ci, [vp, vp])
     P("b200lu_factor_batched", ci, [vp, i64, i64, vp, i64, i64, vp, vp])
@@ -205,6 +206,22 @@ class Handle:
         rc = self.lib.b200lu_solve(self._h, trans.encode(), nrhs, Bm.ctypes.data, ld, X.ctypes.data, ld)
         self._check(rc)
         return X[:, 0] if vec else X
+
+    def residual_norms(self, B, X):
+        """(||B[:, c] - A X[:, c]||_2, ||B[:, c]||_2) per column, computed on the device with the copy of
+        A kept by OPT_KEEP_A (or the FP64 copy of a MIXED handle)."""
+        B, X = np.asarray(B), np.asarray(X)
+        if B.dtype != self.np_dtype or X.dtype != self.np_dtype:
+            raise TypeError(f"expected {self.np_dtype}, got {B.dtype} / {X.dtype}")
+        Bm = np.asfortranarray(B.reshape(self.n, -1, order="F"))
+        Xm = np.asfortranarray(X.reshape(self.n, -1, order="F"))
+        nrhs = Bm.shape[1]
+        resid = np.zeros(nrhs)
+        bnorm = np.zeros(nrhs)
+        ld = max(1, self.n)
+        self._check(self.lib.b200lu_residual_norms(self._h, nrhs, Bm.ctypes.data, ld, Xm.ctypes.data, ld,
+                                                   resid.ctypes.data, bnorm.ctypes.data))
+        return resid, bnorm
 
     def get_factors(self):
         LU = np.zeros((self.n, self.n), dtype=self.factor_dtype, order="F")

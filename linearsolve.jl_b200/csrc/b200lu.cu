@@ -54,6 +54,9 @@ struct b200lu_handle {
     int64_t n = 0, ldd = 0, cap_n = 0, cap_meta = 0;
     void* dA = nullptr;        // factors (double for F64, float for F32/MIXED)
     double* dA64 = nullptr;    // MIXED: FP64 copy of A for residuals
+    void* dA_keep = nullptr;   // B200LU_OPT_KEEP_A: copy of A in the interface type, for b200lu_residual_norms
+    int64_t cap_keep = 0;      // bytes
+    bool keep_valid = false;
     int* d_ipiv = nullptr;
     int* d_perm = nullptr;
     int* d_info = nullptr;
@@ -1314,6 +1317,7 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     h->opt[B200LU_OPT_TRSV_MODE] = 0;
     h->opt[B200LU_OPT_STREAM_H2D] = 1;
     h->opt[B200LU_OPT_MAPPED_RHS] = 1;
+    h->opt[B200LU_OPT_KEEP_A] = 0;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) == cudaSuccess;
@@ -1376,6 +1380,7 @@ void b200lu_destroy(b200lu_handle* h) {
     free_dev(h->d_info); free_dev(h->d_deverr); free_dev(h->d_plans); free_dev(h->d_panelsync); free_dev(h->d_split);
     free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_wL); free_dev(h->d_wU); free_dev(h->d_wLt); free_dev(h->d_wUt); free_dev(h->d_tflags); free_dev(h->d_tticket); free_dev(h->d_t2items); free_dev(h->d_t2x); free_dev(h->d_t2p); free_dev(h->d_t2ticket);
     free_dev(h->d_t3items); free_dev(h->d_t3x); free_dev(h->d_t3p); free_dev(h->d_t3ticket);
+    free_dev(h->dA_keep);
     free_dev(h->d_B); free_dev(h->d_X); free_dev(h->d_r); free_dev(h->d_r32); free_dev(h->d_scal); free_dev(h->d_cscal);
     if (h->h_cscal) cudaFreeHost(h->h_cscal);
     free_dev(h->dB_LU); free_dev(h->dB_ipiv); free_dev(h->dB_info); free_dev(h->dB_perm); free_dev(h->dB_in);
@@ -1494,12 +1499,32 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_TRSV_MODE && (value < 0 || value > 3)) return -3;
     if (option == B200LU_OPT_STREAM_H2D && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_MAPPED_RHS && (value < 0 || value > 1)) return -3;
+    if (option == B200LU_OPT_KEEP_A && (value < 0 || value > 1)) return -3;
     h->opt[option] = value;
     return 0;
 }
 int64_t b200lu_get_option(const b200lu_handle* h, int option) {
     if (!h || option < 0 || option >= B200LU_OPT_COUNT) return -1;
     return h->opt[option];
+}
+
+// B200LU_OPT_KEEP_A: a device copy of A (same layout as dA) taken before the factorization
+// overwrites it, so that the residual check of src/factorization.jl:127-156 can run on the device
+// (b200lu_residual_norms).  MIXED handles keep A in dA64 anyway.
+static int keep_copy_of_A(b200lu_handle* h, int64_t n) {
+    h->keep_valid = false;
+    if (!h->opt[B200LU_OPT_KEEP_A] || h->dtype == B200LU_MIXED) return 0;
+    const int64_t need = h->ldd * n * (int64_t)elem_size(h);
+    if (need > h->cap_keep) {
+        CU_TRY(h, cudaStreamSynchronize(h->s_main));
+        free_dev(h->dA_keep);
+        h->cap_keep = 0;
+        CU_TRY(h, cudaMalloc(&h->dA_keep, (size_t)need));
+        h->cap_keep = need;
+    }
+    CU_TRY(h, cudaMemcpyAsync(h->dA_keep, h->dA, (size_t)need, cudaMemcpyDeviceToDevice, h->s_main));
+    h->keep_valid = true;
+    return 0;
 }
 
 // factor whatever already sits in h->dA (and dA64 for MIXED)
@@ -1575,7 +1600,8 @@ int b200lu_factor(b200lu_handle* h, int64_t n, const void* A_host, int64_t lda, 
     // streamed upload: column chunks on the copy stream, the factorization starts under them
     const int nb = (int)h->opt[B200LU_OPT_NB];
     int nchunks = 0;
-    if (h->opt[B200LU_OPT_STREAM_H2D] && h->opt[B200LU_OPT_LOOKAHEAD] && h->dtype != B200LU_MIXED && n >= 2048) {
+    if (h->opt[B200LU_OPT_STREAM_H2D] && h->opt[B200LU_OPT_LOOKAHEAD] && h->dtype != B200LU_MIXED && n >= 2048 &&
+        !h->opt[B200LU_OPT_KEEP_A]) {   // the kept copy is taken from the complete upload
         static const int want = getenv("B200LU_H2D_CHUNKS") ? std::max(2, atoi(getenv("B200LU_H2D_CHUNKS"))) : 8;
         const int cw = cdiv(cdiv((int)n, want), nb) * nb;
         const int first = std::min(cw, 2 * nb);   // a short first chunk: the first panel starts early
@@ -1604,6 +1630,8 @@ int b200lu_factor(b200lu_handle* h, int64_t n, const void* A_host, int64_t lda, 
     if (nchunks == 0)
         CU_TRY(h, cudaMemcpy2DAsync(dst, (size_t)h->ldd * is, A_host, (size_t)lda * is, (size_t)n * is,
                                     (size_t)n, cudaMemcpyHostToDevice, h->s_main));
+    rc = keep_copy_of_A(h, n);
+    if (rc) return rc;
     rc = factor_resident(h, n, info, nchunks);
     if (rc) {
         if (nchunks) cudaStreamSynchronize(h->s_copy);   // the caller's buffer must not be read after we return
@@ -1635,6 +1663,8 @@ int b200lu_factor_device(b200lu_handle* h, int64_t n, const void* A_dev, int64_t
     if (A_dev != dst)
         CU_TRY(h, cudaMemcpy2DAsync(dst, (size_t)h->ldd * is, A_dev, (size_t)lda * is, (size_t)n * is,
                                     (size_t)n, cudaMemcpyDeviceToDevice, h->s_main));
+    rc = keep_copy_of_A(h, n);
+    if (rc) return rc;
     rc = factor_resident(h, n, info);
     if (rc) return rc;
     float ms = 0.f;
@@ -1756,6 +1786,95 @@ int b200lu_solve(b200lu_handle* h, char trans, int64_t nrhs, const void* B_host,
     CU_TRY(h, cudaEventRecord(h->ev_d, h->s_main));
     rc = finish_solve(h);
     if (rc) return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_a, h->ev_b); h->timing[B200LU_T_H2D] = ms;
+    cudaEventElapsedTime(&ms, h->ev_b, h->ev_c); h->timing[B200LU_T_SOLVE] = ms;
+    cudaEventElapsedTime(&ms, h->ev_c, h->ev_d); h->timing[B200LU_T_D2H] = ms;
+    return 0;
+}
+
+// Residual norms on the device: resid[c] = ||B[:, c] - A X[:, c]||_2 and bnorm[c] = ||B[:, c]||_2 in FP64,
+// with the copy of A kept by B200LU_OPT_KEEP_A (F64/F32) or the FP64 copy of the MIXED handle.
+int b200lu_residual_norms(b200lu_handle* h, int64_t nrhs, const void* B_host, int64_t ldb,
+                          const void* X_host, int64_t ldx, double* resid_out, double* bnorm_out) {
+    if (!h) return -1;
+    if (nrhs < 0) return set_err(h, -2, "nrhs < 0");
+    if (!h->factored) return set_err(h, 3, "no factorization cached");
+    const bool have_A = (h->dtype == B200LU_MIXED) ? (h->dA64 != nullptr) : h->keep_valid;
+    if (!have_A) return set_err(h, 3, "no copy of A on the device: set B200LU_OPT_KEEP_A = 1 before b200lu_factor");
+    const int64_t n = h->n;
+    if (n > 0 && nrhs > 0) {
+        if (!B_host) return set_err(h, -3, "B is NULL");
+        if (ldb < n) return set_err(h, -4, "ldb < n");
+        if (!X_host) return set_err(h, -5, "X is NULL");
+        if (ldx < n) return set_err(h, -6, "ldx < n");
+        if (!resid_out || !bnorm_out) return set_err(h, -7, "output is NULL");
+    }
+    if (nrhs == 0) return 0;
+    if (n == 0) {
+        for (int64_t c = 0; c < nrhs; ++c) resid_out[c] = bnorm_out[c] = 0.0;
+        return 0;
+    }
+    CU_TRY(h, cudaSetDevice(h->dev));
+    cudaStream_t st = h->s_main;
+    int rc = ensure_rhs(h, 2 * nrhs + 2);
+    if (rc) return rc;
+    if (nrhs > h->cap_cscal) {
+        CU_TRY(h, cudaStreamSynchronize(st));
+        free_dev(h->d_cscal);
+        if (h->h_cscal) cudaFreeHost(h->h_cscal);
+        h->h_cscal = nullptr;
+        h->cap_cscal = 0;
+        CU_TRY(h, cudaMalloc((void**)&h->d_cscal, (size_t)2 * nrhs * sizeof(double)));
+        CU_TRY(h, cudaMallocHost((void**)&h->h_cscal, (size_t)2 * nrhs * sizeof(double)));
+        h->cap_cscal = (int)nrhs;
+    }
+    const size_t is = iface_size(h);
+    // interface-typed staging in the upper halves of d_B / d_X, FP64 working copies R (= B, then the
+    // residual) and X64 in the lower halves
+    char* dBs = (char*)h->d_B + (size_t)h->cap_n * (nrhs + 1) * 8;
+    char* dXs = (char*)h->d_X + (size_t)h->cap_n * (nrhs + 1) * 8;
+    double* R = (double*)h->d_B;
+    double* X64 = (double*)h->d_X;
+    CU_TRY(h, cudaEventRecord(h->ev_a, st));
+    CU_TRY(h, cudaMemcpy2DAsync(dBs, (size_t)n * is, B_host, (size_t)ldb * is, (size_t)n * is, (size_t)nrhs, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaMemcpy2DAsync(dXs, (size_t)n * is, X_host, (size_t)ldx * is, (size_t)n * is, (size_t)nrhs, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaEventRecord(h->ev_b, st));
+    const dim3 g2(cdiv(n, 256), (unsigned)nrhs);
+    if (h->dtype == B200LU_F32) {
+        cast2d_kernel<float, double><<<g2, 256, 0, st>>>((const float*)dBs, n, R, n, (int)n, (int)nrhs);
+        LAUNCH_CHECK(h);
+        cast2d_kernel<float, double><<<g2, 256, 0, st>>>((const float*)dXs, n, X64, n, (int)n, (int)nrhs);
+        LAUNCH_CHECK(h);
+    } else {
+        CU_TRY(h, cudaMemcpyAsync(R, dBs, (size_t)n * nrhs * 8, cudaMemcpyDeviceToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(X64, dXs, (size_t)n * nrhs * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    CU_TRY(h, cudaMemsetAsync(h->d_cscal, 0, (size_t)2 * nrhs * sizeof(double), st));
+    const dim3 gn(std::min(cdiv(n, 256), 64), (unsigned)nrhs);
+    colsumsq_kernel<<<gn, 256, 0, st>>>(R, n, (int)n, h->d_cscal + nrhs);     // ||b||^2 before R becomes the residual
+    LAUNCH_CHECK(h);
+    const int cchunk = 512;
+    for (int64_t c = 0; c < nrhs; ++c) {
+        const dim3 gr(cdiv(n, 256), cdiv(n, cchunk));
+        if (h->dtype == B200LU_F64)
+            residual_gemv_kernel<double><<<gr, 256, 0, st>>>((const double*)h->dA_keep, h->ldd, (int)n, X64 + c * n, R + c * n, cchunk);
+        else if (h->dtype == B200LU_F32)
+            residual_gemv_kernel<float><<<gr, 256, 0, st>>>((const float*)h->dA_keep, h->ldd, (int)n, X64 + c * n, R + c * n, cchunk);
+        else
+            residual_gemv_kernel<double><<<gr, 256, 0, st>>>(h->dA64, h->ldd, (int)n, X64 + c * n, R + c * n, cchunk);
+        LAUNCH_CHECK(h);
+    }
+    colsumsq_kernel<<<gn, 256, 0, st>>>(R, n, (int)n, h->d_cscal);
+    LAUNCH_CHECK(h);
+    CU_TRY(h, cudaEventRecord(h->ev_c, st));
+    CU_TRY(h, cudaMemcpyAsync(h->h_cscal, h->d_cscal, (size_t)2 * nrhs * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaEventRecord(h->ev_d, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    for (int64_t c = 0; c < nrhs; ++c) {
+        resid_out[c] = sqrt(h->h_cscal[c]);
+        bnorm_out[c] = sqrt(h->h_cscal[nrhs + c]);
+    }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev_a, h->ev_b); h->timing[B200LU_T_H2D] = ms;
     cudaEventElapsedTime(&ms, h->ev_b, h->ev_c); h->timing[B200LU_T_SOLVE] = ms;

@@ -253,6 +253,8 @@ def _configure(handle, alg):
         handle.set_option(_capi.OPT_LOOKAHEAD, int(alg.lookahead))
     if isinstance(alg, B200LU32MixedLUFactorization):
         handle.set_option(_capi.OPT_REFINE_MAXIT, alg.maxiters if alg.refine else 0)
+    elif alg.residualsafety:
+        handle.set_option(_capi.OPT_KEEP_A, 1)    # the residual check runs on the device
 
 
 # size classes of the batched getrf/getrs: up to 64 rows the register kernels (template NMAX in
@@ -354,10 +356,22 @@ def _solve_blockdiag(cache, adjoint=False):
 
 
 def _check_residual_safety(cache, A_original, u):
-    """a-posteriori check ‖A u − b‖ <= abstol + reltol‖b‖ (src/factorization.jl:127-156)"""
-    Ad = A_original.to_dense() if isinstance(A_original, BlockDiagonal) else A_original
-    r = Ad @ u - cache.b
-    return np.linalg.norm(r) <= cache.abstol + cache.reltol * np.linalg.norm(cache.b)
+    """a-posteriori check ‖A u − b‖ <= abstol + reltol‖b‖ (src/factorization.jl:127-156).  Dense
+    problems: the norms come from the device (b200lu_residual_norms on the copy of A the handle
+    kept); BlockDiagonal problems: block by block on the host (O(sum n_i^2) work on data the host
+    already holds)."""
+    b = np.asarray(cache.b)
+    if isinstance(A_original, BlockDiagonal):
+        r = u.copy()
+        for B, o in zip(A_original.blocks, A_original.offsets[:-1]):
+            k = B.shape[0]
+            r[o:o + k] = B @ u[o:o + k]
+        rn, bn = np.linalg.norm(r - b), np.linalg.norm(b)
+    else:
+        dt = cache.cacheval.handle.np_dtype
+        resid, bnorm = cache.cacheval.handle.residual_norms(b.astype(dt, copy=False), np.asarray(u, dtype=dt))
+        rn, bn = np.sqrt(np.sum(resid ** 2)), np.sqrt(np.sum(bnorm ** 2))    # Frobenius over the columns
+    return rn <= cache.abstol + cache.reltol * bn
 
 
 def solve_(cache: LinearCache, alg=None, adjoint: bool = False) -> LinearSolution:

@@ -160,3 +160,63 @@ def test_batched_shared_memory_class(gpu_required, ls, oracle, dtype, n):
         for r in range(2):
             assert _berr(M, x[s, r].astype(np.float64), b[s, r]) <= 10 * n * eps, (s, r)
             assert _berr(M.T, xt[s, r].astype(np.float64), b[s, r]) <= 10 * n * eps, (s, r)
+
+
+@pytest.mark.parametrize("dtype,n,nrhs", [(np.float64, 64, 1), (np.float64, 777, 3), (np.float64, 3000, 2),
+                                          (np.float32, 500, 2)])
+def test_device_residual_norms(gpu_required, ls, dtype, n, nrhs):
+    """b200lu_residual_norms: the reference's a-posteriori check (`_check_residual_safety`,
+    src/factorization.jl:127-156) with the norms accumulated in FP64 on the device from the copy of
+    A kept by B200LU_OPT_KEEP_A"""
+    rng = np.random.default_rng(5000 + n)
+    A = np.asfortranarray((rng.random((n, n)) + 0.1 * n * np.eye(n)).astype(dtype))
+    B = np.asfortranarray(rng.random((n, nrhs)).astype(dtype))
+    code = ls._capi.F64 if dtype == np.float64 else ls._capi.F32
+    h = ls.Handle(code)
+    h.set_option(ls._capi.OPT_KEEP_A, 1)
+    ipiv, info = h.factor(A)
+    assert info == 0
+    X = h.solve(B)
+    A64, B64 = A.astype(np.float64), B.astype(np.float64)
+    resid, bnorm = h.residual_norms(B, X)
+    np.testing.assert_allclose(bnorm, np.linalg.norm(B64, axis=0), rtol=1e-12)
+    eps = np.finfo(dtype).eps
+    assert np.all(resid <= 10 * n * eps * np.linalg.norm(A64) * np.linalg.norm(X.astype(np.float64), axis=0))
+    # a perturbed "solution": the residual is well above rounding and must match the host value
+    X2 = (X + 1e-2 * rng.random(X.shape)).astype(dtype)
+    resid2, _ = h.residual_norms(B, X2)
+    np.testing.assert_allclose(resid2, np.linalg.norm(A64 @ X2.astype(np.float64) - B64, axis=0), rtol=1e-9)
+    # keeping A bypasses the streamed upload, not the arithmetic: same pivots as a default handle,
+    # which in turn refuses the check (no copy of A on the device)
+    h2 = ls.Handle(code)
+    ipiv2, _ = h2.factor(A)
+    assert np.array_equal(ipiv, ipiv2)
+    with pytest.raises(ls.B200LUError):
+        h2.residual_norms(B, X)
+    # a refactorization with the option switched off invalidates the kept copy
+    h.set_option(ls._capi.OPT_KEEP_A, 0)
+    h.factor(A)
+    with pytest.raises(ls.B200LUError):
+        h.residual_norms(B, X)
+
+
+def test_residualsafety_on_device(gpu_required, ls):
+    rng = np.random.default_rng(11)
+    n = 1200
+    A = rng.random((n, n)) + n * np.eye(n)
+    for b in (rng.random(n), rng.random((n, 4))):
+        for alg in (ls.B200LUFactorization(residualsafety=True), ls.B200LU32MixedLUFactorization(residualsafety=True)):
+            cache = ls.init(ls.LinearProblem(A, b), alg)
+            sol = ls.solve_(cache)
+            assert sol.retcode == ls.ReturnCode.Success
+            assert np.linalg.norm(A @ sol.u - b) <= cache.abstol + cache.reltol * np.linalg.norm(b)
+            if not isinstance(alg, ls.B200LU32MixedLUFactorization):
+                assert cache.cacheval.handle.get_option(ls._capi.OPT_KEEP_A) == 1
+            # an impossible tolerance turns the same solve into a Failure (the check is really evaluated)
+            strict = ls.init(ls.LinearProblem(A, b), alg, abstol=0.0, reltol=1e-300)
+            assert ls.solve_(strict).retcode == ls.ReturnCode.Failure
+    # BlockDiagonal: block-by-block check
+    blocks = [rng.random((k, k)) + k * np.eye(k) for k in (3, 70, 20)]
+    bd = ls.BlockDiagonal(blocks)
+    sol = ls.solve(ls.LinearProblem(bd, rng.random(93)), ls.B200LUFactorization(residualsafety=True))
+    assert sol.retcode == ls.ReturnCode.Success
