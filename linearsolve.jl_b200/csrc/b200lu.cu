@@ -241,7 +241,7 @@ static int launch_trsm_cc(b200lu_handle* h, cudaStream_t st, const T* Lp, int64_
 #define TRSM_CASE(R)                                                                             \
     {                                                                                            \
         const size_t smem = (size_t)32 * (R * 32) * sizeof(T);                                   \
-        static bool attr_set = false;                                                            \
+        static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */                                                            \
         if (!attr_set) {                                                                         \
             CU_TRY(h, cudaFuncSetAttribute(trsm_lunit_kernel<T, R, CC, NWARP>,                   \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -277,7 +277,7 @@ static int launch_dgemm_cfg(b200lu_handle* h, cudaStream_t st, int M, int N, int
                             int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc) {
     using Cfg = DgemmCfg<BM, BN, 16, WM, WN, STAGES>;
     auto kern = dgemm_sub_kernel<BM, BN, 16, WM, WN, STAGES, MINB>;
-    static bool attr_set = false;
+    static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
     if (!attr_set) {
         CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_set = true;
@@ -362,7 +362,7 @@ static int launch_sgemm_tc(b200lu_handle* h, cudaStream_t st, int M, int N, int 
     if ((rc = make_tmap_2d(h, &tAlo, Alo, K, M, lst, TC_BK, TC_BM))) return rc;
     if ((rc = make_tmap_2d(h, &tBhi, Bhi, K, N, lst, TC_BK, TC_BN))) return rc;
     if ((rc = make_tmap_2d(h, &tBlo, Blo, K, N, lst, TC_BK, TC_BN))) return rc;
-    static bool attr_set = false;
+    static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
     if (!attr_set) {
         CU_TRY(h, cudaFuncSetAttribute(sgemm3x_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         attr_set = true;
@@ -442,7 +442,7 @@ template <typename T, int W, int RPT, int NTV = PCL_NT>
 static int launch_panel_cluster_cfg(b200lu_handle* h, cudaStream_t st, PanelArgs<T> p) {
     constexpr int PCL_NT = NTV;   // threads per CTA of this instantiation
     auto kern = panel_cluster_kernel<T, W, RPT, PCL_NT>;
-    static bool attr_set = false;
+    static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
     if (!attr_set) {
         CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -840,7 +840,7 @@ static int trsv3_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const 
     auto kl = trsv3_kernel<T, false, NEAR, CS>;
     auto ku = trsv3_kernel<T, true, NEAR, CS>;
     if (h->t3_ok < 0 || h->t3_nblk != nblk) {
-        static bool attr_set = false;
+        static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
         if (!attr_set) {
             CU_TRY(h, cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, trsv3_smem_bytes<T, NEAR>()));
             CU_TRY(h, cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, trsv3_smem_bytes<T, NEAR>()));
@@ -927,7 +927,7 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T
     const int nblk = cdiv(n, TRSV_TB);
     if (!h->solve_ready) {
         const size_t tsm = sizeof(T) * TRSV_TB * (2 * TRSV_TB + 1);
-        static bool attr_set = false;
+        static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
         if (!attr_set) {
             CU_TRY(h, cudaFuncSetAttribute(trtri_diag_kernel<T>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
@@ -1954,7 +1954,7 @@ static int batched_factor_launch(b200lu_handle* h, const T* A, int64_t lda, int6
     if (n > 64) {
         // 65 ... BATCHED_SMEM_NMAX rows: the system lives in shared memory, one CTA each
         const size_t smem = (size_t)n * (n | 1) * sizeof(T);
-        static bool attr_set = false;
+        static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
         if (!attr_set) {
             CU_TRY(h, cudaFuncSetAttribute(getrf_batched_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)((size_t)BATCHED_SMEM_NMAX * (BATCHED_SMEM_NMAX | 1) * sizeof(T))));
@@ -1983,7 +1983,7 @@ static int batched_solve_launch(b200lu_handle* h, int nrhs, const T* B, int64_t 
     {                                                                                             \
         const unsigned grid = (unsigned)((batch + (WPCV) - 1) / (WPCV));                           \
         if ((NMAXV) > 64) {   /* more than 48 KB of dynamic shared memory: opt in once */          \
-            static bool attr_set = false;                                                         \
+            static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */                                                         \
             if (!attr_set) {                                                                      \
                 CU_TRY(h, cudaFuncSetAttribute(getrs_batched_kernel<T, NMAXV, WPCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                (int)((size_t)(WPCV) * (NMAXV) * (NMAXV) * sizeof(T)))); \
