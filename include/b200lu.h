@@ -124,7 +124,10 @@ enum {
                                    is no longer streamed under the factorization) so that
                                    b200lu_residual_norms can check a solution on the device; default 0.
                                    MIXED handles always hold A in FP64.                              */
-    B200LU_OPT_COUNT = 14
+    B200LU_OPT_BATCHED_MODE = 14, /* batched getrf of systems up to 64 rows: 0 (default) = the rolled
+                                   left-shifting-window kernel; 1 = EXPERIMENTAL fully unrolled kernel
+                                   without the shared-memory tile (not yet validated on hardware)  */
+    B200LU_OPT_COUNT = 15
 };
 
 /* library/ABI version: major*10000 + minor*100 + patch */
