@@ -434,8 +434,10 @@ __global__ void __launch_bounds__(BATCHED_SMEM_NT) getrf_batched_smem_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL (B200LU_OPT_BATCHED_MODE = 1; written at the end of round 1 after the GPU budget
-// was spent: compiled and inspected (registers, spills, SASS size) but NOT yet run on hardware).
+// OPT-IN VARIANT (B200LU_OPT_BATCHED_MODE = 1), measured and not adopted: bitwise the same factors
+// as the kernel above, but 1.120 ms against 1.028 ms for 16384 systems of 64 x 64
+// (profiles/r01_batched_v2_check.txt) — its 248 KB of straight-line SASS costs more in the
+// instruction cache than the removed tile traffic and barrier gain.
 // The register kernel above issues ~213 instructions per warp and column of which ~36 are FMAs
 // (profiles/r01_ncu_batched_getrf_details.txt): the left-shifting window needs a shared-memory
 // tile (two tile stores per thread and column, skewed index arithmetic, a write-out pass) and a

@@ -1,6 +1,6 @@
 """Round-2 first check of the experimental batched getrf (B200LU_OPT_BATCHED_MODE = 1): bitwise
 comparison with the default kernel on 4096 systems, then device times of both on BASELINE config 4
-(65536 systems of 64x64).  No torch.  Usage: python scripts/batched_v2_check.py"""
+(65536 systems of 64x64).  No torch.  Usage: python scripts/batched_v2_check.py [batch]"""
 import os
 import sys
 
@@ -23,7 +23,7 @@ for mode in (0, 1):
     hs.append((h, ipiv, info, LU))
 same = all(np.array_equal(hs[0][i], hs[1][i]) for i in (1, 2, 3))
 print(f"mode 1 == mode 0 (ipiv, info, factors) on {batch} systems: {same}", flush=True)
-batch = 65536
+batch = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 A = rng.random((batch, n, n)) + n * np.eye(n)
 for mode, (h, *_r) in enumerate(hs):
     ts = []
