@@ -188,6 +188,69 @@ def test_blockdiag_padding_is_exact(ls, oracle):
     assert info_p[3] == 3 and not info_p[[0, 1, 2, 4, 5]].any()
 
 
+def _header_prototypes():
+    """name -> list of C parameter type strings, parsed from include/b200lu.h"""
+    hdr = open(os.path.join(ROOT, "include", "b200lu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(b200lu_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr):
+        args = " ".join(m.group(2).split())
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        protos[m.group(1)] = params
+    return protos
+
+
+def _ctype_class(c_param):
+    """coarse class of a C parameter: pointer / int64 / uint64 / int / char / double"""
+    t = c_param.rsplit(" ", 1)[0] if " " in c_param else c_param
+    if "*" in c_param:
+        return "ptr"
+    for key, cls in (("uint64_t", "u64"), ("int64_t", "i64"), ("double", "f64"), ("char", "char"), ("int", "int")):
+        if key in t:
+            return cls
+    raise AssertionError(f"unclassified parameter {c_param!r}")
+
+
+def test_ctypes_binding_matches_header_prototypes(ls):
+    """every argtypes list in _capi.py has the arity and the coarse types of the C prototype"""
+    protos = _header_prototypes()
+    lib = ls._capi.load()
+    cls_of = {ctypes.c_int64: "i64", ctypes.c_uint64: "u64", ctypes.c_int: "int", ctypes.c_double: "f64",
+              ctypes.c_char: "char", ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr"}
+    assert sorted(protos) == sorted(ls._capi.SYMBOLS)
+    for name, params in protos.items():
+        argtypes = getattr(lib, name).argtypes
+        assert argtypes is not None and len(argtypes) == len(params), (name, params, argtypes)
+        for ct, cp in zip(argtypes, params):
+            got = cls_of.get(ct, "ptr")       # POINTER(...) types are pointers
+            assert got == _ctype_class(cp), (name, cp, ct)
+
+
+def test_julia_glue_ccalls_match_header_prototypes():
+    """the Julia file a maintainer adds (not runnable here) binds only symbols the header declares,
+    with the right number of arguments and pointer / integer / char / double in the right places"""
+    protos = _header_prototypes()
+    src = open(os.path.join(ROOT, "linearsolve.jl_b200", "julia", "B200LUFactorization.jl")).read()
+    jl_cls = {"Int64": "i64", "UInt64": "u64", "Cint": "int", "UInt8": "char", "Cdouble": "f64", "Float64": "f64"}
+    calls = re.findall(r"ccall\(\(:(b200lu_[a-z0-9_]+),\s*libb200lu\[\]\),\s*(\w+),\s*\(([^)]*)\)", src)
+    assert len(calls) >= 8
+    seen = set()
+    for name, ret, types in calls:
+        assert name in protos, f"{name} is not declared in include/b200lu.h"
+        seen.add(name)
+        tl = [t.strip() for t in types.split(",") if t.strip()]
+        params = protos[name]
+        assert len(tl) == len(params), (name, tl, params)
+        for jt, cp in zip(tl, params):
+            want = _ctype_class(cp)
+            got = "ptr" if jt.startswith(("Ptr{", "Ref{")) or jt == "Cstring" else jl_cls[jt]
+            assert got == want, (name, jt, cp)
+    # the FFI surface INTEGRATION.md names is actually bound
+    for must in ("b200lu_create", "b200lu_destroy", "b200lu_factor", "b200lu_solve", "b200lu_factor_batched",
+                 "b200lu_solve_batched_trans", "b200lu_residual_norms", "b200lu_last_error", "b200lu_set_option"):
+        assert must in seen, must
+
+
 def test_bench_reference_arm_runs_on_cpu():
     import json
     import subprocess
