@@ -251,6 +251,82 @@ def test_julia_glue_ccalls_match_header_prototypes():
         assert must in seen, must
 
 
+class _OracleHandle:
+    """Stand-in for _capi.Handle backed by the CPU oracle: lets the BlockDiagonal host logic (grouping,
+    padding, packing of right-hand sides, adjoint wiring, retcodes) run without a GPU.  Test
+    infrastructure only — the product has no such path."""
+    created = 0
+
+    def __init__(self, dtype=0, device=0):
+        type(self).created += 1
+        self.dtype, self.np_dtype, self.n = dtype, np.float64, 0
+        self.options = {}
+
+    def set_option(self, opt, value):
+        self.options[opt] = value
+
+    def factor_batched(self, A):
+        from oracle import lu_oracle
+        self.A = np.array(A, copy=True)                      # [s, col, row]
+        _, ipiv, info, _ = lu_oracle.ref_batched(self.A)
+        self.b_batch, self.b_n = A.shape[0], A.shape[1]
+        return ipiv, info
+
+    def solve_batched(self, B, trans="N"):
+        X = np.empty_like(B)
+        for s in range(B.shape[0]):
+            M = self.A[s].T if trans == "N" else self.A[s]
+            X[s] = np.linalg.solve(M, B[s].T).T
+        return X
+
+    def factor(self, A, want_ipiv=True):
+        self.M, self.n = np.array(A, copy=True), A.shape[0]
+        return None, int(np.linalg.matrix_rank(self.M) < self.n)
+
+    def solve(self, B, out=None, trans="N"):
+        return np.linalg.solve(self.M if trans == "N" else self.M.T, B)
+
+
+def test_blockdiagonal_host_logic_with_oracle_backend(ls, monkeypatch):
+    """ext/LinearSolveBlockDiagonalsExt.jl:119-125,183-205 through interface.py with the device
+    replaced by the oracle: ragged blocks, vector and matrix right-hand sides, adjoint, a singular
+    block => Failure with isfresh kept, handle reuse across refactorizations"""
+    monkeypatch.setattr(ls._capi, "Handle", _OracleHandle)
+    _OracleHandle.created = 0
+    rng = np.random.default_rng(3)
+    sizes = [2, 3, 4, 70, 130, 200, 0, 16]
+    blocks = [rng.random((k, k)) + k * np.eye(k) for k in sizes]
+    A = ls.BlockDiagonal(blocks)
+    D = A.to_dense()
+    n = sum(sizes)
+    alg = ls.B200LUFactorization(throwerror=False, residualsafety=True)
+    cache = ls.init(ls.LinearProblem(A, rng.random(n)), alg)
+    sol = ls.solve_(cache)
+    assert sol.retcode == ls.ReturnCode.Success and not cache.isfresh
+    np.testing.assert_allclose(sol.u, np.linalg.solve(D, cache.b), rtol=1e-11)
+    plan = ls.plan_blockdiag(sizes)
+    assert _OracleHandle.created == len(plan) == 4          # classes 16, 96, 160 and the 200-row block
+    assert all(h.options.get(ls._capi.OPT_KEEP_A) == 1 for _, h, _, _ in cache.cacheval.groups)
+    B = rng.random((n, 3))
+    cache.b = B
+    cache.u = np.zeros_like(B)
+    np.testing.assert_allclose(ls.solve_(cache).u, np.linalg.solve(D, B), rtol=1e-11)
+    np.testing.assert_allclose(ls.solve_(cache, adjoint=True).u, np.linalg.solve(D.T, B), rtol=1e-11)
+    # new values, same block sizes: the handles are reused
+    cache.A = ls.BlockDiagonal([2.0 * b for b in blocks])
+    np.testing.assert_allclose(ls.solve_(cache).u, np.linalg.solve(2.0 * D, B), rtol=1e-11)
+    assert _OracleHandle.created == 4
+    # a singular block anywhere => Failure, isfresh stays set
+    bad = [b.copy() for b in blocks]
+    bad[2][:, 1] = 0.0
+    cache.A = ls.BlockDiagonal(bad)
+    assert ls.solve_(cache).retcode == ls.ReturnCode.Failure and cache.isfresh
+    # different block sizes: a new plan
+    cache.A = ls.BlockDiagonal(blocks[:3] + [np.eye(n - 9)])
+    assert ls.solve_(cache).retcode == ls.ReturnCode.Success
+    assert [g[0] for g in cache.cacheval.groups] == ["batched", "single"]
+
+
 def test_bench_reference_arm_runs_on_cpu():
     import json
     import subprocess
