@@ -280,11 +280,20 @@ class _OracleHandle:
         return X
 
     def factor(self, A, want_ipiv=True):
+        self.nfactor = getattr(self, "nfactor", 0) + 1
         self.M, self.n = np.array(A, copy=True), A.shape[0]
         return None, int(np.linalg.matrix_rank(self.M) < self.n)
 
     def solve(self, B, out=None, trans="N"):
-        return np.linalg.solve(self.M if trans == "N" else self.M.T, B)
+        X = np.linalg.solve(self.M if trans == "N" else self.M.T, B)
+        if out is not None:
+            out[...] = X
+            return out
+        return X
+
+    def residual_norms(self, B, X):
+        Bm, Xm = B.reshape(self.n, -1), X.reshape(self.n, -1)
+        return np.linalg.norm(Bm - self.M @ Xm, axis=0), np.linalg.norm(Bm, axis=0)
 
 
 def test_blockdiagonal_host_logic_with_oracle_backend(ls, monkeypatch):
@@ -325,6 +334,44 @@ def test_blockdiagonal_host_logic_with_oracle_backend(ls, monkeypatch):
     cache.A = ls.BlockDiagonal(blocks[:3] + [np.eye(n - 9)])
     assert ls.solve_(cache).retcode == ls.ReturnCode.Success
     assert [g[0] for g in cache.cacheval.groups] == ["batched", "single"]
+
+
+def test_dense_solve_protocol_with_oracle_backend(ls, monkeypatch):
+    """solve! protocol of src/openblas.jl:362-459 through interface.py with the device replaced by the
+    oracle: factor only when fresh, Failure keeps isfresh, getrs straight into cache.u, adjoint reuse,
+    residual safety (src/factorization.jl:127-156) and the option wiring of both algorithms"""
+    monkeypatch.setattr(ls._capi, "Handle", _OracleHandle)
+    _OracleHandle.created = 0
+    rng = np.random.default_rng(8)
+    n = 40
+    A = rng.random((n, n)) + n * np.eye(n)
+    b = rng.random(n)
+    alg = ls.B200LUFactorization(throwerror=False, residualsafety=True, nb=128, lookahead=False)
+    cache = ls.init(ls.LinearProblem(A, b), alg)
+    u_buffer = cache.u
+    sol = ls.solve_(cache)
+    assert sol.retcode == ls.ReturnCode.Success and not cache.isfresh
+    assert sol.u is u_buffer                                   # written in place
+    np.testing.assert_allclose(sol.u, np.linalg.solve(A, b), rtol=1e-12)
+    h = cache.cacheval.handle
+    assert h.options == {ls._capi.OPT_NB: 128, ls._capi.OPT_LOOKAHEAD: 0, ls._capi.OPT_KEEP_A: 1}
+    cache.b = rng.random(n)                                    # re-solve only: no new handle, no refactor
+    np.testing.assert_allclose(ls.solve_(cache).u, np.linalg.solve(A, cache.b), rtol=1e-12)
+    np.testing.assert_allclose(ls.solve_(cache, adjoint=True).u, np.linalg.solve(A.T, cache.b), rtol=1e-12)
+    assert _OracleHandle.created == 1 and h.nfactor == 1
+    cache.A = np.ones((n, n))                                  # singular => Failure, isfresh stays set
+    assert cache.isfresh
+    assert ls.solve_(cache).retcode == ls.ReturnCode.Failure and cache.isfresh
+    cache.A = A
+    assert ls.solve_(cache).retcode == ls.ReturnCode.Success
+    strict = ls.init(ls.LinearProblem(A, b), alg, abstol=0.0, reltol=1e-300)
+    assert ls.solve_(strict).retcode == ls.ReturnCode.Failure   # the residual check is evaluated
+    mixed = ls.B200LU32MixedLUFactorization(throwerror=False, refine=False)
+    cm = ls.init(ls.LinearProblem(A, b), mixed)
+    assert ls.solve_(cm).retcode == ls.ReturnCode.Success
+    assert cm.cacheval.handle.dtype == ls._capi.MIXED and cm.cacheval.handle.options == {ls._capi.OPT_REFINE_MAXIT: 0}
+    with pytest.raises(TypeError):
+        ls.init(ls.LinearProblem(A.astype(np.float32), b.astype(np.float32)), mixed).alg.handle_dtype(np.float32)
 
 
 def test_bench_reference_arm_runs_on_cpu():
