@@ -124,11 +124,7 @@ enum {
                                    is no longer streamed under the factorization) so that
                                    b200lu_residual_norms can check a solution on the device; default 0.
                                    MIXED handles always hold A in FP64.                              */
-    B200LU_OPT_BATCHED_MODE = 14, /* batched getrf of systems up to 64 rows: 0 (default) = the rolled
-                                   left-shifting-window kernel; 1 = fully unrolled kernel without the
-                                   shared-memory tile (same factors bit for bit; measured 8 % slower
-                                   at n = 64, kept for the round-2 study)                          */
-    B200LU_OPT_COUNT = 15
+    B200LU_OPT_COUNT = 14
 };
 
 /* library/ABI version: major*10000 + minor*100 + patch */

@@ -1318,7 +1318,6 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     h->opt[B200LU_OPT_STREAM_H2D] = 1;
     h->opt[B200LU_OPT_MAPPED_RHS] = 1;
     h->opt[B200LU_OPT_KEEP_A] = 0;
-    h->opt[B200LU_OPT_BATCHED_MODE] = 0;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) == cudaSuccess;
@@ -1501,7 +1500,6 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_STREAM_H2D && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_MAPPED_RHS && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_KEEP_A && (value < 0 || value > 1)) return -3;
-    if (option == B200LU_OPT_BATCHED_MODE && (value < 0 || value > 1)) return -3;
     h->opt[option] = value;
     return 0;
 }
@@ -1963,14 +1961,6 @@ static int batched_factor_launch(b200lu_handle* h, const T* A, int64_t lda, int6
             attr_set = true;
         }
         getrf_batched_smem_kernel<T><<<(unsigned)batch, BATCHED_SMEM_NT, smem, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_perm, h->dB_info, n);
-    } else if (h->opt[B200LU_OPT_BATCHED_MODE] == 1) {
-        // experimental: fully unrolled column loop, no shared-memory tile (see batched.cuh)
-        if (n <= 16)
-            getrf_batched_unrolled_kernel<T, 16><<<(unsigned)batch, 32, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_perm, h->dB_info, n);
-        else if (n <= 32)
-            getrf_batched_unrolled_kernel<T, 32><<<(unsigned)batch, 32, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_perm, h->dB_info, n);
-        else
-            getrf_batched_unrolled_kernel<T, 64><<<(unsigned)batch, 64, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_perm, h->dB_info, n);
     } else if (n <= 16)
         getrf_batched_kernel<T, 16><<<(unsigned)batch, 32, 0, st>>>(A, lda, strideA, LU, n, (int64_t)n * n, h->dB_ipiv, h->dB_perm, h->dB_info, n);
     else if (n <= 32)

@@ -433,133 +433,4 @@ __global__ void __launch_bounds__(BATCHED_SMEM_NT) getrf_batched_smem_kernel(
     if (tid == 0) info[sys] = myinfo;
 }
 
-// ---------------------------------------------------------------------------------------------
-// OPT-IN VARIANT (B200LU_OPT_BATCHED_MODE = 1), measured and not adopted: bitwise the same factors
-// as the kernel above, but 1.120 ms against 1.028 ms for 16384 systems of 64 x 64
-// (profiles/r01_batched_v2_check.txt) — its 248 KB of straight-line SASS costs more in the
-// instruction cache than the removed tile traffic and barrier gain.
-// The register kernel above issues ~213 instructions per warp and column of which ~36 are FMAs
-// (profiles/r01_ncu_batched_getrf_details.txt): the left-shifting window needs a shared-memory
-// tile (two tile stores per thread and column, skewed index arithmetic, a write-out pass) and a
-// second barrier per column.  This variant unrolls the column loop COMPLETELY instead, so every
-// register index is static without any shifting:
-//  * thread t holds row t for the whole factorization; finished multipliers stay where they are
-//    (a[c], c < k), a frozen pivot row keeps its U entries (a[c], c >= k): at the end every
-//    thread owns its complete final row and writes it at its final position — for a fixed column
-//    the 64 threads write a permutation of one contiguous 512-byte segment, so no tile is needed;
-//  * exact live counts (no dead FMAs), one barrier per column (each warp's candidate lane stages
-//    its row; no second "winner only" round), frozen rows are predicated off the update.
-// Same pivot / tie / zero-pivot / NaN contract as getrf_batched_kernel.
-template <typename T, int NMAX>
-struct BatchedSharedU {
-    static constexpr int NW = (NMAX + 31) / 32;
-    T cand_row[2][NW][NMAX];      // per-warp candidate rows (entry c at index c), double-buffered by column parity
-    T cand_val[2][NW];
-    T cand_rinv[2][NW];
-    int cand_pos[2][NW];
-    int cand_thr[2][NW];
-    int red[NW];
-};
-
-template <typename T, int NMAX>
-__global__ void __launch_bounds__(batched_threads(NMAX)) getrf_batched_unrolled_kernel(
-    const T* __restrict__ A, long long lda, long long strideA, T* __restrict__ LU,
-    long long ldlu, long long strideLU, int* __restrict__ ipiv, int* __restrict__ perm,
-    int* __restrict__ info, int n) {
-    constexpr int NW = (NMAX + 31) / 32;
-    __shared__ __align__(16) BatchedSharedU<T, NMAX> sh;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const long long sys = blockIdx.x;
-    const T* Ab = A + sys * strideA;
-
-    T a[NMAX];   // row t; static indices everywhere below (the k loop is fully unrolled)
-#pragma unroll
-    for (int c = 0; c < NMAX; ++c) a[c] = (t < n && c < n) ? Ab[(long long)c * lda + t] : T(0);
-    int pos = t < n ? t : INT_MAX;   // logical position of my row; padding rows never compete
-    bool done = t >= n;              // row already used as a pivot row (frozen)
-    int myinfo = 0;
-
-#pragma unroll
-    for (int k = 0; k < NMAX; ++k) {
-        if (k < n) {   // uniform over the CTA
-            const int par = k & 1;
-            // every thread computes the reciprocal of its OWN candidate: independent of the arg-max, so
-            // the FP64 division (~81 cycles) runs under the redux + ballot instead of behind them
-            const T rinv_own = T(1) / a[k];
-            const T v = done ? T(0) : tabs(a[k]);
-            const int wl = pcl_warp_argmax(v, pos);
-            if (lane == wl) {
-#pragma unroll
-                for (int c = k; c < NMAX; ++c) sh.cand_row[par][warp][c] = a[c];
-                sh.cand_val[par][warp] = v;
-                sh.cand_rinv[par][warp] = rinv_own;
-                sh.cand_pos[par][warp] = pos;
-                sh.cand_thr[par][warp] = t;
-            }
-            if (wl < 0 && lane == 0) { sh.cand_val[par][warp] = T(0); sh.cand_pos[par][warp] = INT_MAX; }
-            if (NW > 1) __syncthreads(); else __syncwarp();
-            int bw = 0;
-            T bv = sh.cand_val[par][0];
-            int bp = sh.cand_pos[par][0];
-#pragma unroll
-            for (int w = 1; w < NW; ++w) {
-                const T ov = sh.cand_val[par][w];
-                const int op = sh.cand_pos[par][w];
-                if (ov > bv || (ov == bv && op < bp)) { bv = ov; bp = op; bw = w; }
-            }
-            if (!(bv > T(0))) {
-                // all-zero / all-NaN subcolumn: kp = k, the "pivot" row is the row at position k (rare)
-                if (NW > 1) __syncthreads(); else __syncwarp();
-                if (!done && pos == k) {
-#pragma unroll
-                    for (int c = k; c < NMAX; ++c) sh.cand_row[par][0][c] = a[c];
-                    sh.cand_thr[par][0] = t;
-                    sh.cand_rinv[par][0] = rinv_own;
-                }
-                if (NW > 1) __syncthreads(); else __syncwarp();
-                bw = 0;
-                bp = k;
-            }
-            const T* prow = &sh.cand_row[par][bw][0];
-            const int pthr = sh.cand_thr[par][bw];
-            const T pv = prow[k];
-            if (t == pthr) {
-                done = true;   // frozen: a[c >= k] are the U entries of row k, a[c < k] its multipliers
-                pos = k;
-                ipiv[sys * n + k] = bp;
-                if (pv == T(0) && myinfo == 0) myinfo = k + 1;
-            } else if (!done) {
-                if (pos == k) pos = bp;   // the displaced top row stays active
-                T l = a[k];
-                if (pv != T(0)) l *= sh.cand_rinv[par][bw];
-                a[k] = l;
-                const T nl = -l;
-#pragma unroll
-                for (int c = k + 1; c < NMAX; ++c) a[c] = tfma(nl, prow[c], a[c]);
-            }
-        }
-    }
-
-    // first zero pivot over the system (each pivot thread saw at most one)
-    {
-        int v = myinfo ? myinfo : INT_MAX;
-        v = __reduce_min_sync(0xffffffffu, v);
-        if (lane == 0) sh.red[warp] = v;
-        __syncthreads();
-        v = sh.red[0];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) v = min(v, sh.red[w]);
-        if (t == 0) info[sys] = (v == INT_MAX) ? 0 : v;
-    }
-    // every thread owns its complete final row: for a fixed column the CTA writes a permutation of
-    // one contiguous segment
-    if (t < n) {
-        T* Lb = LU + sys * strideLU + pos;
-        perm[sys * n + pos] = t;
-#pragma unroll
-        for (int c = 0; c < NMAX; ++c)
-            if (c < n) Lb[(long long)c * ldlu] = a[c];
-    }
-}
-
 }  // namespace b200lu

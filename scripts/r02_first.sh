@@ -1,11 +1,11 @@
 #!/bin/bash
 # First GPU call of round 2 (one B200): the state the round starts from.
-#   1. the whole -m gpu suite (incl. the opt-in batched variant), smoke()
+#   1. the whole -m gpu suite, smoke()
 #   2. the default bench line + reference arm
 #   3. where a single-RHS solve's host time goes
 #   4. ncu: launch list of the default bench, full captures of the kernels added late in round 1
 mkdir -p gpurun_out
-B200LU_EXPERIMENTAL=1 timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -5 | tee gpurun_out/r02_tests.log
+timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -5 | tee gpurun_out/r02_tests.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/r02_smoke.log
 timeout 600 python bench.py > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err
 timeout 300 python bench.py --impl reference > gpurun_out/r02_bench_reference.json 2>&1

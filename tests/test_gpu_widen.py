@@ -2,8 +2,6 @@
 every handle type (`solve!(cache; adjoint = true)`, reference src/common.jl:1012-1027 and
 test/Core/adjoint.jl) and ragged BlockDiagonal problems in one batched launch per kernel class
 (ext/LinearSolveBlockDiagonalsExt.jl:119-125,183-205; test/Core/basictests.jl:1168-1223)."""
-import os
-
 import numpy as np
 import pytest
 
@@ -223,30 +221,3 @@ def test_residualsafety_on_device(gpu_required, ls):
     sol = ls.solve(ls.LinearProblem(bd, rng.random(93)), ls.B200LUFactorization(residualsafety=True))
     assert sol.retcode == ls.ReturnCode.Success
 
-
-@pytest.mark.skipif(not os.environ.get("B200LU_EXPERIMENTAL"),
-                    reason="opt-in variant, measured 8 % slower than the default kernel (profiles/r01_batched_v2_check.txt: "
-                           "bitwise-equal factors at n = 64); the other size classes have not been run on hardware yet — "
-                           "B200LU_EXPERIMENTAL=1 runs them")
-@pytest.mark.parametrize("n", [1, 2, 3, 8, 16, 17, 31, 32, 33, 48, 63, 64])
-def test_experimental_unrolled_batched_getrf(gpu_required, ls, oracle, n):
-    """B200LU_OPT_BATCHED_MODE = 1 must reproduce the default kernel bit for bit (same arithmetic in the
-    same order per element) and therefore the oracle's pivots"""
-    rng = np.random.default_rng(n)
-    batch = 37
-    A = rng.random((batch, n, n)) + (n if n % 2 else 0) * np.eye(n)
-    A[5].T[:, 0] = 0.0             # a singular system
-    A[7] = 0.0
-    h0 = ls.Handle(ls._capi.F64)
-    h1 = ls.Handle(ls._capi.F64)
-    h1.set_option(ls._capi.OPT_BATCHED_MODE, 1)
-    ipiv0, info0 = h0.factor_batched(A)
-    ipiv1, info1 = h1.factor_batched(A)
-    LU0, _, _ = h0.get_factors_batched()
-    LU1, _, _ = h1.get_factors_batched()
-    assert np.array_equal(ipiv0, ipiv1) and np.array_equal(info0, info1)
-    assert np.array_equal(LU0, LU1)
-    ok = [s for s in range(batch) if info1[s] == 0]
-    b = rng.random((batch, n))
-    x0, x1 = h0.solve_batched(b), h1.solve_batched(b)
-    assert np.array_equal(x0[ok], x1[ok])
