@@ -134,9 +134,8 @@ struct b200lu_handle {
     void* dB_rhs = nullptr;
     void* dB_x = nullptr;
     int64_t b_cap_rhs = 0;
-    long long* hB_ipiv = nullptr;
-    int* hB_info = nullptr;
-    int64_t hb_cap = 0;
+    int* hB_stage = nullptr;   // pinned staging of batched pivots / info on their way to the host
+    int64_t hb_cap = 0;        // ints
     bool b_factored = false;
 
     // profiling (B200LU_OPT_PROFILE)
@@ -1389,8 +1388,7 @@ void b200lu_destroy(b200lu_handle* h) {
     if (h->h_rhs) cudaFreeHost(h->h_rhs);
     if (h->h_small) cudaFreeHost(h->h_small);
     if (h->h_scal) cudaFreeHost(h->h_scal);
-    if (h->hB_ipiv) cudaFreeHost(h->hB_ipiv);
-    if (h->hB_info) cudaFreeHost(h->hB_info);
+    if (h->hB_stage) cudaFreeHost(h->hB_stage);
     for (cudaEvent_t e : h->ev_panel) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
@@ -1919,6 +1917,17 @@ int b200lu_get_ipiv(b200lu_handle* h, int64_t* ipiv_out) {
 }  // extern "C"
 
 // ------------------------------------------------------------------ batched --
+// pinned host staging for the int32 pivots / info of a batch (grown on demand, reused by warm calls)
+static int ensure_batched_stage(b200lu_handle* h, int64_t count) {
+    if (count <= h->hb_cap) return 0;
+    if (h->hB_stage) cudaFreeHost(h->hB_stage);
+    h->hB_stage = nullptr;
+    h->hb_cap = 0;
+    CU_TRY(h, cudaMallocHost((void**)&h->hB_stage, (size_t)count * sizeof(int)));
+    h->hb_cap = count;
+    return 0;
+}
+
 static int ensure_batched(b200lu_handle* h, int64_t batch, int64_t n) {
     const size_t es = elem_size(h) == 8 ? 8 : 4;
     const size_t fs = (h->dtype == B200LU_F64) ? 8 : 4;
@@ -2046,11 +2055,12 @@ int b200lu_factor_batched_device(b200lu_handle* h, int64_t batch, int64_t n, con
     h->b_factored = true;
     if (any_info) {
         // count failures: max over info on the host side is done by the host path; here a cheap flag
+        rc = ensure_batched_stage(h, batch);
+        if (rc) return rc;
+        CU_TRY(h, cudaMemcpyAsync(h->hB_stage, h->dB_info, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
         CU_TRY(h, cudaStreamSynchronize(h->s_main));
-        std::vector<int> tmp((size_t)batch);
-        CU_TRY(h, cudaMemcpy(tmp.data(), h->dB_info, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost));
         int64_t bad = 0;
-        for (int64_t i = 0; i < batch; ++i) bad += tmp[(size_t)i] != 0;
+        for (int64_t i = 0; i < batch; ++i) bad += h->hB_stage[i] != 0;
         *any_info = bad;
     } else {
         CU_TRY(h, cudaStreamSynchronize(h->s_main));
@@ -2158,15 +2168,20 @@ int b200lu_get_factors_batched(b200lu_handle* h, void* LU_host, int64_t lda, int
                                        (size_t)n * fs, (size_t)n, cudaMemcpyDeviceToHost));
         }
     }
+    if (ipiv_out || info_out) {
+        int rc = ensure_batched_stage(h, batch * n);
+        if (rc) return rc;
+    }
     if (ipiv_out) {
-        std::vector<int> tmp((size_t)(batch * n));
-        CU_TRY(h, cudaMemcpy(tmp.data(), h->dB_ipiv, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < tmp.size(); ++i) ipiv_out[i] = (int64_t)tmp[i] + 1;
+        const int64_t cnt = batch * n;
+        CU_TRY(h, cudaMemcpyAsync(h->hB_stage, h->dB_ipiv, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
+        CU_TRY(h, cudaStreamSynchronize(h->s_main));
+        for (int64_t i = 0; i < cnt; ++i) ipiv_out[i] = (int64_t)h->hB_stage[i] + 1;
     }
     if (info_out) {
-        std::vector<int> tmp((size_t)batch);
-        CU_TRY(h, cudaMemcpy(tmp.data(), h->dB_info, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < tmp.size(); ++i) info_out[i] = tmp[i];
+        CU_TRY(h, cudaMemcpyAsync(h->hB_stage, h->dB_info, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
+        CU_TRY(h, cudaStreamSynchronize(h->s_main));
+        for (int64_t i = 0; i < batch; ++i) info_out[i] = h->hB_stage[i];
     }
     return 0;
 }
