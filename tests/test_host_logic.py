@@ -63,6 +63,16 @@ def test_bad_arguments_do_not_need_a_device(ls):
     assert lib.b200lu_create(None, 0, 1, None) == -1
     assert lib.b200lu_last_timing(None, 0) == -1.0
     assert lib.b200lu_set_option(None, 0, 64) == -1
+    # every compute entry point answers a null handle with status -1 (LAPACK style: first argument), no crash
+    assert lib.b200lu_factor(None, 4, None, 4, None, None) == -1
+    assert lib.b200lu_solve(None, b"N", 1, None, 4, None, 4) == -1
+    assert lib.b200lu_residual_norms(None, 1, None, 4, None, 4, None, None) == -1
+    assert lib.b200lu_factor_batched(None, 1, 4, None, 4, 16, None, None) == -1
+    assert lib.b200lu_solve_batched(None, 1, None, 4, 4, None, 4, 4) == -1
+    assert lib.b200lu_solve_batched_trans(None, b"T", 1, None, 4, 4, None, 4, 4) == -1
+    assert lib.b200lu_solve_batched_trans_device(None, b"T", 1, None, 4, 4, None, 4, 4) == -1
+    assert lib.b200lu_get_factors(None, None, 4) == -1 and lib.b200lu_get_ipiv(None, None) == -1
+    assert lib.b200lu_last_error(None) == b"null handle"
 
 
 def test_header_enums_match_the_python_binding(ls):
