@@ -33,7 +33,7 @@ unsigned long long g_launch_count = 0;
 }
 using namespace b200lu;
 
-#define B200LU_VERSION 100
+#define B200LU_VERSION 200   // 0.2.0: transposed batched solves, residual norms, KEEP_A, batched n <= 160
 
 // ------------------------------------------------------------------ handle --
 struct b200lu_handle {
