@@ -135,10 +135,20 @@ int b200lu_version(void);
 int64_t b200lu_launch_count(void);
 
 /*
- * Create a handle bound to `ngpus` devices.  ngpus == 1 is the single-GPU
- * path; `devices` may be NULL (device 0 .. ngpus-1).  For one-process-per-GPU
- * multi-GPU runs create the handle with ngpus == 1 on the local device and
- * attach a communicator with b200lu_comm_init.
+ * Create a handle bound to `ngpus` devices; `devices` may be NULL (device 0 .. ngpus-1).
+ *   ngpus == 1 : the single-GPU path.  For one-PROCESS-per-GPU multi-GPU runs create such a
+ *                handle on the local device and attach a communicator with b200lu_comm_init.
+ *   ngpus in 2..16 : ONE process drives all the GPUs (what a Julia `solve!` can reach; SURVEY §5
+ *                "single process, 8 devices").  The handle owns one sub-handle and one host
+ *                thread per GPU; every pair of devices must be peers (NVLink / NVSwitch).
+ *                b200lu_factor distributes the host matrix itself (1-D block-cyclic columns of
+ *                width B200LU_OPT_NB: each GPU pulls its own column blocks over its own PCIe
+ *                link), the owner of a panel stores it into its peers' memory (no NCCL),
+ *                b200lu_solve runs the distributed getrs (trans = 'N'), b200lu_factor_batched /
+ *                b200lu_solve_batched shard the batch index over the GPUs (no communication).
+ *                F64 and F32 handles; the *_device entry points, b200lu_residual_norms and the
+ *                comm/dist entry points are single-GPU-handle calls (status -1 / 3 here).
+ * Returns 5 when the devices are not all peers of each other.
  */
 int b200lu_create(b200lu_handle** h, int dtype, int ngpus, const int* devices);
 void b200lu_destroy(b200lu_handle* h);
@@ -234,16 +244,23 @@ int b200lu_get_factors_batched(b200lu_handle* h, void* LU_host, int64_t lda,
                                int64_t strideA, int64_t* ipiv_out, int64_t* info_out);
 
 /*
- * One-process-per-GPU multi-GPU (1D block-cyclic columns, NCCL panel
- * broadcast).  Rank 0 calls b200lu_comm_unique_id, the host language
- * broadcasts the 128 bytes (torch.distributed / MPI / files), every rank calls
- * b200lu_comm_init.  Afterwards b200lu_factor_dist / b200lu_solve_dist operate
- * on this rank's local column blocks: global column block j (width nb) lives on
- * rank j % nranks at local block index j / nranks.
+ * One-process-per-GPU multi-GPU (1-D block-cyclic columns).  Rank 0 calls
+ * b200lu_comm_unique_id, the host language broadcasts the 128 bytes (torch.distributed / MPI /
+ * files), every rank calls b200lu_comm_init (nranks == 1 needs no id).  Afterwards
+ * b200lu_factor_dist / b200lu_solve_dist (collective calls) operate on this rank's local column
+ * blocks: global column block j (width nb) lives on rank j % nranks at local block index
+ * j / nranks; lda must be a multiple of 16 bytes, A 16-byte aligned; the local matrix is factored
+ * in place.  The factored panel travels by peer stores into device windows the ranks map with
+ * cudaIpc (the NCCL communicator only carries the handle exchange); when the windows cannot be
+ * mapped, or with B200LU_DIST_MODE=nccl in the environment, the panel is ncclBroadcast instead
+ * (b200lu_dist_transport: 1 = peer stores, 0 = NCCL).  b200lu_solve_dist: B and X replicated
+ * (n x nrhs on every rank), the factors stay distributed (no n x n replica, warm calls allocate
+ * nothing); it needs the peer-store transport (status 5 otherwise).
  */
 int b200lu_comm_unique_id(void* id128);
 int b200lu_comm_init(b200lu_handle* h, const void* id128, int rank, int nranks);
 int b200lu_dist_local_cols(const b200lu_handle* h, int64_t n, int64_t* ncols_local);
+int b200lu_dist_transport(const b200lu_handle* h);
 int b200lu_factor_dist(b200lu_handle* h, int64_t n, const void* Aloc_dev, int64_t lda,
                        int64_t* info);
 int b200lu_solve_dist(b200lu_handle* h, int64_t nrhs, const void* B_dev, int64_t ldb,

@@ -32,7 +32,7 @@ SYMBOLS = [
     "b200lu_factor_batched", "b200lu_solve_batched", "b200lu_factor_batched_device",
     "b200lu_solve_batched_device", "b200lu_get_factors_batched",
     "b200lu_solve_batched_trans", "b200lu_solve_batched_trans_device",
-    "b200lu_comm_unique_id", "b200lu_comm_init", "b200lu_dist_local_cols",
+    "b200lu_comm_unique_id", "b200lu_comm_init", "b200lu_dist_local_cols", "b200lu_dist_transport",
     "b200lu_factor_dist", "b200lu_solve_dist", "b200lu_fill_uniform_device",
 ]
 
@@ -88,6 +88,7 @@ def load():
     P("b200lu_comm_unique_id", ci, [vp])
     P("b200lu_comm_init", ci, [vp, vp, ci, ci])
     P("b200lu_dist_local_cols", ci, [vp, i64, pi64])
+    P("b200lu_dist_transport", ci, [vp])
     P("b200lu_factor_dist", ci, [vp, i64, vp, i64, pi64])
     P("b200lu_solve_dist", ci, [vp, i64, vp, i64, vp, i64])
     P("b200lu_fill_uniform_device", ci, [vp, vp, i64, i64, i64, i64, i64, i64, ctypes.c_uint64, cd])
@@ -122,18 +123,23 @@ class Handle:
     """RAII wrapper of a b200lu_handle (freed like the reference frees AMGX
     handles by finalizer, src/extension_algs.jl:1555-1556)."""
 
-    def __init__(self, dtype=F64, device=0):
+    def __init__(self, dtype=F64, device=0, devices=None):
+        """`devices`: a sequence of >= 2 device indices creates ONE handle that drives all of them from
+        this process (b200lu_create with ngpus > 1); otherwise a single-GPU handle on `device`."""
         self.lib = load()
         self.dtype = dtype
         self.np_dtype = _NP[dtype]          # interface element type
         self.factor_dtype = _NPF[dtype]     # element type of the stored factors
         self._h = ctypes.c_void_p()
-        dev = (ctypes.c_int * 1)(device)
-        rc = self.lib.b200lu_create(ctypes.byref(self._h), dtype, 1, dev)
+        devs = [int(d) for d in devices] if devices is not None and len(devices) > 1 else [int(device)]
+        self.ngpus = len(devs)
+        dev = (ctypes.c_int * len(devs))(*devs)
+        rc = self.lib.b200lu_create(ctypes.byref(self._h), dtype, len(devs), dev)
         if rc != 0:
             self._h = None
-            raise B200LUError(rc, "b200lu_create failed: no usable sm_100 CUDA device "
-                                  "(this library has no CPU fallback)")
+            why = ("the devices are not all peers of each other" if rc == 5 else
+                   "no usable sm_100 CUDA device (this library has no CPU fallback)")
+            raise B200LUError(rc, f"b200lu_create(ngpus={len(devs)}) failed: {why}")
         self.n = 0
 
     def close(self):
@@ -261,9 +267,13 @@ class Handle:
         return buf.raw
 
     def comm_init(self, id_bytes: bytes, rank: int, nranks: int):
-        buf = ctypes.create_string_buffer(id_bytes, 128)
+        buf = ctypes.create_string_buffer(id_bytes or b"", 128)
         self._check(self.lib.b200lu_comm_init(self._h, buf, rank, nranks))
         self.rank, self.nranks = rank, nranks
+
+    def dist_transport(self) -> str:
+        """how the factored panel travels between the ranks: 'p2p' (peer stores into mapped windows) or 'nccl'"""
+        return {1: "p2p", 0: "nccl"}.get(int(self.lib.b200lu_dist_transport(self._h)), "none")
 
     def dist_local_cols(self, n: int) -> int:
         out = ctypes.c_int64(0)

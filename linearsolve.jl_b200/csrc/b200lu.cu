@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "batched.cuh"
@@ -29,7 +30,7 @@
 #include "util_kernels.cuh"
 
 namespace b200lu {
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 }
 using namespace b200lu;
 
@@ -39,6 +40,7 @@ using namespace b200lu;
 struct b200lu_handle {
     int dtype = 0;
     int dev = 0;
+    int sms = 148;             // multiprocessors of `dev`
     cudaStream_t s_main = nullptr, s_panel = nullptr, s_copy = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_next = nullptr, ev_h2d = nullptr;
@@ -144,11 +146,32 @@ struct b200lu_handle {
     double prof_flops = 0.0;
     double counters[B200LU_C_COUNT] = {0};
 
-    // distributed (filled by dist.cuh)
-    void* comm = nullptr;  // DistState*
+    // distributed (filled by dist.inc)
+    void* comm = nullptr;  // DistState*: this handle is one rank of a multi-GPU factorization
     int rank = 0, nranks = 1;
     bool factored_dist = false;
+    void* team = nullptr;  // Team*: this handle was created with ngpus > 1 and drives one sub-handle per GPU
 };
+
+// multi-GPU (dist.inc, included at the end of this file)
+static int dist_destroy(b200lu_handle* h);
+static void team_destroy(b200lu_handle* h);
+static int team_create(b200lu_handle** out, int dtype, int ngpus, const int* devices);
+static int team_set_option(b200lu_handle* h, int option, int64_t value);
+static int team_factor(b200lu_handle* h, int64_t n, const void* A_host, int64_t lda, int64_t* ipiv_out, int64_t* info);
+static int team_solve(b200lu_handle* h, char trans, int64_t nrhs, const void* B_host, int64_t ldb, void* X_host, int64_t ldx);
+static int team_get_factors(b200lu_handle* h, void* LU_host, int64_t ldlu);
+static int team_factor_batched(b200lu_handle* h, int64_t batch, int64_t n, const void* A_host, int64_t lda,
+                               int64_t strideA, int64_t* ipiv_out, int64_t* info_out);
+static int team_solve_batched(b200lu_handle* h, bool is_trans_call, char trans, int64_t nrhs, const void* B_host, int64_t ldb,
+                              int64_t strideB, void* X_host, int64_t ldx, int64_t strideX);
+static int team_get_factors_batched(b200lu_handle* h, void* LU_host, int64_t lda, int64_t strideA, int64_t* ipiv_out,
+                                    int64_t* info_out);
+static b200lu_handle* team_first(b200lu_handle* h);
+#define TEAM_ONLY_HOST(h)                                                                                     \
+    if ((h) && (h)->team)                                                                                     \
+        return set_err((h), -1, "a multi-GPU handle (ngpus > 1) takes HOST matrices: use the entry points without _device")
+
 
 static int set_err(b200lu_handle* h, int status, const char* fmt, ...) {
     if (h) {
@@ -240,7 +263,7 @@ static int launch_trsm_cc(b200lu_handle* h, cudaStream_t st, const T* Lp, int64_
 #define TRSM_CASE(R)                                                                             \
     {                                                                                            \
         const size_t smem = (size_t)32 * (R * 32) * sizeof(T);                                   \
-        static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */                                                            \
+        static std::atomic<bool> attr_dev[64]; std::atomic<bool>& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */                                                            \
         if (!attr_set) {                                                                         \
             CU_TRY(h, cudaFuncSetAttribute(trsm_lunit_kernel<T, R, CC, NWARP>,                   \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -276,7 +299,7 @@ static int launch_dgemm_cfg(b200lu_handle* h, cudaStream_t st, int M, int N, int
                             int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc) {
     using Cfg = DgemmCfg<BM, BN, 16, WM, WN, STAGES>;
     auto kern = dgemm_sub_kernel<BM, BN, 16, WM, WN, STAGES, MINB>;
-    static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
+    static std::atomic<bool> attr_dev[64]; std::atomic<bool>& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
     if (!attr_set) {
         CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_set = true;
@@ -303,16 +326,15 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                         CUtensorMapFloatOOBfill);
 static PFN_tmapEncodeTiled get_tmap_encode() {
-    static PFN_tmapEncodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // function-local static: initialised once, thread-safe (handles may live on different host threads)
+    static const PFN_tmapEncodeTiled fn = []() -> PFN_tmapEncodeTiled {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = (PFN_tmapEncodeTiled)p;
-    }
+            return (PFN_tmapEncodeTiled)p;
+        return nullptr;
+    }();
     return fn;
 }
 // 2-D FP32 tensor map: dim0 = rows (contiguous), dim1 = cols (stride ld), 128-byte swizzle
@@ -354,20 +376,19 @@ static int launch_sgemm_tc(b200lu_handle* h, cudaStream_t st, int M, int N, int 
     const int64_t lst = 256;   // both splits are stored K-major with a fixed leading dimension of 256
     split_tf32_transpose_kernel<<<dim3(cdiv(M, 32), cdiv(K, 32)), 256, 0, st>>>(A, lda, Ahi, Alo, lst, M, K);
     LAUNCH_CHECK(h);
-    split_tf32_kernel<<<dim3(cdiv(K, 1024), N), 256, 0, st>>>(B, ldb, Bhi, Blo, lst, K, N);
+    split_tf32_kernel<<<dim3(cdiv(K, 1024), grid_y(N)), 256, 0, st>>>(B, ldb, Bhi, Blo, lst, K, N);
     LAUNCH_CHECK(h);
     CUtensorMap tAhi, tAlo, tBhi, tBlo;
     if ((rc = make_tmap_2d(h, &tAhi, Ahi, K, M, lst, TC_BK, TC_BM))) return rc;
     if ((rc = make_tmap_2d(h, &tAlo, Alo, K, M, lst, TC_BK, TC_BM))) return rc;
     if ((rc = make_tmap_2d(h, &tBhi, Bhi, K, N, lst, TC_BK, TC_BN))) return rc;
     if ((rc = make_tmap_2d(h, &tBlo, Blo, K, N, lst, TC_BK, TC_BN))) return rc;
-    static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
+    static std::atomic<bool> attr_dev[64]; std::atomic<bool>& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
     if (!attr_set) {
         CU_TRY(h, cudaFuncSetAttribute(sgemm3x_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         attr_set = true;
     }
-    static int sms = 0;
-    if (!sms) CU_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->dev));
+    const int sms = h->sms;
     const int ntiles = cdiv(M, TC_BM) * cdiv(N, TC_BN);
     const int tpc = std::max(1, std::min(4, ntiles / (2 * sms)));
     TcGemmParams p{C, ldc, M, N, K, tpc, h->d_deverr};
@@ -441,7 +462,7 @@ template <typename T, int W, int RPT, int NTV = PCL_NT>
 static int launch_panel_cluster_cfg(b200lu_handle* h, cudaStream_t st, PanelArgs<T> p) {
     constexpr int PCL_NT = NTV;   // threads per CTA of this instantiation
     auto kern = panel_cluster_kernel<T, W, RPT, PCL_NT>;
-    static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
+    static std::atomic<bool> attr_dev[64]; std::atomic<bool>& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
     if (!attr_set) {
         CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -720,41 +741,58 @@ static int ensure_meta(b200lu_handle* h, int64_t n) {
     CU_TRY(h, cudaStreamSynchronize(h->s_main));
     int* old_ipiv = h->d_ipiv;
     int* old_perm = h->d_perm;
+    const int64_t old_cap = h->cap_meta;
     h->d_ipiv = nullptr;
     h->d_perm = nullptr;
+    h->cap_meta = 0;   // committed at the end; a failed allocation leaves an empty, consistent handle
     free_dev(h->d_plans);
-    CU_TRY(h, cudaMalloc((void**)&h->d_ipiv, (size_t)n * sizeof(int)));
-    CU_TRY(h, cudaMalloc((void**)&h->d_perm, (size_t)n * sizeof(int)));
-    if (old_ipiv && h->cap_meta > 0) {  // keep a cached factorization's pivots alive
-        CU_TRY(h, cudaMemcpy(h->d_ipiv, old_ipiv, (size_t)h->cap_meta * sizeof(int), cudaMemcpyDeviceToDevice));
-        CU_TRY(h, cudaMemcpy(h->d_perm, old_perm, (size_t)h->cap_meta * sizeof(int), cudaMemcpyDeviceToDevice));
+    h->cap_plans = 0;
+    bool ok = cudaMalloc((void**)&h->d_ipiv, (size_t)n * sizeof(int)) == cudaSuccess &&
+              cudaMalloc((void**)&h->d_perm, (size_t)n * sizeof(int)) == cudaSuccess;
+    if (ok && old_ipiv && old_perm && old_cap > 0) {  // keep a cached factorization's pivots alive
+        ok = cudaMemcpy(h->d_ipiv, old_ipiv, (size_t)old_cap * sizeof(int), cudaMemcpyDeviceToDevice) == cudaSuccess &&
+             cudaMemcpy(h->d_perm, old_perm, (size_t)old_cap * sizeof(int), cudaMemcpyDeviceToDevice) == cudaSuccess;
     }
     free_dev(old_ipiv);
     free_dev(old_perm);
-    h->cap_plans = cdiv(n, 16) + 1;
-    CU_TRY(h, cudaMalloc((void**)&h->d_plans, (size_t)h->cap_plans * sizeof(LaswpPlan)));
-    if (n > h->cap_hipiv) {
+    const int nplans = cdiv(n, 16) + 1;
+    ok = ok && cudaMalloc((void**)&h->d_plans, (size_t)nplans * sizeof(LaswpPlan)) == cudaSuccess;
+    if (ok && n > h->cap_hipiv) {
         if (h->h_ipiv) cudaFreeHost(h->h_ipiv);
-        CU_TRY(h, cudaMallocHost((void**)&h->h_ipiv, (size_t)n * sizeof(long long)));
-        h->cap_hipiv = n;
+        h->h_ipiv = nullptr;
+        h->cap_hipiv = 0;
+        ok = cudaMallocHost((void**)&h->h_ipiv, (size_t)n * sizeof(long long)) == cudaSuccess;
+        if (ok) h->cap_hipiv = n;
     }
+    if (!ok) {
+        const cudaError_t e = cudaGetLastError();
+        h->factored = false;
+        h->factored_dist = false;
+        free_dev(h->d_ipiv);
+        free_dev(h->d_perm);
+        free_dev(h->d_plans);
+        return set_err(h, 1, "CUDA error %s while growing the pivot buffers to n = %lld: %s", cudaGetErrorName(e),
+                       (long long)n, cudaGetErrorString(e));
+    }
+    h->cap_plans = nplans;
     h->cap_meta = n;
     return 0;
 }
 
-static int ensure_capacity(b200lu_handle* h, int64_t n) {
-    int rc = ensure_meta(h, n);
-    if (rc) return rc;
-    if (n <= h->cap_n) {
-        if (n != h->n || h->ldd != ((n + 15) / 16) * 16) {
-            h->n = n;
-            h->ldd = ((n + 15) / 16) * 16;
-            // keep padding rows finite for the 16-byte chunk loads
-            CU_TRY(h, cudaMemsetAsync(h->dA, 0, (size_t)h->ldd * n * elem_size(h), h->s_main));
-        }
-        return 0;
-    }
-    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+// drop every per-size buffer of the dense path and return the handle to the empty state
+static void reset_dense_state(b200lu_handle* h) {
+    h->factored = false;
+    h->solve_ready = false;
+    h->solve_ready_t = false;
+    h->keep_valid = false;
+    h->n = 0;
+    h->ldd = 0;
+    h->cap_n = 0;
+    h->cap_rhs = 0;
+    h->cap_tgroups = 0;
+    h->cap_tflag_bytes = 0;
+    h->t2_nblk = 0;
+    h->t3_nblk = 0;
     free_dev(h->dA);
     free_dev(h->dA64);
     free_dev(h->d_dinvL);
@@ -765,29 +803,55 @@ static int ensure_capacity(b200lu_handle* h, int64_t n) {
     free_dev(h->d_wUt);
     free_dev(h->d_r);
     free_dev(h->d_r32);
-    h->n = n;
-    h->ldd = ((n + 15) / 16) * 16;
-    h->cap_n = n;
-    const size_t es = elem_size(h);
-    CU_TRY(h, cudaMalloc(&h->dA, (size_t)h->ldd * n * es));
-    CU_TRY(h, cudaMemsetAsync(h->dA, 0, (size_t)h->ldd * n * es, h->s_main));
-    if (h->dtype == B200LU_MIXED) {
-        CU_TRY(h, cudaMalloc((void**)&h->dA64, (size_t)h->ldd * n * 8));
-        CU_TRY(h, cudaMalloc((void**)&h->d_r, (size_t)n * 8));
-        CU_TRY(h, cudaMalloc((void**)&h->d_r32, (size_t)n * 4));
-    }
-    const int nblk = cdiv(n, TRSV_TB);
-    CU_TRY(h, cudaMalloc(&h->d_dinvL, (size_t)nblk * TRSV_TB * TRSV_TB * es));
-    CU_TRY(h, cudaMalloc(&h->d_dinvU, (size_t)nblk * TRSV_TB * TRSV_TB * es));
-    CU_TRY(h, cudaMalloc(&h->d_wL, (size_t)TRSV3_NEAR_MAX * nblk * TRSV_TB * TRSV_TB * es));   // coupling planes
-    CU_TRY(h, cudaMalloc(&h->d_wU, (size_t)TRSV3_NEAR_MAX * nblk * TRSV_TB * TRSV_TB * es));
     free_dev(h->d_tflags);
     free_dev(h->d_tticket);
-    h->cap_tgroups = 0;
-    h->cap_tflag_bytes = 0;
-    h->cap_rhs = 0;
     free_dev(h->d_B);
     free_dev(h->d_X);
+}
+
+static int ensure_capacity(b200lu_handle* h, int64_t n) {
+    int rc = ensure_meta(h, n);
+    if (rc) return rc;
+    if (n <= h->cap_n) {
+        if (n != h->n || h->ldd != ((n + 15) / 16) * 16) {
+            h->factored = false;   // the cached factors are about to be overwritten
+            h->solve_ready = false;
+            h->solve_ready_t = false;
+            h->n = n;
+            h->ldd = ((n + 15) / 16) * 16;
+            // keep padding rows finite for the 16-byte chunk loads
+            CU_TRY(h, cudaMemsetAsync(h->dA, 0, (size_t)h->ldd * n * elem_size(h), h->s_main));
+        }
+        return 0;
+    }
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    // growth: from here until every allocation has succeeded the handle is EMPTY (no cached
+    // factorization, zero capacity), so a failed cudaMalloc cannot leave stale state behind
+    // that a later solve / smaller factor call would run on freed or null buffers
+    reset_dense_state(h);
+    const int64_t ldd = ((n + 15) / 16) * 16;
+    const size_t es = elem_size(h);
+    const int nblk = cdiv(n, TRSV_TB);
+    bool ok = cudaMalloc(&h->dA, (size_t)ldd * n * es) == cudaSuccess;
+    if (ok && h->dtype == B200LU_MIXED) {
+        ok = cudaMalloc((void**)&h->dA64, (size_t)ldd * n * 8) == cudaSuccess &&
+             cudaMalloc((void**)&h->d_r, (size_t)n * 8) == cudaSuccess &&
+             cudaMalloc((void**)&h->d_r32, (size_t)n * 4) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc(&h->d_dinvL, (size_t)nblk * TRSV_TB * TRSV_TB * es) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_dinvU, (size_t)nblk * TRSV_TB * TRSV_TB * es) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_wL, (size_t)TRSV3_NEAR_MAX * nblk * TRSV_TB * TRSV_TB * es) == cudaSuccess;   // coupling planes
+    ok = ok && cudaMalloc(&h->d_wU, (size_t)TRSV3_NEAR_MAX * nblk * TRSV_TB * TRSV_TB * es) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(h->dA, 0, (size_t)ldd * n * es, h->s_main) == cudaSuccess;
+    if (!ok) {
+        const cudaError_t e = cudaGetLastError();
+        reset_dense_state(h);
+        return set_err(h, 1, "CUDA error %s while growing the factor buffers to n = %lld: %s", cudaGetErrorName(e),
+                       (long long)n, cudaGetErrorString(e));
+    }
+    h->n = n;
+    h->ldd = ldd;
+    h->cap_n = n;
     return 0;
 }
 
@@ -796,8 +860,15 @@ static int ensure_rhs(b200lu_handle* h, int64_t nrhs) {
     CU_TRY(h, cudaStreamSynchronize(h->s_main));
     free_dev(h->d_B);
     free_dev(h->d_X);
-    CU_TRY(h, cudaMalloc(&h->d_B, (size_t)h->cap_n * nrhs * 8));
-    CU_TRY(h, cudaMalloc(&h->d_X, (size_t)h->cap_n * nrhs * 8));
+    h->cap_rhs = 0;   // committed only when both allocations have succeeded
+    if (cudaMalloc(&h->d_B, (size_t)h->cap_n * nrhs * 8) != cudaSuccess ||
+        cudaMalloc(&h->d_X, (size_t)h->cap_n * nrhs * 8) != cudaSuccess) {
+        const cudaError_t e = cudaGetLastError();
+        free_dev(h->d_B);
+        free_dev(h->d_X);
+        return set_err(h, 1, "CUDA error %s allocating %lld right-hand sides: %s", cudaGetErrorName(e), (long long)nrhs,
+                       cudaGetErrorString(e));
+    }
     h->cap_rhs = nrhs;
     return 0;
 }
@@ -839,7 +910,7 @@ static int trsv3_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const 
     auto kl = trsv3_kernel<T, false, NEAR, CS>;
     auto ku = trsv3_kernel<T, true, NEAR, CS>;
     if (h->t3_ok < 0 || h->t3_nblk != nblk) {
-        static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
+        static std::atomic<bool> attr_dev[64]; std::atomic<bool>& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
         if (!attr_set) {
             CU_TRY(h, cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, trsv3_smem_bytes<T, NEAR>()));
             CU_TRY(h, cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, trsv3_smem_bytes<T, NEAR>()));
@@ -926,7 +997,7 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T
     const int nblk = cdiv(n, TRSV_TB);
     if (!h->solve_ready) {
         const size_t tsm = sizeof(T) * TRSV_TB * (2 * TRSV_TB + 1);
-        static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
+        static std::atomic<bool> attr_dev[64]; std::atomic<bool>& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
         if (!attr_set) {
             CU_TRY(h, cudaFuncSetAttribute(trtri_diag_kernel<T>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
@@ -1052,7 +1123,7 @@ static int trsv_sweeps(b200lu_handle* h, const T* A, int64_t lda, int n, const T
     if (nrhs >= 16 && h->opt[B200LU_OPT_TRSV_MODE] == 0 && n > db && (ldx % 4) == 0 && (n % 4) == 0 &&
         (reinterpret_cast<uintptr_t>(X) % 16) == 0) {   // 16-byte cp.async chunks of the GEMM operands
         // P B -> X (B does not alias X here)
-        perm_gather_kernel<T><<<dim3(cdiv(n, 256), nrhs), 256, 0, st>>>(B, ldb, h->d_perm, X, ldx, n);
+        perm_gather_kernel<T><<<dim3(cdiv(n, 256), grid_y(nrhs)), 256, 0, st>>>(B, ldb, h->d_perm, X, ldx, n, nrhs);
         LAUNCH_CHECK(h);
         const int nd = cdiv(n, db);
         auto diag_solve = [&](int j, bool upper) -> int {
@@ -1169,7 +1240,7 @@ static int refine_solve_block_device(b200lu_handle* h, const double* B, int64_t 
     double* R = (double*)h->d_B;
     float* W32 = (float*)h->d_X;
     float* C32 = W32 + (size_t)ldr * nrhs;
-    const dim3 g2(cdiv(n, 256), nrhs);
+    const dim3 g2(cdiv(n, 256), grid_y(nrhs));
     cast2d_kernel<double, float><<<g2, 256, 0, st>>>(B, ldb, W32, ldr, n, nrhs);
     LAUNCH_CHECK(h);
     rc = getrs_device<float>(h, W32, ldr, C32, ldr, nrhs);
@@ -1184,9 +1255,9 @@ static int refine_solve_block_device(b200lu_handle* h, const double* B, int64_t 
         rc = launch_gemm(h, st, n, nrhs, n, h->dA64, h->ldd, X, ldx, R, ldr);
         if (rc) return rc;
         CU_TRY(h, cudaMemsetAsync(h->d_cscal, 0, (size_t)2 * nrhs * sizeof(double), st));
-        colsumsq_kernel<<<dim3(std::min(cdiv(n, 256), 64), nrhs), 256, 0, st>>>(R, ldr, n, h->d_cscal);
+        colsumsq_kernel<<<dim3(std::min(cdiv(n, 256), 64), grid_y(nrhs)), 256, 0, st>>>(R, ldr, n, h->d_cscal, nrhs);
         LAUNCH_CHECK(h);
-        colsumsq_kernel<<<dim3(std::min(cdiv(n, 256), 64), nrhs), 256, 0, st>>>(X, ldx, n, h->d_cscal + nrhs);
+        colsumsq_kernel<<<dim3(std::min(cdiv(n, 256), 64), grid_y(nrhs)), 256, 0, st>>>(X, ldx, n, h->d_cscal + nrhs, nrhs);
         LAUNCH_CHECK(h);
         CU_TRY(h, cudaMemcpyAsync(h->h_cscal, h->d_cscal, (size_t)2 * nrhs * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU_TRY(h, cudaStreamSynchronize(st));
@@ -1203,7 +1274,7 @@ static int refine_solve_block_device(b200lu_handle* h, const double* B, int64_t 
         LAUNCH_CHECK(h);
         rc = getrs_device<float>(h, W32, ldr, C32, ldr, nrhs);
         if (rc) return rc;
-        axpy_f32_cols_kernel<<<g2, 256, 0, st>>>(X, ldx, C32, ldr, n);
+        axpy_f32_cols_kernel<<<g2, 256, 0, st>>>(X, ldx, C32, ldr, n, nrhs);
         LAUNCH_CHECK(h);
         h->last_refine_iters = std::max(h->last_refine_iters, it + 1);
     }
@@ -1285,12 +1356,13 @@ static int refine_solve_device(b200lu_handle* h, const double* B, int64_t ldb, d
 extern "C" {
 
 int b200lu_version(void) { return B200LU_VERSION; }
-int64_t b200lu_launch_count(void) { return (int64_t)g_launch_count; }
+int64_t b200lu_launch_count(void) { return (int64_t)g_launch_count.load(std::memory_order_relaxed); }
 
 int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices) {
     if (!out) return -1;
     *out = nullptr;
     if (dtype < 0 || dtype > 2) return -2;
+    if (ngpus > 1) return team_create(out, dtype, ngpus, devices);   // one process, ngpus GPUs (dist.inc)
     if (ngpus != 1) return -3;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return 1;  // no CPU fallback
@@ -1303,6 +1375,7 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     b200lu_handle* h = new b200lu_handle();
     h->dtype = dtype;
     h->dev = dev;
+    h->sms = prop.multiProcessorCount;
     h->opt[B200LU_OPT_NB] = 256;
     h->opt[B200LU_OPT_LOOKAHEAD] = 1;
     h->opt[B200LU_OPT_REFINE_MAXIT] = 10;
@@ -1349,7 +1422,13 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
 
 void b200lu_destroy(b200lu_handle* h) {
     if (!h) return;
+    if (h->team) {   // the sub-handles own every device resource
+        team_destroy(h);
+        delete h;
+        return;
+    }
     cudaSetDevice(h->dev);
+    dist_destroy(h);
     if (h->s_main) cudaStreamSynchronize(h->s_main);
     if (h->s_panel) cudaStreamSynchronize(h->s_panel);
     if (h->s_copy) cudaStreamSynchronize(h->s_copy);
@@ -1417,6 +1496,7 @@ double b200lu_last_counter(const b200lu_handle* h, int which) {
 int b200lu_debug_gemm_sub(b200lu_handle* h, int64_t M, int64_t N, int64_t K, const void* dA, int64_t lda,
                           const void* dB, int64_t ldb, void* dC, int64_t ldc) {
     if (!h) return -1;
+    TEAM_ONLY_HOST(h);
     if (M < 0 || N < 0 || K < 0 || !dA || !dB || !dC) return set_err(h, -2, "bad gemm arguments");
     CU_TRY(h, cudaSetDevice(h->dev));
     int rc;
@@ -1434,6 +1514,7 @@ int b200lu_debug_gemm_sub(b200lu_handle* h, int64_t M, int64_t N, int64_t K, con
 
 int b200lu_probe_peak(b200lu_handle* h, int kind, double* out) {
     if (!h || !out) return -1;
+    if (h->team) return b200lu_probe_peak(team_first(h), kind, out);
     CU_TRY(h, cudaSetDevice(h->dev));
     cudaStream_t st = h->s_main;
     int sms = 0;
@@ -1498,6 +1579,7 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_STREAM_H2D && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_MAPPED_RHS && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_KEEP_A && (value < 0 || value > 1)) return -3;
+    if (h->team) return team_set_option(h, option, value);
     h->opt[option] = value;
     return 0;
 }
@@ -1584,6 +1666,7 @@ static int factor_resident(b200lu_handle* h, int64_t n, int64_t* info, int nchun
 int b200lu_factor(b200lu_handle* h, int64_t n, const void* A_host, int64_t lda, int64_t* ipiv_out,
                   int64_t* info) {
     if (!h) return -1;
+    if (h->team) return team_factor(h, n, A_host, lda, ipiv_out, info);
     if (n < 0 || n > 131072) return set_err(h, -2, "n out of range");
     if (!A_host && n > 0) return set_err(h, -3, "A is NULL");
     if (lda < std::max<int64_t>(1, n)) return set_err(h, -4, "lda < max(1,n)");
@@ -1647,6 +1730,7 @@ int b200lu_factor(b200lu_handle* h, int64_t n, const void* A_host, int64_t lda, 
 
 int b200lu_factor_device(b200lu_handle* h, int64_t n, const void* A_dev, int64_t lda, int64_t* info) {
     if (!h) return -1;
+    TEAM_ONLY_HOST(h);
     if (n < 0 || n > 131072) return set_err(h, -2, "n out of range");
     if (!A_dev && n > 0) return set_err(h, -3, "A is NULL");
     if (lda < std::max<int64_t>(1, n)) return set_err(h, -4, "lda < max(1,n)");
@@ -1700,6 +1784,7 @@ static int finish_solve(b200lu_handle* h) {
 
 int b200lu_solve_device(b200lu_handle* h, char trans, int64_t nrhs, const void* B_dev, int64_t ldb,
                         void* X_dev, int64_t ldx) {
+    TEAM_ONLY_HOST(h);
     int rc = check_solve_args(h, trans, nrhs, B_dev, ldb, X_dev, ldx);
     if (rc) return rc;
     if (h->n == 0 || nrhs == 0) return 0;
@@ -1723,6 +1808,7 @@ int b200lu_solve_device(b200lu_handle* h, char trans, int64_t nrhs, const void* 
 
 int b200lu_solve(b200lu_handle* h, char trans, int64_t nrhs, const void* B_host, int64_t ldb,
                  void* X_host, int64_t ldx) {
+    if (h && h->team) return team_solve(h, trans, nrhs, B_host, ldb, X_host, ldx);
     int rc = check_solve_args(h, trans, nrhs, B_host, ldb, X_host, ldx);
     if (rc) return rc;
     if (h->n == 0 || nrhs == 0) return 0;
@@ -1796,6 +1882,7 @@ int b200lu_solve(b200lu_handle* h, char trans, int64_t nrhs, const void* B_host,
 int b200lu_residual_norms(b200lu_handle* h, int64_t nrhs, const void* B_host, int64_t ldb,
                           const void* X_host, int64_t ldx, double* resid_out, double* bnorm_out) {
     if (!h) return -1;
+    if (h->team) return set_err(h, 3, "the residual check on the device needs a single-GPU handle (no copy of A is kept on a multi-GPU handle)");
     if (nrhs < 0) return set_err(h, -2, "nrhs < 0");
     if (!h->factored) return set_err(h, 3, "no factorization cached");
     const bool have_A = (h->dtype == B200LU_MIXED) ? (h->dA64 != nullptr) : h->keep_valid;
@@ -1838,7 +1925,7 @@ int b200lu_residual_norms(b200lu_handle* h, int64_t nrhs, const void* B_host, in
     CU_TRY(h, cudaMemcpy2DAsync(dBs, (size_t)n * is, B_host, (size_t)ldb * is, (size_t)n * is, (size_t)nrhs, cudaMemcpyHostToDevice, st));
     CU_TRY(h, cudaMemcpy2DAsync(dXs, (size_t)n * is, X_host, (size_t)ldx * is, (size_t)n * is, (size_t)nrhs, cudaMemcpyHostToDevice, st));
     CU_TRY(h, cudaEventRecord(h->ev_b, st));
-    const dim3 g2(cdiv(n, 256), (unsigned)nrhs);
+    const dim3 g2(cdiv(n, 256), grid_y(nrhs));
     if (h->dtype == B200LU_F32) {
         cast2d_kernel<float, double><<<g2, 256, 0, st>>>((const float*)dBs, n, R, n, (int)n, (int)nrhs);
         LAUNCH_CHECK(h);
@@ -1849,8 +1936,8 @@ int b200lu_residual_norms(b200lu_handle* h, int64_t nrhs, const void* B_host, in
         CU_TRY(h, cudaMemcpyAsync(X64, dXs, (size_t)n * nrhs * 8, cudaMemcpyDeviceToDevice, st));
     }
     CU_TRY(h, cudaMemsetAsync(h->d_cscal, 0, (size_t)2 * nrhs * sizeof(double), st));
-    const dim3 gn(std::min(cdiv(n, 256), 64), (unsigned)nrhs);
-    colsumsq_kernel<<<gn, 256, 0, st>>>(R, n, (int)n, h->d_cscal + nrhs);     // ||b||^2 before R becomes the residual
+    const dim3 gn(std::min(cdiv(n, 256), 64), grid_y(nrhs));
+    colsumsq_kernel<<<gn, 256, 0, st>>>(R, n, (int)n, h->d_cscal + nrhs, (int)nrhs);     // ||b||^2 before R becomes the residual
     LAUNCH_CHECK(h);
     const int cchunk = 512;
     for (int64_t c = 0; c < nrhs; ++c) {
@@ -1863,7 +1950,7 @@ int b200lu_residual_norms(b200lu_handle* h, int64_t nrhs, const void* B_host, in
             residual_gemv_kernel<double><<<gr, 256, 0, st>>>(h->dA64, h->ldd, (int)n, X64 + c * n, R + c * n, cchunk);
         LAUNCH_CHECK(h);
     }
-    colsumsq_kernel<<<gn, 256, 0, st>>>(R, n, (int)n, h->d_cscal);
+    colsumsq_kernel<<<gn, 256, 0, st>>>(R, n, (int)n, h->d_cscal, (int)nrhs);
     LAUNCH_CHECK(h);
     CU_TRY(h, cudaEventRecord(h->ev_c, st));
     CU_TRY(h, cudaMemcpyAsync(h->h_cscal, h->d_cscal, (size_t)2 * nrhs * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1882,6 +1969,7 @@ int b200lu_residual_norms(b200lu_handle* h, int64_t nrhs, const void* B_host, in
 
 int b200lu_get_factors(b200lu_handle* h, void* LU_host, int64_t ldlu) {
     if (!h) return -1;
+    if (h->team) return team_get_factors(h, LU_host, ldlu);
     if (!h->factored) return set_err(h, 3, "no factorization cached");
     if (!LU_host) return set_err(h, -2, "LU is NULL");
     if (ldlu < h->n) return set_err(h, -3, "ldlu < n");
@@ -1896,7 +1984,13 @@ int b200lu_get_factors(b200lu_handle* h, void* LU_host, int64_t ldlu) {
 
 int b200lu_get_ipiv(b200lu_handle* h, int64_t* ipiv_out) {
     if (!h) return -1;
-    if (!h->factored) return set_err(h, 3, "no factorization cached");
+    if (h->team) {
+        if (!h->factored) return set_err(h, 3, "no factorization cached");
+        b200lu_handle* s0 = team_first(h);
+        const int rc = b200lu_get_ipiv(s0, ipiv_out);
+        return rc ? set_err(h, rc, "%s", s0->err) : 0;
+    }
+    if (!h->factored && !h->factored_dist) return set_err(h, 3, "no factorization cached");
     if (!ipiv_out) return set_err(h, -2, "ipiv is NULL");
     if (h->n == 0) return 0;
     CU_TRY(h, cudaSetDevice(h->dev));
@@ -1963,7 +2057,7 @@ static int batched_factor_launch(b200lu_handle* h, const T* A, int64_t lda, int6
     if (n > 64) {
         // 65 ... BATCHED_SMEM_NMAX rows: the system lives in shared memory, one CTA each
         const size_t smem = (size_t)n * (n | 1) * sizeof(T);
-        static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
+        static std::atomic<bool> attr_dev[64]; std::atomic<bool>& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
         if (!attr_set) {
             CU_TRY(h, cudaFuncSetAttribute(getrf_batched_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)((size_t)BATCHED_SMEM_NMAX * (BATCHED_SMEM_NMAX | 1) * sizeof(T))));
@@ -1992,7 +2086,7 @@ static int batched_solve_launch(b200lu_handle* h, int nrhs, const T* B, int64_t 
     {                                                                                             \
         const unsigned grid = (unsigned)((batch + (WPCV) - 1) / (WPCV));                           \
         if ((NMAXV) > 64) {   /* more than 48 KB of dynamic shared memory: opt in once */          \
-            static bool attr_dev[64] = {}; bool& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */                                                         \
+            static std::atomic<bool> attr_dev[64]; std::atomic<bool>& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */                                                         \
             if (!attr_set) {                                                                      \
                 CU_TRY(h, cudaFuncSetAttribute(getrs_batched_kernel<T, NMAXV, WPCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                (int)((size_t)(WPCV) * (NMAXV) * (NMAXV) * sizeof(T)))); \
@@ -2039,6 +2133,7 @@ static int check_batched_args(b200lu_handle* h, int64_t batch, int64_t n, const 
 
 int b200lu_factor_batched_device(b200lu_handle* h, int64_t batch, int64_t n, const void* A_dev,
                                  int64_t lda, int64_t strideA, int64_t* any_info) {
+    TEAM_ONLY_HOST(h);
     int rc = check_batched_args(h, batch, n, A_dev, lda, strideA);
     if (rc) return rc;
     if (any_info) *any_info = 0;
@@ -2103,12 +2198,14 @@ static int solve_batched_device_impl(b200lu_handle* h, bool trans, int64_t nrhs,
 int b200lu_solve_batched_device(b200lu_handle* h, int64_t nrhs, const void* B_dev, int64_t ldb,
                                 int64_t strideB, void* X_dev, int64_t ldx, int64_t strideX) {
     if (!h) return -1;
+    TEAM_ONLY_HOST(h);
     return solve_batched_device_impl(h, false, nrhs, B_dev, ldb, strideB, X_dev, ldx, strideX);
 }
 
 int b200lu_solve_batched_trans_device(b200lu_handle* h, char trans, int64_t nrhs, const void* B_dev, int64_t ldb,
                                       int64_t strideB, void* X_dev, int64_t ldx, int64_t strideX) {
     if (!h) return -1;
+    TEAM_ONLY_HOST(h);
     bool tr = false;
     int rc = parse_trans(h, trans, &tr);
     if (rc) return rc;
@@ -2117,6 +2214,7 @@ int b200lu_solve_batched_trans_device(b200lu_handle* h, char trans, int64_t nrhs
 
 int b200lu_factor_batched(b200lu_handle* h, int64_t batch, int64_t n, const void* A_host, int64_t lda,
                           int64_t strideA, int64_t* ipiv_out, int64_t* info_out) {
+    if (h && h->team) return team_factor_batched(h, batch, n, A_host, lda, strideA, ipiv_out, info_out);
     int rc = check_batched_args(h, batch, n, A_host, lda, strideA);
     if (rc) return rc;
     h->b_factored = false;
@@ -2152,6 +2250,7 @@ int b200lu_factor_batched(b200lu_handle* h, int64_t batch, int64_t n, const void
 int b200lu_get_factors_batched(b200lu_handle* h, void* LU_host, int64_t lda, int64_t strideA,
                                int64_t* ipiv_out, int64_t* info_out) {
     if (!h) return -1;
+    if (h->team) return team_get_factors_batched(h, LU_host, lda, strideA, ipiv_out, info_out);
     if (!h->b_factored) return set_err(h, 3, "no batched factorization cached");
     const int64_t batch = h->b_batch, n = h->b_n;
     if (batch == 0 || n == 0) return 0;
@@ -2238,12 +2337,14 @@ static int solve_batched_impl(b200lu_handle* h, bool trans, int64_t nrhs, const 
 int b200lu_solve_batched(b200lu_handle* h, int64_t nrhs, const void* B_host, int64_t ldb,
                          int64_t strideB, void* X_host, int64_t ldx, int64_t strideX) {
     if (!h) return -1;
+    if (h->team) return team_solve_batched(h, false, 'N', nrhs, B_host, ldb, strideB, X_host, ldx, strideX);
     return solve_batched_impl(h, false, nrhs, B_host, ldb, strideB, X_host, ldx, strideX);
 }
 
 int b200lu_solve_batched_trans(b200lu_handle* h, char trans, int64_t nrhs, const void* B_host, int64_t ldb,
                                int64_t strideB, void* X_host, int64_t ldx, int64_t strideX) {
     if (!h) return -1;
+    if (h->team) return team_solve_batched(h, true, trans, nrhs, B_host, ldb, strideB, X_host, ldx, strideX);
     bool tr = false;
     int rc = parse_trans(h, trans, &tr);
     if (rc) return rc;
@@ -2255,6 +2356,7 @@ int b200lu_fill_uniform_device(b200lu_handle* h, void* A_dev, int64_t lda, int64
                                int64_t first_global_col, int64_t col_block, int64_t col_block_stride,
                                uint64_t seed, double diag_shift) {
     if (!h) return -1;
+    TEAM_ONLY_HOST(h);
     if (!A_dev || lda < n || n <= 0 || ncols <= 0 || col_block <= 0) return set_err(h, -2, "bad fill arguments");
     CU_TRY(h, cudaSetDevice(h->dev));
     dim3 grid(cdiv(n, 256), (unsigned)std::min<int64_t>(ncols, 4096));

@@ -64,7 +64,10 @@ __global__ void __launch_bounds__(batched_threads(NMAX)) getrf_batched_kernel(
     {                                                                                              \
         const int par = k & 1;                                                                     \
         /* pivot search: |a| max over the rows not yet used, lowest position on ties */            \
-        const T v = done ? T(0) : tabs(a[0]);                                                      \
+        /* zeros AND NaNs are no candidates (key 0): the redux works on bit patterns, where a NaN */ \
+        /* would be the largest key and then fail the v > 0 test for the whole warp              */ \
+        const T av_ = tabs(a[0]);                                                                  \
+        const T v = (done || !(av_ > T(0))) ? T(0) : av_;                                          \
         const int wl = pcl_warp_argmax(v, pos);                                                    \
         if (lane == wl) {                                                                          \
             if (NW == 1) {                                                                         \

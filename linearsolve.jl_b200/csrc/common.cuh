@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "b200lu kernels are written for sm_100a (B200) only"
 #endif
@@ -10,8 +12,8 @@
 namespace b200lu {
 
 // Global launch counter (bench reports gpu_launches from it).
-extern unsigned long long g_launch_count;
-#define B200LU_COUNT_LAUNCH() (++::b200lu::g_launch_count)
+extern std::atomic<unsigned long long> g_launch_count;   // handles on different host threads count concurrently
+#define B200LU_COUNT_LAUNCH() (::b200lu::g_launch_count.fetch_add(1, std::memory_order_relaxed))
 
 // ---- error word written by device code (spin-wait watchdogs etc.) ----------
 enum DevErr : int {
@@ -19,6 +21,7 @@ enum DevErr : int {
     DEV_ERR_PANEL_TIMEOUT = 1,
     DEV_ERR_TRSV_TIMEOUT = 2,
     DEV_ERR_GEMM_TIMEOUT = 3,
+    DEV_ERR_PEER_TIMEOUT = 4,   // a peer GPU's panel / right-hand side never arrived
 };
 
 // ~2 s at 1.9 GHz: a spin loop that runs this long means a lost CTA, not work.

@@ -50,8 +50,9 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
                                                          float* __restrict__ hi, float* __restrict__ lo,
                                                          long long ldd, int rows, int cols) {
     const int r4 = (blockIdx.x * 256 + threadIdx.x) * 4;
-    const int c = blockIdx.y;
-    if (r4 >= rows || c >= cols) return;
+    if (r4 >= rows) return;
+    // columns are strided over gridDim.y: the launcher clamps it to the 65535 limit of the y dimension
+    for (int c = blockIdx.y; c < cols; c += gridDim.y) {
     const float* s = src + (long long)c * lds + r4;
     float x[4];
     if (r4 + 3 < rows && ((reinterpret_cast<uintptr_t>(s) & 15) == 0)) {
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             if (r4 + i < rows) { ph[i] = h[i]; pl[i] = l[i]; }
+    }
     }
 }
 

@@ -104,10 +104,11 @@ __global__ void __launch_bounds__(256) trsv_coupling_kernel(const T* __restrict_
 // X[i, c] = B[perm[i], c]: the row interchanges of getrs applied to a block of right-hand sides
 template <typename T>
 __global__ void perm_gather_kernel(const T* __restrict__ B, long long ldb, const int* __restrict__ perm,
-                                   T* __restrict__ X, long long ldx, int n) {
+                                   T* __restrict__ X, long long ldx, int n, int nrhs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const long long c = blockIdx.y;
-    if (i < n) X[c * ldx + i] = B[c * ldb + perm[i]];
+    if (i >= n) return;
+    const int src = perm[i];
+    for (long long c = blockIdx.y; c < nrhs; c += gridDim.y) X[c * ldx + i] = B[c * ldb + src];
 }
 
 // x[perm[i]] = z[i]: the row interchanges of a transposed solve (A^T = U^T L^T P)

@@ -8,6 +8,10 @@
 
 namespace b200lu {
 
+// gridDim.y carries a column index in several kernels here: the hardware limit of that dimension is
+// 65535, so launchers clamp it and the kernels stride over the columns
+inline unsigned grid_y(long long cols) { return (unsigned)(cols < 1 ? 1 : (cols > 32768 ? 32768 : cols)); }
+
 __global__ void iota_kernel(int* p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;
@@ -58,23 +62,24 @@ __global__ void sumsq2d_kernel(const double* __restrict__ A, long long lda, int 
 
 // x += (double) d
 // per-column sums of squares of an n x ncols block: out[c] += sum_i A[i, c]^2
-__global__ void colsumsq_kernel(const double* __restrict__ A, long long lda, int n, double* __restrict__ out) {
-    const int c = blockIdx.y;
-    double s = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double v = A[(long long)c * lda + i];
-        s = fma(v, v, s);
-    }
+__global__ void colsumsq_kernel(const double* __restrict__ A, long long lda, int n, double* __restrict__ out, int ncols) {
+    for (int c = blockIdx.y; c < ncols; c += gridDim.y) {   // gridDim.y is clamped by grid_y()
+        double s = 0.0;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const double v = A[(long long)c * lda + i];
+            s = fma(v, v, s);
+        }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if ((threadIdx.x & 31) == 0) atomicAdd(out + c, s);
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if ((threadIdx.x & 31) == 0) atomicAdd(out + c, s);
+    }
 }
 
 // X[:, c] += double(D[:, c]) for an n x ncols block
-__global__ void axpy_f32_cols_kernel(double* __restrict__ X, long long ldx, const float* __restrict__ D, long long ldd, int n) {
+__global__ void axpy_f32_cols_kernel(double* __restrict__ X, long long ldx, const float* __restrict__ D, long long ldd, int n, int ncols) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const long long c = blockIdx.y;
-    if (i < n) X[c * ldx + i] += (double)D[c * ldd + i];
+    if (i >= n) return;
+    for (long long c = blockIdx.y; c < ncols; c += gridDim.y) X[c * ldx + i] += (double)D[c * ldd + i];
 }
 
 __global__ void axpy_f32_kernel(double* __restrict__ x, const float* __restrict__ d, int n) {

@@ -12,7 +12,7 @@ Mirrored (reference file:line):
   LinearCache + `cache.A =` / `cache.b =`        src/common.jl:281-306,313-360
   solve!(cache) / solve(prob, alg)               src/common.jl:966-1017
   reinit!(cache; A, b)                           src/common.jl:933-964
-  ReturnCode.Success / Failure                   src/factorization.jl:714-722
+  ReturnCode.Success / Failure / APosterioriSafetyFailure   src/factorization.jl:714-722,150-153
   B200LUFactorization <: AbstractFactorization   (new; shaped like CudaOffloadLUFactorization,
                                                   src/extension_algs.jl:344-354, and the solve!
                                                   protocol of OpenBLASLUFactorization,
@@ -33,9 +33,13 @@ from . import _capi
 
 
 class ReturnCode(enum.Enum):
+    """the members of SciMLBase.ReturnCode this path produces"""
     Default = 0
     Success = 1
     Failure = 2
+    # the a-posteriori residual check failed (src/factorization.jl:150-153); the default solver
+    # treats it like Failure and runs its QR fallback (src/default.jl:946-969)
+    APosterioriSafetyFailure = 3
 
 
 def successful_retcode(sol) -> bool:
@@ -81,12 +85,19 @@ class B200LUFactorization(AbstractFactorization):
     _dtype_code = {np.dtype(np.float64): _capi.F64, np.dtype(np.float32): _capi.F32}
 
     def __init__(self, throwerror: bool = True, residualsafety: bool = False, device: int = 0,
-                 nb: int | None = None, lookahead: bool | None = None):
+                 nb: int | None = None, lookahead: bool | None = None, devices=None):
+        """`devices = (0, 1, ..., 7)`: ONE cache drives all these GPUs from this process (Julia:
+        `B200LUFactorization(; devices = 0:7)`): a dense A is factored 1-D block-cyclic over them, the
+        blocks of a BlockDiagonal are sharded over them.  Float32/Float64; `solve!(cache; adjoint = true)`
+        and `residualsafety` need the single-GPU handle."""
         if throwerror and not useb200():
             raise RuntimeError("B200LUFactorization requires libb200lu.so and a B200 (sm_100) GPU; "
                                "there is no CPU fallback")
         self.residualsafety = residualsafety
         self.device = device
+        self.devices = tuple(int(d) for d in devices) if devices is not None and len(devices) > 1 else None
+        if self.devices is not None and residualsafety:
+            raise ValueError("residualsafety needs the single-GPU handle (the multi-GPU handle keeps no copy of A)")
         self.nb = nb
         self.lookahead = lookahead
 
@@ -110,6 +121,8 @@ class B200LU32MixedLUFactorization(B200LUFactorization):
     def handle_dtype(self, eltype):
         if np.dtype(eltype) != np.float64:
             raise TypeError("B200LU32MixedLUFactorization expects a Float64 problem")
+        if self.devices is not None:
+            raise TypeError("B200LU32MixedLUFactorization runs on one GPU")
         return _capi.MIXED
 
 
@@ -313,7 +326,7 @@ def _factor_blockdiag(cache, alg):
     if cv.groups is None or cv.group_sizes != (sizes, dt):
         cv.groups = []
         for kind, idx, m in plan_blockdiag(sizes):
-            h = _capi.Handle(dt, alg.device)
+            h = _capi.Handle(dt, alg.device, devices=alg.devices if kind == "batched" else None)
             _configure(h, alg)
             cv.groups.append((kind, h, idx, m))
         cv.group_sizes = (sizes, dt)
@@ -385,6 +398,8 @@ def solve_(cache: LinearCache, alg=None, adjoint: bool = False) -> LinearSolutio
     alg = alg or cache.alg
     cv = cache.cacheval
     A = cache.A
+    if adjoint and getattr(alg, "devices", None) is not None:
+        raise NotImplementedError("solve!(cache; adjoint = true) needs the single-GPU handle")
     check_safety = alg.residualsafety and cache.isfresh
     if cache.isfresh:
         if isinstance(A, BlockDiagonal):
@@ -392,7 +407,7 @@ def solve_(cache: LinearCache, alg=None, adjoint: bool = False) -> LinearSolutio
         else:
             A = np.asarray(A)
             if cv.handle is None or cv.handle.dtype != alg.handle_dtype(A.dtype):
-                cv.handle = _capi.Handle(alg.handle_dtype(A.dtype), alg.device)
+                cv.handle = _capi.Handle(alg.handle_dtype(A.dtype), alg.device, devices=alg.devices)
                 _configure(cv.handle, alg)
             cv.ipiv, info = cv.handle.factor(A)
             cv.info = info
@@ -417,7 +432,9 @@ def solve_(cache: LinearCache, alg=None, adjoint: bool = False) -> LinearSolutio
     if adjoint:
         return LinearSolution(cache.u, ReturnCode.Success, alg)
     if check_safety and not _check_residual_safety(cache, A, cache.u):
-        return LinearSolution(cache.u, ReturnCode.Failure, alg)
+        if cache.verbose:
+            print("Residual safety check failed")   # @SciMLMessage(cache.verbose, :residual_safety)
+        return LinearSolution(cache.u, ReturnCode.APosterioriSafetyFailure, alg)
     return LinearSolution(cache.u, ReturnCode.Success, alg)
 
 

@@ -237,9 +237,10 @@ function SciMLBase.solve!(
         # the device from the copy of A the handle kept (B200LU_OPT_KEEP_A, set in
         # _b200lu_ensure_handle! when alg.residualsafety): 0.18 ms at n = 8192 instead of a host GEMV
         if !_b200lu_residual_ok(cacheval, cache.u, cache.b, cache.abstol, cache.reltol)
+            @SciMLMessage("Residual safety check failed", cache.verbose, :residual_safety)
             return SciMLBase.build_linear_solution(
-                alg, cache.u, nothing, nothing; retcode = ReturnCode.Failure
-            )
+                alg, cache.u, nothing, nothing; retcode = ReturnCode.APosterioriSafetyFailure
+            )                                   # as `_check_residual_safety`, src/factorization.jl:150-153
         end
     end
     return SciMLBase.build_linear_solution(

@@ -214,7 +214,7 @@ def test_residualsafety_on_device(gpu_required, ls):
                 assert cache.cacheval.handle.get_option(ls._capi.OPT_KEEP_A) == 1
             # an impossible tolerance turns the same solve into a Failure (the check is really evaluated)
             strict = ls.init(ls.LinearProblem(A, b), alg, abstol=0.0, reltol=1e-300)
-            assert ls.solve_(strict).retcode == ls.ReturnCode.Failure
+            assert ls.solve_(strict).retcode == ls.ReturnCode.APosterioriSafetyFailure
     # BlockDiagonal: block-by-block check
     blocks = [rng.random((k, k)) + k * np.eye(k) for k in (3, 70, 20)]
     bd = ls.BlockDiagonal(blocks)

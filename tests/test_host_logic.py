@@ -59,7 +59,10 @@ def test_bad_arguments_do_not_need_a_device(ls):
     lib = ls._capi.load()
     h = ctypes.c_void_p()
     assert lib.b200lu_create(ctypes.byref(h), 7, 1, None) == -2       # bad dtype
-    assert lib.b200lu_create(ctypes.byref(h), 0, 3, None) == -3       # ngpus != 1 per process
+    assert lib.b200lu_create(ctypes.byref(h), 0, 0, None) == -3       # ngpus out of range
+    assert lib.b200lu_create(ctypes.byref(h), 0, 17, None) == -3      # at most 16 GPUs behind one handle
+    assert lib.b200lu_create(ctypes.byref(h), 2, 2, None) == -2       # MIXED has no multi-GPU handle
+    assert lib.b200lu_create(ctypes.byref(h), 0, 3, None) == 1        # ngpus > 1 needs that many devices (none here)
     assert lib.b200lu_create(None, 0, 1, None) == -1
     assert lib.b200lu_last_timing(None, 0) == -1.0
     assert lib.b200lu_set_option(None, 0, 64) == -1
@@ -267,8 +270,9 @@ class _OracleHandle:
     infrastructure only — the product has no such path."""
     created = 0
 
-    def __init__(self, dtype=0, device=0):
+    def __init__(self, dtype=0, device=0, devices=None):
         type(self).created += 1
+        self.devices = devices
         self.dtype, self.np_dtype, self.n = dtype, np.float64, 0
         self.options = {}
 
@@ -375,7 +379,7 @@ def test_dense_solve_protocol_with_oracle_backend(ls, monkeypatch):
     cache.A = A
     assert ls.solve_(cache).retcode == ls.ReturnCode.Success
     strict = ls.init(ls.LinearProblem(A, b), alg, abstol=0.0, reltol=1e-300)
-    assert ls.solve_(strict).retcode == ls.ReturnCode.Failure   # the residual check is evaluated
+    assert ls.solve_(strict).retcode == ls.ReturnCode.APosterioriSafetyFailure   # src/factorization.jl:150-153
     mixed = ls.B200LU32MixedLUFactorization(throwerror=False, refine=False)
     cm = ls.init(ls.LinearProblem(A, b), mixed)
     assert ls.solve_(cm).retcode == ls.ReturnCode.Success
