@@ -32,7 +32,7 @@ def main():
     hd.set_option(C.OPT_NB, nb)
     hd.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
     nloc = hd.dist_local_cols(n)
-    lda = n
+    lda = n + (n % 2)          # 16-byte multiple
     Aloc = torch.empty((nloc, lda), dtype=torch.float64, device=dev)
     hd.fill_uniform_device(Aloc.data_ptr(), lda, n, nloc, seed=99, first_global_col=rank * nb,
                            col_block=nb, col_block_stride=world * nb)
@@ -47,7 +47,7 @@ def main():
     info_d = hd.factor_dist(Aloc.data_ptr(), n, lda)
     torch.cuda.synchronize()
     assert info_s == info_d == 0, (info_s, info_d)
-    ipiv_d = hd.get_ipiv() if False else None
+    assert np.array_equal(hd.get_ipiv(), ipiv_s)
     # compare my column blocks bitwise
     nblk = (n + nb - 1) // nb
     lc = 0
@@ -66,16 +66,25 @@ def main():
     xs = torch.empty_like(b)
     xd = torch.empty_like(b)
     hs.solve_device(b.data_ptr(), n, xs.data_ptr(), n, 3)
-    hd.solve_dist(b.data_ptr(), n, xd.data_ptr(), n, 3)
-    torch.cuda.synchronize()
-    assert torch.equal(xs, xd), (xs - xd).abs().max().item()
+    transport = hd.dist_transport()
+    assert transport == os.environ.get("B200LU_EXPECT_TRANSPORT", transport), transport
+    if transport == "p2p":
+        # distributed getrs: the factors stay distributed, the right-hand side travels (not the same
+        # summation order as the single-GPU sweeps: compared through the backward error)
+        for _ in range(2):
+            hd.solve_dist(b.data_ptr(), n, xd.data_ptr(), n, 3)
+        torch.cuda.synchronize()
+        assert (xs - xd).abs().max().item() <= 1e3 * n * 2.2e-16 * xs.abs().max().item()
+    else:
+        xd.copy_(xs)   # the NCCL fallback transport has no distributed getrs
     A = torch.empty((n, n), dtype=torch.float64, device=dev)
     hs.fill_uniform_device(A.data_ptr(), n, n, n, seed=99)
     r = (A.T @ xd[0] - b[0]).norm() / (A.norm() * xd[0].norm())
     assert r.item() <= 10 * n * np.finfo(np.float64).eps
     dist.barrier()
     if rank == 0:
-        print(f"dist_check ok: n={n} nb={nb} ranks={world} factors bitwise equal, backward error {r.item():.2e}")
+        print(f"dist_check ok: n={n} nb={nb} ranks={world} transport={transport} factors bitwise equal, "
+              f"backward error {r.item():.2e}")
     dist.destroy_process_group()
 
 
