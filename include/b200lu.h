@@ -124,7 +124,10 @@ enum {
                                    is no longer streamed under the factorization) so that
                                    b200lu_residual_norms can check a solution on the device; default 0.
                                    MIXED handles always hold A in FP64.                              */
-    B200LU_OPT_COUNT = 14
+    B200LU_OPT_BATCHED_MODE = 14, /* batched getrf of systems of <= 64 rows: 0 (default) = one WARP per system, the
+                                   system in shared memory, 8-column register panels (and b200lu_factor_solve_batched
+                                   fuses the first getrs into it); 1 = the round-1 kernel, one row per thread    */
+    B200LU_OPT_COUNT = 15
 };
 
 /* library/ABI version: major*10000 + minor*100 + patch */
@@ -240,6 +243,19 @@ int b200lu_solve_batched_device(b200lu_handle* h, int64_t nrhs,
 int b200lu_solve_batched_trans_device(b200lu_handle* h, char trans, int64_t nrhs,
                                       const void* B_dev, int64_t ldb, int64_t strideB,
                                       void* X_dev, int64_t ldx, int64_t strideX);
+/* getrf of the batch AND getrs of one right-hand side per system (B: n values per system at
+ * B + i*strideB, X likewise) in the SAME kernel for n <= 64 — what `solve!` on a fresh BlockDiagonal
+ * cache does (per-block lu! followed by per-block ldiv!, ext/LinearSolveBlockDiagonalsExt.jl:119-125,
+ * 183-205): A is read once, the factors are written once and stay cached for later
+ * b200lu_solve_batched calls. */
+int b200lu_factor_solve_batched(b200lu_handle* h, int64_t batch, int64_t n,
+                                const void* A_host, int64_t lda, int64_t strideA,
+                                const void* B_host, int64_t strideB, void* X_host, int64_t strideX,
+                                int64_t* ipiv_out, int64_t* info_out);
+int b200lu_factor_solve_batched_device(b200lu_handle* h, int64_t batch, int64_t n,
+                                       const void* A_dev, int64_t lda, int64_t strideA,
+                                       const void* B_dev, int64_t strideB, void* X_dev, int64_t strideX,
+                                       int64_t* any_info);
 int b200lu_get_factors_batched(b200lu_handle* h, void* LU_host, int64_t lda,
                                int64_t strideA, int64_t* ipiv_out, int64_t* info_out);
 

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libb200lu.so")
 
 F64, F32, MIXED = 0, 1, 2
 T_H2D, T_FACTOR, T_SOLVE, T_D2H, T_GEMM = range(5)
-OPT_NB, OPT_LOOKAHEAD, OPT_REFINE_MAXIT, OPT_PANEL_CTAS, OPT_SOLVE_NRHS_TILE, OPT_PROFILE, OPT_PANEL_RPT, OPT_GEMM_CFG, OPT_PANEL_MODE, OPT_SGEMM_MODE, OPT_TRSV_MODE, OPT_STREAM_H2D, OPT_MAPPED_RHS, OPT_KEEP_A = range(14)
+OPT_NB, OPT_LOOKAHEAD, OPT_REFINE_MAXIT, OPT_PANEL_CTAS, OPT_SOLVE_NRHS_TILE, OPT_PROFILE, OPT_PANEL_RPT, OPT_GEMM_CFG, OPT_PANEL_MODE, OPT_SGEMM_MODE, OPT_TRSV_MODE, OPT_STREAM_H2D, OPT_MAPPED_RHS, OPT_KEEP_A, OPT_BATCHED_MODE = range(15)
 C_GEMM_FLOPS, C_GEMM_LAUNCHES, C_REFINE_ITERS = range(3)
 PEAK_FP64_DMMA, PEAK_FP64_DFMA, PEAK_HBM_COPY = range(3)
 
@@ -32,6 +32,7 @@ SYMBOLS = [
     "b200lu_factor_batched", "b200lu_solve_batched", "b200lu_factor_batched_device",
     "b200lu_solve_batched_device", "b200lu_get_factors_batched",
     "b200lu_solve_batched_trans", "b200lu_solve_batched_trans_device",
+    "b200lu_factor_solve_batched", "b200lu_factor_solve_batched_device",
     "b200lu_comm_unique_id", "b200lu_comm_init", "b200lu_dist_local_cols", "b200lu_dist_transport",
     "b200lu_factor_dist", "b200lu_solve_dist", "b200lu_fill_uniform_device",
 ]
@@ -85,6 +86,8 @@ def load():
     P("b200lu_solve_batched_trans", ci, [vp, ctypes.c_char, i64, vp, i64, i64, vp, i64, i64])
     P("b200lu_solve_batched_trans_device", ci, [vp, ctypes.c_char, i64, vp, i64, i64, vp, i64, i64])
     P("b200lu_get_factors_batched", ci, [vp, vp, i64, i64, vp, vp])
+    P("b200lu_factor_solve_batched", ci, [vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, vp, vp])
+    P("b200lu_factor_solve_batched_device", ci, [vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, pi64])
     P("b200lu_comm_unique_id", ci, [vp])
     P("b200lu_comm_init", ci, [vp, vp, ci, ci])
     P("b200lu_dist_local_cols", ci, [vp, i64, pi64])
@@ -305,6 +308,31 @@ class Handle:
                                                    ipiv.ctypes.data, info.ctypes.data))
         self.b_batch, self.b_n = batch, n
         return ipiv, info
+
+    def factor_solve_batched(self, A, b):
+        """getrf of every system AND getrs of its right-hand side b[s] in one kernel (n <= 64); the
+        factors stay cached.  A: (batch, n, n) column-major per system, b: (batch, n).  Returns (x, ipiv, info)."""
+        A = np.ascontiguousarray(A)
+        b = np.ascontiguousarray(b)
+        if A.dtype != self.np_dtype or b.dtype != self.np_dtype:
+            raise TypeError(f"expected {self.np_dtype}, got {A.dtype} / {b.dtype}")
+        batch, n, n2 = A.shape
+        assert n == n2 and b.shape == (batch, n)
+        ipiv = np.zeros((batch, n), dtype=np.int64)
+        info = np.zeros(batch, dtype=np.int64)
+        x = np.empty_like(b)
+        self._check(self.lib.b200lu_factor_solve_batched(self._h, batch, n, A.ctypes.data, n, n * n, b.ctypes.data, n,
+                                                         x.ctypes.data, n, ipiv.ctypes.data, info.ctypes.data))
+        self.b_batch, self.b_n = batch, n
+        return x, ipiv, info
+
+    def factor_solve_batched_device(self, a_ptr, b_ptr, x_ptr, batch, n):
+        bad = ctypes.c_int64(0)
+        self._check(self.lib.b200lu_factor_solve_batched_device(self._h, batch, n, ctypes.c_void_p(a_ptr), n, n * n,
+                                                                ctypes.c_void_p(b_ptr), n, ctypes.c_void_p(x_ptr), n,
+                                                                ctypes.byref(bad)))
+        self.b_batch, self.b_n = batch, n
+        return int(bad.value)
 
     def solve_batched(self, B, trans="N"):
         """B: (batch, n) or (batch, nrhs, n) (each right-hand side contiguous).

@@ -167,6 +167,9 @@ static int team_solve_batched(b200lu_handle* h, bool is_trans_call, char trans, 
                               int64_t strideB, void* X_host, int64_t ldx, int64_t strideX);
 static int team_get_factors_batched(b200lu_handle* h, void* LU_host, int64_t lda, int64_t strideA, int64_t* ipiv_out,
                                     int64_t* info_out);
+static int team_factor_solve_batched(b200lu_handle* h, int64_t batch, int64_t n, const void* A_host, int64_t lda, int64_t strideA,
+                                     const void* B_host, int64_t strideB, void* X_host, int64_t strideX, int64_t* ipiv_out,
+                                     int64_t* info_out);
 static b200lu_handle* team_first(b200lu_handle* h);
 #define TEAM_ONLY_HOST(h)                                                                                     \
     if ((h) && (h)->team)                                                                                     \
@@ -1390,6 +1393,7 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     h->opt[B200LU_OPT_STREAM_H2D] = 1;
     h->opt[B200LU_OPT_MAPPED_RHS] = 1;
     h->opt[B200LU_OPT_KEEP_A] = 0;
+    h->opt[B200LU_OPT_BATCHED_MODE] = 0;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) == cudaSuccess;
@@ -1579,6 +1583,7 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_STREAM_H2D && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_MAPPED_RHS && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_KEEP_A && (value < 0 || value > 1)) return -3;
+    if (option == B200LU_OPT_BATCHED_MODE && (value < 0 || value > 1)) return -3;
     if (h->team) return team_set_option(h, option, value);
     h->opt[option] = value;
     return 0;
@@ -2048,12 +2053,35 @@ static int ensure_batched(b200lu_handle* h, int64_t batch, int64_t n) {
     return 0;
 }
 
+// warp-per-system kernel (batched.cuh): factor, optionally with the first solve fused in
+template <typename T, int NMAX, bool SOLVE>
+static int launch_batched_warp(b200lu_handle* h, const BwArgs<T>& a, int64_t batch) {
+    auto kern = getrf_batched_warp_kernel<T, NMAX, SOLVE>;
+    constexpr size_t smem = bw_smem_bytes<T, NMAX>();
+    static std::atomic<bool> attr_dev[64]; std::atomic<bool>& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
+    if (!attr_set) {
+        CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    kern<<<(unsigned)batch, 32, smem, h->s_main>>>(a);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+// B (strideB) / X (strideX) non-null: the first right-hand side is solved in the same kernel (n <= 64 only)
 template <typename T>
-static int batched_factor_launch(b200lu_handle* h, const T* A, int64_t lda, int64_t strideA) {
+static int batched_factor_launch(b200lu_handle* h, const T* A, int64_t lda, int64_t strideA, const T* B = nullptr,
+                                 int64_t strideB = 0, T* X = nullptr, int64_t strideX = 0) {
     const int n = (int)h->b_n;
     const int64_t batch = h->b_batch;
     T* LU = (T*)h->dB_LU;
     cudaStream_t st = h->s_main;
+    if (n <= 64 && h->opt[B200LU_OPT_BATCHED_MODE] == 0) {
+        BwArgs<T> a{A, lda, strideA, LU, n, (long long)n * n, h->dB_ipiv, h->dB_perm, h->dB_info, n, B, strideB, X, strideX};
+        if (B) return n <= 32 ? launch_batched_warp<T, 32, true>(h, a, batch) : launch_batched_warp<T, 64, true>(h, a, batch);
+        return n <= 32 ? launch_batched_warp<T, 32, false>(h, a, batch) : launch_batched_warp<T, 64, false>(h, a, batch);
+    }
     if (n > 64) {
         // 65 ... BATCHED_SMEM_NMAX rows: the system lives in shared memory, one CTA each
         const size_t smem = (size_t)n * (n | 1) * sizeof(T);
@@ -2131,9 +2159,9 @@ static int check_batched_args(b200lu_handle* h, int64_t batch, int64_t n, const 
     return 0;
 }
 
-int b200lu_factor_batched_device(b200lu_handle* h, int64_t batch, int64_t n, const void* A_dev,
-                                 int64_t lda, int64_t strideA, int64_t* any_info) {
-    TEAM_ONLY_HOST(h);
+static int factor_batched_device_impl(b200lu_handle* h, int64_t batch, int64_t n, const void* A_dev, int64_t lda,
+                                      int64_t strideA, const void* B_dev, int64_t strideB, void* X_dev, int64_t strideX,
+                                      int64_t* any_info) {
     int rc = check_batched_args(h, batch, n, A_dev, lda, strideA);
     if (rc) return rc;
     if (any_info) *any_info = 0;
@@ -2143,9 +2171,23 @@ int b200lu_factor_batched_device(b200lu_handle* h, int64_t batch, int64_t n, con
     rc = ensure_batched(h, batch, n);
     if (rc) return rc;
     CU_TRY(h, cudaEventRecord(h->ev_b, h->s_main));
-    if (h->dtype == B200LU_F64) rc = batched_factor_launch<double>(h, (const double*)A_dev, lda, strideA);
-    else rc = batched_factor_launch<float>(h, (const float*)A_dev, lda, strideA);
+    // the first right-hand side rides in the factorization kernel when the warp kernel runs (n <= 64);
+    // otherwise it is an ordinary getrs launch behind the factorization
+    const bool fuse = B_dev && n <= 64 && h->opt[B200LU_OPT_BATCHED_MODE] == 0;
+    if (h->dtype == B200LU_F64)
+        rc = batched_factor_launch<double>(h, (const double*)A_dev, lda, strideA, fuse ? (const double*)B_dev : nullptr, strideB,
+                                           fuse ? (double*)X_dev : nullptr, strideX);
+    else
+        rc = batched_factor_launch<float>(h, (const float*)A_dev, lda, strideA, fuse ? (const float*)B_dev : nullptr, strideB,
+                                          fuse ? (float*)X_dev : nullptr, strideX);
     if (rc) return rc;
+    if (B_dev && !fuse) {
+        if (h->dtype == B200LU_F64)
+            rc = batched_solve_launch<double>(h, 1, (const double*)B_dev, n, strideB, (double*)X_dev, n, strideX, false);
+        else
+            rc = batched_solve_launch<float>(h, 1, (const float*)B_dev, n, strideB, (float*)X_dev, n, strideX, false);
+        if (rc) return rc;
+    }
     CU_TRY(h, cudaEventRecord(h->ev_c, h->s_main));
     h->b_factored = true;
     if (any_info) {
@@ -2164,6 +2206,23 @@ int b200lu_factor_batched_device(b200lu_handle* h, int64_t batch, int64_t n, con
     cudaEventElapsedTime(&ms, h->ev_b, h->ev_c);
     h->timing[B200LU_T_FACTOR] = ms;
     return 0;
+}
+
+int b200lu_factor_batched_device(b200lu_handle* h, int64_t batch, int64_t n, const void* A_dev,
+                                 int64_t lda, int64_t strideA, int64_t* any_info) {
+    TEAM_ONLY_HOST(h);
+    return factor_batched_device_impl(h, batch, n, A_dev, lda, strideA, nullptr, 0, nullptr, 0, any_info);
+}
+
+int b200lu_factor_solve_batched_device(b200lu_handle* h, int64_t batch, int64_t n, const void* A_dev, int64_t lda,
+                                       int64_t strideA, const void* B_dev, int64_t strideB, void* X_dev, int64_t strideX,
+                                       int64_t* any_info) {
+    TEAM_ONLY_HOST(h);
+    if (h && batch > 0 && n > 0) {
+        if (!B_dev || !X_dev) return set_err(h, -7, "B or X is NULL");
+        if (batch > 1 && (strideB < n || strideX < n)) return set_err(h, -8, "strideB / strideX < n");
+    }
+    return factor_batched_device_impl(h, batch, n, A_dev, lda, strideA, B_dev, strideB, X_dev, strideX, any_info);
 }
 
 static int parse_trans(b200lu_handle* h, char trans, bool* tr) {
@@ -2240,6 +2299,61 @@ int b200lu_factor_batched(b200lu_handle* h, int64_t batch, int64_t n, const void
     }
     rc = b200lu_factor_batched_device(h, batch, n, h->dB_in, n, n * n, nullptr);
     if (rc) return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
+    h->timing[B200LU_T_H2D] = ms;
+    if (ipiv_out || info_out) return b200lu_get_factors_batched(h, nullptr, 0, 0, ipiv_out, info_out);
+    return 0;
+}
+
+// getrf of the batch + getrs of ONE right-hand side per system in the same kernel; the factors stay
+// cached like after b200lu_factor_batched (the `solve!` of a fresh BlockDiagonal cache)
+int b200lu_factor_solve_batched(b200lu_handle* h, int64_t batch, int64_t n, const void* A_host, int64_t lda,
+                                int64_t strideA, const void* B_host, int64_t strideB, void* X_host, int64_t strideX,
+                                int64_t* ipiv_out, int64_t* info_out) {
+    if (h && h->team) return team_factor_solve_batched(h, batch, n, A_host, lda, strideA, B_host, strideB, X_host, strideX, ipiv_out, info_out);
+    int rc = check_batched_args(h, batch, n, A_host, lda, strideA);
+    if (rc) return rc;
+    h->b_factored = false;
+    if (batch == 0 || n == 0) { h->b_batch = batch; h->b_n = n; h->b_factored = true; return 0; }
+    if (!B_host || !X_host) return set_err(h, -7, "B or X is NULL");
+    if (batch > 1 && (strideB < n || strideX < n)) return set_err(h, -8, "strideB / strideX < n");
+    CU_TRY(h, cudaSetDevice(h->dev));
+    const size_t is = iface_size(h);
+    const int64_t in_bytes = batch * n * n * (int64_t)is;
+    if (in_bytes > h->b_cap_in) {
+        CU_TRY(h, cudaStreamSynchronize(h->s_main));
+        free_dev(h->dB_in);
+        h->b_cap_in = 0;
+        CU_TRY(h, cudaMalloc(&h->dB_in, (size_t)in_bytes));
+        h->b_cap_in = in_bytes;
+    }
+    const int64_t rbytes = batch * n * (int64_t)is;
+    if (rbytes > h->b_cap_rhs) {
+        CU_TRY(h, cudaStreamSynchronize(h->s_main));
+        free_dev(h->dB_rhs);
+        free_dev(h->dB_x);
+        h->b_cap_rhs = 0;
+        CU_TRY(h, cudaMalloc(&h->dB_rhs, (size_t)rbytes));
+        CU_TRY(h, cudaMalloc(&h->dB_x, (size_t)rbytes));
+        h->b_cap_rhs = rbytes;
+    }
+    CU_TRY(h, cudaEventRecord(h->ev_a, h->s_main));
+    if (lda == n && (strideA == n * n || batch == 1)) {
+        CU_TRY(h, cudaMemcpyAsync(h->dB_in, A_host, (size_t)in_bytes, cudaMemcpyHostToDevice, h->s_main));
+    } else {
+        for (int64_t i = 0; i < batch; ++i)
+            CU_TRY(h, cudaMemcpy2DAsync((char*)h->dB_in + (size_t)(i * n * n) * is, (size_t)n * is,
+                                        (const char*)A_host + (size_t)(i * strideA) * is, (size_t)lda * is,
+                                        (size_t)n * is, (size_t)n, cudaMemcpyHostToDevice, h->s_main));
+    }
+    CU_TRY(h, cudaMemcpy2DAsync(h->dB_rhs, (size_t)n * is, B_host, (size_t)strideB * is, (size_t)n * is, (size_t)batch,
+                                cudaMemcpyHostToDevice, h->s_main));
+    rc = factor_batched_device_impl(h, batch, n, h->dB_in, n, n * n, h->dB_rhs, n, h->dB_x, n, nullptr);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpy2DAsync(X_host, (size_t)strideX * is, h->dB_x, (size_t)n * is, (size_t)n * is, (size_t)batch,
+                                cudaMemcpyDeviceToHost, h->s_main));
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev_a, h->ev_b);
     h->timing[B200LU_T_H2D] = ms;

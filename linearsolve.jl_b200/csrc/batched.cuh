@@ -436,4 +436,299 @@ __global__ void __launch_bounds__(BATCHED_SMEM_NT) getrf_batched_smem_kernel(
     if (tid == 0) info[sys] = myinfo;
 }
 
+// ---------------------------------------------------------------------------------------------
+// getrf (+ optionally the first getrs) of one small system per WARP, the system resident in shared
+// memory in LAPACK layout, blocked right-looking with panels of 8 columns:
+//   * the panel (rows kb.. x 8 columns) lives in registers (lane l holds rows l and l + 32): per
+//     column one redux arg-max, the winning lane stages its 8-wide row, one __syncwarp, scale +
+//     update in registers; rows do not move inside a panel (positions are tracked as in the
+//     register kernel above) and are written back at their final positions when the panel is done;
+//   * the panel's 8 interchanges are then applied to all other columns (lane <-> column), U12 is
+//     solved with the 8 x 8 unit-lower block (lane <-> column) and A22 -= L21 U12 runs lane <-> rows
+//     with the 2 x 8 multipliers in registers and U12 broadcast from shared memory.
+// Every entry sees the FMA sequence of the unblocked right-looking algorithm (pivot 0, 1, 2, ... in
+// order), so factors and pivots are those of the reference's `generic_lufact!`
+// (src/generic_lufact.jl:86-131) bit for bit; pivot / tie / zero-pivot / NaN rules as above.
+// Why: the register kernel above keeps 12 warps per SM and spends ~210 instructions per column and
+// warp staging and re-reading 64-wide rows (13 % of the HBM bound for 64 x 64 FP64).  Here a column
+// step moves 8 values, not 64; the bulk of the flops is a straight FMA stream; one warp needs no
+// CTA barrier; a system costs ~34 KB of shared memory (6 systems in flight per SM for FP64/64).
+// SOLVE: the right-hand side is solved while the factors are still in shared memory and the
+// factors are written out as well ("factors kept"): HBM traffic per 64 x 64 FP64 system is A in,
+// LU out, pivots, b in, x out = 66,816 bytes — the bound of SURVEY §8(d).
+template <typename T, int NMAX>
+__host__ __device__ constexpr int bw_ld() { return NMAX + 16 / (int)sizeof(T); }   // 16-byte aligned columns, rows staggered over the banks
+template <typename T, int NMAX>
+__host__ __device__ constexpr size_t bw_smem_bytes() { return (size_t)NMAX * bw_ld<T, NMAX>() * sizeof(T) + 2 * NMAX * sizeof(int) + 2 * 8 * sizeof(T); }
+
+template <typename T>
+struct BwArgs {
+    const T* A; long long lda, strideA;
+    T* LU; long long ldlu, strideLU;
+    int* ipiv; int* perm; int* info;
+    int n;
+    const T* B; long long strideB;   // SOLVE: one right-hand side per system
+    T* X; long long strideX;
+};
+
+template <typename T, int NMAX, bool SOLVE>
+__global__ void __launch_bounds__(32) getrf_batched_warp_kernel(BwArgs<T> p) {
+    constexpr int RPL = NMAX / 32, LD = bw_ld<T, NMAX>(), EPV = 16 / (int)sizeof(T), NB = 8;
+    static_assert(NMAX == 32 || NMAX == 64, "one or two rows per lane");
+    extern __shared__ __align__(16) unsigned char bw_smem[];
+    T* S = reinterpret_cast<T*>(bw_smem);                       // S[c * LD + r]
+    int* s_perm = reinterpret_cast<int*>(S + NMAX * LD);
+    int* s_ipiv = s_perm + NMAX;
+    T* s_stage = reinterpret_cast<T*>(s_ipiv + NMAX);           // [2][8]: the pivot row of the current column
+    const int lane = threadIdx.x;
+    const long long sys = blockIdx.x;
+    const int n = p.n;
+    const T* Ab = p.A + sys * p.strideA;
+    {
+        const bool vec = (n % EPV == 0) && (p.lda % EPV == 0) && (p.strideA % EPV == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+        if (vec) {
+            const int cpc = n / EPV, total = cpc * n;
+            for (int i = lane; i < total; i += 32) {
+                const int c = i / cpc, r = (i - c * cpc) * EPV;
+                cp_async16(S + c * LD + r, Ab + (long long)c * p.lda + r, true);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+        } else {
+            for (int i = lane; i < n * n; i += 32) {
+                const int c = i / n, r = i - c * n;
+                S[c * LD + r] = Ab[(long long)c * p.lda + r];
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) s_perm[lane + 32 * q] = lane + 32 * q;
+    __syncwarp();
+    int myinfo = 0;   // uniform
+
+    for (int kb = 0; kb < n; kb += NB) {
+        const int jb = min(NB, n - kb);
+        // ---- panel in registers
+        T a[RPL][NB];
+        int pos[RPL];
+        bool act[RPL];
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+            const int row = lane + 32 * q;
+            act[q] = row >= kb && row < n;
+            pos[q] = row;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) a[q][c] = (act[q] && c < jb) ? S[(kb + c) * LD + row] : T(0);
+        }
+        bool inpanel[RPL];   // rows of mine that belong to this panel
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) inpanel[q] = act[q];
+        int pv[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            pv[j] = kb + j;
+            if (j < jb) {
+                const int k = kb + j;
+                // local candidate: strict '>' from 0 (zeros and NaNs are no candidates), lowest position on ties
+                T best = T(0), cand = T(1);
+                int bpos = INT_MAX;
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    if (act[q]) {
+                        const T v = tabs(a[q][j]);
+                        if (v > best || (v == best && v > T(0) && pos[q] < bpos)) { best = v; bpos = pos[q]; cand = a[q][j]; }
+                    }
+                }
+                T rinv = T(1) / cand;                       // under the redux latency
+                const int wl = pcl_warp_argmax(best, bpos);
+                const bool none = wl < 0;                   // all-zero / all-NaN subcolumn: kp = k
+                const int piv = none ? k : __shfl_sync(0xffffffffu, bpos, wl);
+                rinv = __shfl_sync(0xffffffffu, rinv, none ? 0 : wl);
+                T* stg = s_stage + (j & 1) * NB;
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    if (act[q] && pos[q] == piv) {
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) stg[c] = a[q][c];
+                    }
+                }
+                __syncwarp();
+                T prow[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) prow[c] = stg[c];
+                bool scale = true;
+                if (none) {
+                    const T pvv = prow[j];
+                    scale = (pvv != T(0));
+                    rinv = T(1) / pvv;
+                    if (!scale && myinfo == 0) myinfo = k + 1;
+                }
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    if (act[q]) {
+                        if (pos[q] == piv) { pos[q] = k; act[q] = false; }   // the pivot row: frozen
+                        else if (pos[q] == k) pos[q] = piv;                  // the displaced top row stays active
+                    }
+                    if (act[q]) {
+                        T l = a[q][j];
+                        if (scale) l *= rinv;
+                        a[q][j] = l;
+#pragma unroll
+                        for (int c = j + 1; c < NB; ++c) a[q][c] = tfma(-l, prow[c], a[q][c]);
+                    }
+                }
+                pv[j] = piv;
+            }
+        }
+        // ---- panel back to shared memory, every row at its final position
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+            if (inpanel[q]) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c < jb) S[(kb + c) * LD + pos[q]] = a[q][c];
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                if (j < jb) {
+                    s_ipiv[kb + j] = pv[j];
+                    if (pv[j] != kb + j) { const int t = s_perm[kb + j]; s_perm[kb + j] = s_perm[pv[j]]; s_perm[pv[j]] = t; }
+                }
+            }
+        }
+        // ---- the panel's interchanges on all other columns (left and right): lane <-> column
+        for (int c = lane; c < n; c += 32) {
+            if (c >= kb && c < kb + jb) continue;
+            T* col = S + c * LD;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                if (j < jb && pv[j] != kb + j) {
+                    const T x = col[kb + j], y = col[pv[j]];
+                    col[kb + j] = y;
+                    col[pv[j]] = x;
+                }
+            }
+        }
+        __syncwarp();
+        if (kb + jb < n) {   // (then jb == NB)
+            // ---- U12 = L11^{-1} A12: lane <-> trailing column, the strictly lower 8 x 8 block in registers
+            T L[NB][NB];
+#pragma unroll
+            for (int i = 1; i < NB; ++i)
+#pragma unroll
+                for (int i2 = 0; i2 < i; ++i2) L[i][i2] = S[(kb + i2) * LD + kb + i];
+            for (int c = kb + NB + lane; c < n; c += 32) {
+                T* col = S + c * LD + kb;
+                T x[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) x[i] = col[i];
+#pragma unroll
+                for (int i = 1; i < NB; ++i)
+#pragma unroll
+                    for (int i2 = 0; i2 < i; ++i2) x[i] = tfma(-L[i][i2], x[i2], x[i]);
+#pragma unroll
+                for (int i = 1; i < NB; ++i) col[i] = x[i];
+            }
+            __syncwarp();
+            // ---- A22 -= L21 U12: lane <-> rows
+            T l21[RPL][NB];
+            bool upd[RPL];
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) {
+                const int row = lane + 32 * q;
+                upd[q] = row >= kb + NB && row < n;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) l21[q][i] = upd[q] ? S[(kb + i) * LD + row] : T(0);
+            }
+#pragma unroll 2
+            for (int c = kb + NB; c < n; ++c) {
+                const T* col = S + c * LD;
+                T u[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) u[i] = col[kb + i];
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) {
+                    if (RPL > 1 && q == 0 && kb + NB >= 32) continue;   // rows 0..31 are all finished
+                    if (upd[q]) {
+                        T v = col[lane + 32 * q];
+#pragma unroll
+                        for (int i = 0; i < NB; ++i) v = tfma(-l21[q][i], u[i], v);
+                        S[c * LD + lane + 32 * q] = v;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- outputs: info, pivots, permutation, the packed factors
+    if (lane == 0) p.info[sys] = myinfo;
+    for (int i = lane; i < n; i += 32) {
+        p.ipiv[sys * n + i] = s_ipiv[i];
+        p.perm[sys * n + i] = s_perm[i];
+    }
+    {
+        T* Lb = p.LU + sys * p.strideLU;
+        const bool vec = (n % EPV == 0) && (p.ldlu % EPV == 0) && (p.strideLU % EPV == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.LU) & 15) == 0);
+        if (vec) {
+            const int cpc = n / EPV, total = cpc * n;
+            for (int i = lane; i < total; i += 32) {
+                const int c = i / cpc, r = (i - c * cpc) * EPV;
+                *reinterpret_cast<uint4*>(Lb + (long long)c * p.ldlu + r) = *reinterpret_cast<const uint4*>(S + c * LD + r);
+            }
+        } else {
+            for (int i = lane; i < n * n; i += 32) {
+                const int c = i / n, r = i - c * n;
+                Lb[(long long)c * p.ldlu + r] = S[c * LD + r];
+            }
+        }
+    }
+    if constexpr (SOLVE) {
+        // x = U \ (L \ (P b)) with the factors still in shared memory (the sweeps of getrs_batched_kernel)
+        T b[RPL];
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const int row = r * 32 + lane;
+            b[r] = row < n ? p.B[sys * p.strideB + s_perm[row]] : T(0);
+        }
+#pragma unroll
+        for (int kr = 0; kr < RPL; ++kr) {
+            const int kend = min(32, n - kr * 32);
+#pragma unroll 4
+            for (int kk = 0; kk < kend; ++kk) {
+                const int k = kr * 32 + kk;
+                const T xk = __shfl_sync(0xffffffffu, b[kr], kk);
+#pragma unroll
+                for (int r = kr; r < RPL; ++r) {
+                    const int row = r * 32 + lane;
+                    if (row > k && row < n) b[r] = tfma(-S[k * LD + row], xk, b[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int kr = RPL - 1; kr >= 0; --kr) {
+            const int kend = min(32, n - kr * 32);
+#pragma unroll 4
+            for (int kk = kend - 1; kk >= 0; --kk) {
+                const int k = kr * 32 + kk;
+                if (lane == kk) b[kr] = b[kr] / S[k * LD + k];
+                const T xk = __shfl_sync(0xffffffffu, b[kr], kk);
+#pragma unroll
+                for (int r = 0; r <= kr; ++r) {
+                    const int row = r * 32 + lane;
+                    if (row < k) b[r] = tfma(-S[k * LD + row], xk, b[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RPL; ++r)
+            if (r * 32 + lane < n) p.X[sys * p.strideX + r * 32 + lane] = b[r];
+    }
+}
+
+
 }  // namespace b200lu

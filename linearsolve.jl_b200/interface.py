@@ -314,9 +314,11 @@ def pad_blocks(blocks, idx, m, dtype):
     return stack
 
 
-def _factor_blockdiag(cache, alg):
+def _factor_blockdiag(cache, alg, fuse_b=None):
     """Blockwise LU (ext/LinearSolveBlockDiagonalsExt.jl:119-125): see plan_blockdiag.
-    success = all(issuccess) (:121-124)."""
+    success = all(issuccess) (:121-124).  `fuse_b` (a vector right-hand side): batched groups of
+    blocks of up to 64 rows solve it inside the factorization kernel (b200lu_factor_solve_batched);
+    returns (info, {group index: solution rows})."""
     A = cache.A
     cv = cache.cacheval
     if not A.all_square():
@@ -331,27 +333,44 @@ def _factor_blockdiag(cache, alg):
             cv.groups.append((kind, h, idx, m))
         cv.group_sizes = (sizes, dt)
     ok = True
-    for kind, h, idx, m in cv.groups:
+    fused = {}
+    for gi, (kind, h, idx, m) in enumerate(cv.groups):
         if kind == "batched":
-            _, info = h.factor_batched(pad_blocks(A.blocks, idx, m, h.np_dtype))
+            stack = pad_blocks(A.blocks, idx, m, h.np_dtype)
+            if fuse_b is not None and m <= 64 and hasattr(h, "factor_solve_batched"):
+                rhs = np.zeros((len(idx), m), dtype=h.np_dtype)
+                for s_, i in enumerate(idx):
+                    o, n = A.offsets[i], A.blocks[i].shape[0]
+                    rhs[s_, :n] = fuse_b[o:o + n]
+                x, _, info = h.factor_solve_batched(stack, rhs)
+                fused[gi] = x
+            else:
+                _, info = h.factor_batched(stack)
             ok = ok and not np.any(info != 0)
         else:
             _, info = h.factor(np.asfortranarray(A.blocks[idx[0]], dtype=h.np_dtype), want_ipiv=False)
             ok = ok and info == 0
     cv.info = 0 if ok else 1
+    cv.fused = fused if ok else {}
     return cv.info
 
 
-def _solve_blockdiag(cache, adjoint=False):
+def _solve_blockdiag(cache, adjoint=False, fused=None):
     """per-block ldiv! on views of b (ext/LinearSolveBlockDiagonalsExt.jl:183-205); `adjoint`: the
-    transposed blocks with the same factors (block-diagonal structure is its own transpose)"""
+    transposed blocks with the same factors (block-diagonal structure is its own transpose);
+    `fused`: solutions the factorization kernel already produced for some groups"""
     A, cv = cache.A, cache.cacheval
     b = np.asarray(cache.b)
     vec = b.ndim == 1
     Bm = b.reshape(b.shape[0], -1)
     X = np.empty_like(Bm)
     trans = "T" if adjoint else "N"
-    for kind, h, idx, m in cv.groups:
+    for gi, (kind, h, idx, m) in enumerate(cv.groups):
+        if fused and gi in fused:
+            for s, i in enumerate(idx):
+                o, n = A.offsets[i], A.blocks[i].shape[0]
+                X[o:o + n, 0] = fused[gi][s, :n]
+            continue
         if kind == "batched":
             # (batch, nrhs, m): each right-hand side contiguous, zero in the padding rows
             rhs = np.zeros((len(idx), Bm.shape[1], m), dtype=h.np_dtype)
@@ -401,9 +420,12 @@ def solve_(cache: LinearCache, alg=None, adjoint: bool = False) -> LinearSolutio
     if adjoint and getattr(alg, "devices", None) is not None:
         raise NotImplementedError("solve!(cache; adjoint = true) needs the single-GPU handle")
     check_safety = alg.residualsafety and cache.isfresh
+    fused = None
     if cache.isfresh:
         if isinstance(A, BlockDiagonal):
-            info = _factor_blockdiag(cache, alg)
+            b0 = np.asarray(cache.b)
+            info = _factor_blockdiag(cache, alg, fuse_b=b0 if (b0.ndim == 1 and not adjoint) else None)
+            fused = getattr(cv, "fused", None)
         else:
             A = np.asarray(A)
             if cv.handle is None or cv.handle.dtype != alg.handle_dtype(A.dtype):
@@ -417,7 +439,7 @@ def solve_(cache: LinearCache, alg=None, adjoint: bool = False) -> LinearSolutio
             return LinearSolution(cache.u, ReturnCode.Failure, alg)
         cache.isfresh = False
     if isinstance(A, BlockDiagonal):
-        x = _solve_blockdiag(cache, adjoint)
+        x = _solve_blockdiag(cache, adjoint, fused)
     else:
         u, b = cache.u, np.asarray(cache.b)
         # a plain vector u, or a column-major matrix u: getrs writes straight into cache.u

@@ -84,3 +84,74 @@ def test_batched_full_size_properties(gpu_required, ls, oracle):
     for s in rng.choice(batch, 16, replace=False):
         _, ipiv_ref, _ = oracle.lapack_getrf(A[s].T)
         assert np.array_equal(ipiv[s], ipiv_ref)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [1, 5, 8, 9, 16, 17, 32, 33, 40, 63, 64])
+def test_warp_kernel_matches_reference_algorithm_bitwise(gpu_required, ls, oracle, n, dtype):
+    """The warp-per-system kernel (OPT_BATCHED_MODE 0, blocked with 8-column register panels) and the round-1
+    row-per-thread kernel (mode 1) both run the FMA sequence of the unblocked right-looking algorithm, and so
+    does the C oracle (`_blocked_lu_unblocked!`, src/blocked_lufact.jl:58-90: pivot rule of :38-54, FMA updates): factors, pivots and
+    info are compared BIT FOR BIT, also with a singular and a NaN-carrying system in the batch."""
+    C = ls._capi
+    rng = np.random.default_rng(100 + n)
+    batch = 23
+    A = rng.random((batch, n, n)).astype(dtype)
+    if n > 2:
+        A[3].T[:, 1] = 0          # zero column 2 of system 3: info = 2, the factorization runs on
+        A[7][0, min(2, n - 1)] = np.nan   # a NaN entry: never chosen while a finite candidate exists
+    code = C.F64 if dtype == np.float64 else C.F32
+    h0, h1 = ls.Handle(code), ls.Handle(code)
+    h1.set_option(C.OPT_BATCHED_MODE, 1)
+    ip0, info0 = h0.factor_batched(A)
+    ip1, info1 = h1.factor_batched(A)
+    LU0, _, _ = h0.get_factors_batched()
+    LU1, _, _ = h1.get_factors_batched()
+    assert np.array_equal(ip0, ip1) and np.array_equal(info0, info1)
+    assert np.array_equal(LU0, LU1, equal_nan=True)
+    if dtype == np.float64:
+        for s in range(batch):
+            F, ipr, infr = oracle.ref_lufact(np.asfortranarray(A[s].T), variant="unblocked")
+            assert infr == info0[s], (s, infr, info0[s])
+            assert np.array_equal(ipr, ip0[s]), s
+            assert np.array_equal(F, LU0[s].T, equal_nan=True), s
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [3, 16, 31, 32, 47, 64])
+def test_fused_factor_solve_batched(gpu_required, ls, oracle, n, dtype):
+    """b200lu_factor_solve_batched: getrf + the first getrs in one kernel, factors kept: same pivots and factors
+    as b200lu_factor_batched, x within the backward-error bar, later solves from the cached factors agree."""
+    C = ls._capi
+    rng = np.random.default_rng(200 + n)
+    batch = 41
+    A = (rng.random((batch, n, n)) + n * np.eye(n)).astype(dtype)
+    b = rng.random((batch, n)).astype(dtype)
+    code = C.F64 if dtype == np.float64 else C.F32
+    h, hr = ls.Handle(code), ls.Handle(code)
+    x, ipiv, info = h.factor_solve_batched(A, b)
+    ipr, infr = hr.factor_batched(A)
+    assert np.array_equal(ipiv, ipr) and not info.any() and not infr.any()
+    assert np.array_equal(h.get_factors_batched()[0], hr.get_factors_batched()[0])
+    eps = np.finfo(dtype).eps
+    for s in range(batch):
+        assert oracle.backward_error(A[s].T.astype(np.float64), x[s].astype(np.float64), b[s].astype(np.float64)) <= 10 * n * eps
+        _, ipiv_lapack, _ = oracle.lapack_getrf(A[s].T)
+        assert oracle.compare_ipiv(A[s].T, ipiv[s], ipiv_lapack)[1] in ("exact", "tie")
+    assert np.array_equal(h.solve_batched(b), hr.solve_batched(b))
+    np.testing.assert_allclose(h.solve_batched(b), x, rtol=0, atol=100 * n * eps * np.abs(x).max())
+    # device entry with the same data
+    import torch
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    Ad = torch.from_numpy(A).cuda()
+    bd = torch.from_numpy(b).cuda()
+    xd = torch.empty_like(bd)
+    assert h.factor_solve_batched_device(Ad.data_ptr(), bd.data_ptr(), xd.data_ptr(), batch, n) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(xd.cpu().numpy(), x)
+    # a singular system in the batch is reported, the others are solved
+    A2 = A.copy()
+    A2[5] = 1.0
+    x2, _, info2 = h.factor_solve_batched(A2, b)
+    assert info2[5] > 0 and not np.delete(info2, 5).any()
+    assert np.array_equal(np.delete(x2, 5, axis=0), np.delete(x, 5, axis=0))
