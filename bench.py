@@ -826,9 +826,11 @@ def bench_dist(args, ls, torch, dist, dev, rank, world, local, barrier, max_over
         ms_f, ms_s = max_over_ranks(ms_f), max_over_ranks(ms_s)
         line["batched_65536x64"] = batched_entry(ms_f, ms_s, per, world, read_peaks().get("hbm_gbs", 6650.0))
 
-    # ---- e2e: rank 0 drives ALL the GPUs through one multi-GPU handle from pinned host memory
+    # ---- e2e: rank 0 drives ALL the GPUs through one multi-GPU handle from pinned host memory; the other
+    # ranks wait on a HOST-side (gloo) barrier, so that no NCCL kernel spins on their GPUs meanwhile
     barrier()
     if not args.no_e2e:
+        cpu_group = dist.new_group(backend="gloo") if world > 1 else None
         if rank == 0:
             try:
                 A_dev = torch.empty((n, n), dtype=torch.float64, device=dev)
@@ -840,7 +842,8 @@ def bench_dist(args, ls, torch, dist, dev, rank, world, local, barrier, max_over
                 del A_dev
             except Exception as ex:   # the device-timed line stands on its own
                 line["e2e_error"] = str(ex)[:300]
-        barrier()
+        if cpu_group is not None:
+            dist.barrier(group=cpu_group)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
