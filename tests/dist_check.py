@@ -75,6 +75,11 @@ def main():
             hd.solve_dist(b.data_ptr(), n, xd.data_ptr(), n, 3)
         torch.cuda.synchronize()
         assert (xs - xd).abs().max().item() <= 1e3 * n * 2.2e-16 * xs.abs().max().item()
+        x1 = torch.empty(n, dtype=torch.float64, device=dev)       # one right-hand side: the fused step kernel
+        for _ in range(2):
+            hd.solve_dist(b[2].data_ptr(), n, x1.data_ptr(), n, 1)
+        torch.cuda.synchronize()
+        assert (xs[2] - x1).abs().max().item() <= 1e3 * n * 2.2e-16 * xs.abs().max().item()
     else:
         xd.copy_(xs)   # the NCCL fallback transport has no distributed getrs
     A = torch.empty((n, n), dtype=torch.float64, device=dev)

@@ -73,6 +73,13 @@ def test_dist_engine_single_rank(gpu_required, ls, n, nb, dtype):
         assert _berr(A64, X[:, c].astype(np.float64), B[:, c].astype(np.float64)) <= 10 * n * eps
     Xs = hs.solve(np.asfortranarray(B))
     assert np.allclose(X, Xs, rtol=0, atol=1e3 * n * eps * np.abs(Xs).max())
+    # ONE right-hand side takes the fused per-step kernel (wait, inverted diagonal block, update, tag)
+    x1 = torch.empty(n, dtype=tdt, device=dev)
+    for _ in range(2):
+        hd.solve_dist(Bd[1].data_ptr(), n, x1.data_ptr(), n, 1)
+    torch.cuda.synchronize()
+    assert _berr(A64, x1.cpu().numpy().astype(np.float64), B[:, 1].astype(np.float64)) <= 10 * n * eps
+    assert np.allclose(x1.cpu().numpy(), Xs[:, 1], rtol=0, atol=1e3 * n * eps * np.abs(Xs).max())
     # a second factorization on the same handle (slots and tags are reused), singular this time
     Z = np.asfortranarray(rng.random((n, n)).astype(dtype))
     Z[:, 5] = 0
