@@ -476,9 +476,9 @@ __global__ void __launch_bounds__(32) getrf_batched_warp_kernel(BwArgs<T> p) {
     constexpr int RPL = NMAX / 32, LD = bw_ld<T, NMAX>(), EPV = 16 / (int)sizeof(T), NB = 8;
     static_assert(NMAX == 32 || NMAX == 64, "one or two rows per lane");
     extern __shared__ __align__(16) unsigned char bw_smem[];
-    T* S = reinterpret_cast<T*>(bw_smem);                       // S[c * LD + r]
-    int* s_perm = reinterpret_cast<int*>(S + NMAX * LD);
-    int* s_ipiv = s_perm + NMAX;
+    T* S = reinterpret_cast<T*>(bw_smem);                       // S[c * LD + r]: rows stay where they were loaded
+    int* s_rowof = reinterpret_cast<int*>(S + NMAX * LD);       // physical row at each position (for the solve)
+    int* s_ipiv = s_rowof + NMAX;
     T* s_stage = reinterpret_cast<T*>(s_ipiv + NMAX);           // [2][8]: the pivot row of the current column
     const int lane = threadIdx.x;
     const long long sys = blockIdx.x;
@@ -502,32 +502,35 @@ __global__ void __launch_bounds__(32) getrf_batched_warp_kernel(BwArgs<T> p) {
             }
         }
     }
-#pragma unroll
-    for (int q = 0; q < RPL; ++q) s_perm[lane + 32 * q] = lane + 32 * q;
     __syncwarp();
+    // Rows never move: pos[q] is the current position of physical row lane + 32 q in the LAPACK row order
+    // (the interchange sequence acts on positions), act[q] says it has not been a pivot row yet.
+    int pos[RPL];
+    bool act[RPL];
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+        const int row = lane + 32 * q;
+        act[q] = row < n;
+        pos[q] = act[q] ? row : INT_MAX;
+    }
     int myinfo = 0;   // uniform
 
     for (int kb = 0; kb < n; kb += NB) {
         const int jb = min(NB, n - kb);
-        // ---- panel in registers
+        // ---- panel in registers (rows that are still active; finished rows are final already)
         T a[RPL][NB];
-        int pos[RPL];
-        bool act[RPL];
+        bool inpanel[RPL];
 #pragma unroll
         for (int q = 0; q < RPL; ++q) {
-            const int row = lane + 32 * q;
-            act[q] = row >= kb && row < n;
-            pos[q] = row;
+            inpanel[q] = act[q];
 #pragma unroll
-            for (int c = 0; c < NB; ++c) a[q][c] = (act[q] && c < jb) ? S[(kb + c) * LD + row] : T(0);
+            for (int c = 0; c < NB; ++c) a[q][c] = (act[q] && c < jb) ? S[(kb + c) * LD + lane + 32 * q] : T(0);
         }
-        bool inpanel[RPL];   // rows of mine that belong to this panel
-#pragma unroll
-        for (int q = 0; q < RPL; ++q) inpanel[q] = act[q];
-        int pv[NB];
+        int pv[NB], pr[NB];   // uniform: position and physical row of the pivot of column kb + j
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
             pv[j] = kb + j;
+            pr[j] = 0;
             if (j < jb) {
                 const int k = kb + j;
                 // local candidate: strict '>' from 0 (zeros and NaNs are no candidates), lowest position on ties
@@ -544,15 +547,21 @@ __global__ void __launch_bounds__(32) getrf_batched_warp_kernel(BwArgs<T> p) {
                 const int wl = pcl_warp_argmax(best, bpos);
                 const bool none = wl < 0;                   // all-zero / all-NaN subcolumn: kp = k
                 const int piv = none ? k : __shfl_sync(0xffffffffu, bpos, wl);
-                rinv = __shfl_sync(0xffffffffu, rinv, none ? 0 : wl);
+                // the pivot row (at position piv) stages its 8-wide row and tells its physical index
                 T* stg = s_stage + (j & 1) * NB;
+                int ownq = -1;
 #pragma unroll
                 for (int q = 0; q < RPL; ++q) {
                     if (act[q] && pos[q] == piv) {
+                        ownq = q;
 #pragma unroll
                         for (int c = 0; c < NB; ++c) stg[c] = a[q][c];
                     }
                 }
+                const unsigned ob = __ballot_sync(0xffffffffu, ownq >= 0);
+                const int ol = __ffs(ob) - 1;
+                rinv = __shfl_sync(0xffffffffu, rinv, ol);
+                pr[j] = ol + 32 * __shfl_sync(0xffffffffu, ownq, ol);
                 __syncwarp();
                 T prow[NB];
 #pragma unroll
@@ -581,82 +590,58 @@ __global__ void __launch_bounds__(32) getrf_batched_warp_kernel(BwArgs<T> p) {
                 pv[j] = piv;
             }
         }
-        // ---- panel back to shared memory, every row at its final position
+        // ---- panel back to shared memory (rows in place)
 #pragma unroll
         for (int q = 0; q < RPL; ++q) {
             if (inpanel[q]) {
 #pragma unroll
                 for (int c = 0; c < NB; ++c)
-                    if (c < jb) S[(kb + c) * LD + pos[q]] = a[q][c];
+                    if (c < jb) S[(kb + c) * LD + lane + 32 * q] = a[q][c];
             }
         }
-        if (lane == 0) {
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                if (j < jb) {
-                    s_ipiv[kb + j] = pv[j];
-                    if (pv[j] != kb + j) { const int t = s_perm[kb + j]; s_perm[kb + j] = s_perm[pv[j]]; s_perm[pv[j]] = t; }
-                }
-            }
-        }
-        // ---- the panel's interchanges on all other columns (left and right): lane <-> column
-        for (int c = lane; c < n; c += 32) {
-            if (c >= kb && c < kb + jb) continue;
-            T* col = S + c * LD;
-#pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                if (j < jb && pv[j] != kb + j) {
-                    const T x = col[kb + j], y = col[pv[j]];
-                    col[kb + j] = y;
-                    col[pv[j]] = x;
-                }
-            }
-        }
+        for (int j = 0; j < NB; ++j)
+            if (j < jb && lane == j) s_ipiv[kb + j] = pv[j];
         __syncwarp();
         if (kb + jb < n) {   // (then jb == NB)
-            // ---- U12 = L11^{-1} A12: lane <-> trailing column, the strictly lower 8 x 8 block in registers
+            // ---- U12 = L11^{-1} A12 on the 8 pivot rows: lane <-> trailing column
             T L[NB][NB];
 #pragma unroll
             for (int i = 1; i < NB; ++i)
 #pragma unroll
-                for (int i2 = 0; i2 < i; ++i2) L[i][i2] = S[(kb + i2) * LD + kb + i];
+                for (int i2 = 0; i2 < i; ++i2) L[i][i2] = S[(kb + i2) * LD + pr[i]];
             for (int c = kb + NB + lane; c < n; c += 32) {
-                T* col = S + c * LD + kb;
+                T* col = S + c * LD;
                 T x[NB];
 #pragma unroll
-                for (int i = 0; i < NB; ++i) x[i] = col[i];
+                for (int i = 0; i < NB; ++i) x[i] = col[pr[i]];
 #pragma unroll
                 for (int i = 1; i < NB; ++i)
 #pragma unroll
                     for (int i2 = 0; i2 < i; ++i2) x[i] = tfma(-L[i][i2], x[i2], x[i]);
 #pragma unroll
-                for (int i = 1; i < NB; ++i) col[i] = x[i];
+                for (int i = 1; i < NB; ++i) col[pr[i]] = x[i];
             }
             __syncwarp();
-            // ---- A22 -= L21 U12: lane <-> rows
+            // ---- A22 -= L21 U12 on the rows that are still active: lane <-> rows
             T l21[RPL][NB];
-            bool upd[RPL];
 #pragma unroll
-            for (int q = 0; q < RPL; ++q) {
-                const int row = lane + 32 * q;
-                upd[q] = row >= kb + NB && row < n;
+            for (int q = 0; q < RPL; ++q)
 #pragma unroll
-                for (int i = 0; i < NB; ++i) l21[q][i] = upd[q] ? S[(kb + i) * LD + row] : T(0);
-            }
-#pragma unroll 2
+                for (int i = 0; i < NB; ++i) l21[q][i] = act[q] ? S[(kb + i) * LD + lane + 32 * q] : T(0);
+#pragma unroll 4
             for (int c = kb + NB; c < n; ++c) {
-                const T* col = S + c * LD;
+                T* col = S + c * LD;
                 T u[NB];
 #pragma unroll
-                for (int i = 0; i < NB; ++i) u[i] = col[kb + i];
+                for (int i = 0; i < NB; ++i) u[i] = col[pr[i]];
 #pragma unroll
                 for (int q = 0; q < RPL; ++q) {
-                    if (RPL > 1 && q == 0 && kb + NB >= 32) continue;   // rows 0..31 are all finished
-                    if (upd[q]) {
+                    if (act[q]) {
                         T v = col[lane + 32 * q];
 #pragma unroll
                         for (int i = 0; i < NB; ++i) v = tfma(-l21[q][i], u[i], v);
-                        S[c * LD + lane + 32 * q] = v;
+                        col[lane + 32 * q] = v;
                     }
                 }
             }
@@ -664,36 +649,42 @@ __global__ void __launch_bounds__(32) getrf_batched_warp_kernel(BwArgs<T> p) {
         }
     }
 
-    // ---- outputs: info, pivots, permutation, the packed factors
+    // ---- outputs: info, pivots, permutation, the packed factors (every row stored at its final position)
     if (lane == 0) p.info[sys] = myinfo;
-    for (int i = lane; i < n; i += 32) {
-        p.ipiv[sys * n + i] = s_ipiv[i];
-        p.perm[sys * n + i] = s_perm[i];
+    for (int i = lane; i < n; i += 32) p.ipiv[sys * n + i] = s_ipiv[i];
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+        const int row = lane + 32 * q;
+        if (row < n) {
+            p.perm[sys * n + pos[q]] = row;
+            s_rowof[pos[q]] = row;
+        }
     }
     {
         T* Lb = p.LU + sys * p.strideLU;
-        const bool vec = (n % EPV == 0) && (p.ldlu % EPV == 0) && (p.strideLU % EPV == 0) &&
-                         ((reinterpret_cast<uintptr_t>(p.LU) & 15) == 0);
-        if (vec) {
-            const int cpc = n / EPV, total = cpc * n;
-            for (int i = lane; i < total; i += 32) {
-                const int c = i / cpc, r = (i - c * cpc) * EPV;
-                *reinterpret_cast<uint4*>(Lb + (long long)c * p.ldlu + r) = *reinterpret_cast<const uint4*>(S + c * LD + r);
-            }
-        } else {
-            for (int i = lane; i < n * n; i += 32) {
-                const int c = i / n, r = i - c * n;
-                Lb[(long long)c * p.ldlu + r] = S[c * LD + r];
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+            const int row = lane + 32 * q;
+            if (row < n) {
+                T* dst = Lb + pos[q];
+                const T* src = S + row;
+#pragma unroll 8
+                for (int c = 0; c < n; ++c) dst[(long long)c * p.ldlu] = src[c * LD];
             }
         }
     }
     if constexpr (SOLVE) {
-        // x = U \ (L \ (P b)) with the factors still in shared memory (the sweeps of getrs_batched_kernel)
-        T b[RPL];
+        // x = U \ (L \ (P b)) with the factors still in shared memory; b stays with its physical row, the sweeps
+        // run in position order (s_rowof); the diagonal reciprocals are taken up front, off the chain
+        __syncwarp();
+        T b[RPL], rd[RPL];
+        int ro[RPL];
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) {
-            const int row = r * 32 + lane;
-            b[r] = row < n ? p.B[sys * p.strideB + s_perm[row]] : T(0);
+        for (int q = 0; q < RPL; ++q) {
+            const int row = lane + 32 * q;
+            b[q] = row < n ? p.B[sys * p.strideB + row] : T(0);
+            rd[q] = row < n ? T(1) / S[pos[q] * LD + row] : T(1);
+            ro[q] = row < n ? s_rowof[row] : 0;       // lane l, slot q: physical row at POSITION l + 32 q
         }
 #pragma unroll
         for (int kr = 0; kr < RPL; ++kr) {
@@ -701,12 +692,13 @@ __global__ void __launch_bounds__(32) getrf_batched_warp_kernel(BwArgs<T> p) {
 #pragma unroll 4
             for (int kk = 0; kk < kend; ++kk) {
                 const int k = kr * 32 + kk;
-                const T xk = __shfl_sync(0xffffffffu, b[kr], kk);
+                const int r = __shfl_sync(0xffffffffu, ro[kr], kk);          // physical row at position k
+                const T mine = (RPL > 1 && (r >> 5)) ? b[RPL - 1] : b[0];
+                const T xk = __shfl_sync(0xffffffffu, mine, r & 31);
+                const T* col = S + k * LD;
 #pragma unroll
-                for (int r = kr; r < RPL; ++r) {
-                    const int row = r * 32 + lane;
-                    if (row > k && row < n) b[r] = tfma(-S[k * LD + row], xk, b[r]);
-                }
+                for (int q = 0; q < RPL; ++q)
+                    if (pos[q] > k && pos[q] != INT_MAX) b[q] = tfma(-col[lane + 32 * q], xk, b[q]);
             }
         }
 #pragma unroll
@@ -715,20 +707,22 @@ __global__ void __launch_bounds__(32) getrf_batched_warp_kernel(BwArgs<T> p) {
 #pragma unroll 4
             for (int kk = kend - 1; kk >= 0; --kk) {
                 const int k = kr * 32 + kk;
-                if (lane == kk) b[kr] = b[kr] / S[k * LD + k];
-                const T xk = __shfl_sync(0xffffffffu, b[kr], kk);
+                const int r = __shfl_sync(0xffffffffu, ro[kr], kk);
 #pragma unroll
-                for (int r = 0; r <= kr; ++r) {
-                    const int row = r * 32 + lane;
-                    if (row < k) b[r] = tfma(-S[k * LD + row], xk, b[r]);
-                }
+                for (int q = 0; q < RPL; ++q)
+                    if (pos[q] == k) b[q] *= rd[q];
+                const T mine = (RPL > 1 && (r >> 5)) ? b[RPL - 1] : b[0];
+                const T xk = __shfl_sync(0xffffffffu, mine, r & 31);
+                const T* col = S + k * LD;
+#pragma unroll
+                for (int q = 0; q < RPL; ++q)
+                    if (pos[q] < k) b[q] = tfma(-col[lane + 32 * q], xk, b[q]);
             }
         }
 #pragma unroll
-        for (int r = 0; r < RPL; ++r)
-            if (r * 32 + lane < n) p.X[sys * p.strideX + r * 32 + lane] = b[r];
+        for (int q = 0; q < RPL; ++q)
+            if (lane + 32 * q < n) p.X[sys * p.strideX + pos[q]] = b[q];
     }
 }
-
 
 }  // namespace b200lu
