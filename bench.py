@@ -786,6 +786,11 @@ def bench_dist(args, ls, torch, dist, dev, rank, world, local, barrier, max_over
     h.factor_dist(Aloc.data_ptr(), n, n)
     g_ms, g_fl = h.timing(C.T_GEMM), h.counter(C.C_GEMM_FLOPS)
     t_prof = h.timing(C.T_FACTOR)
+    chain = [h.timing(C.T_PANEL), h.timing(C.T_LOOKAHEAD), h.timing(C.T_PUSH)]
+    if world > 1:
+        ct = torch.tensor(chain, dtype=torch.float64, device=dev)
+        dist.all_reduce(ct)                      # every panel has one owner: the sum over ranks is the whole chain
+        chain = [float(x) for x in ct.tolist()]
     h.set_option(C.OPT_PROFILE, 0)
     peak = h.probe_peak(C.PEAK_FP64_DMMA)
     ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
@@ -811,6 +816,10 @@ def bench_dist(args, ls, torch, dist, dev, rank, world, local, barrier, max_over
                          "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
                          "traffic": None, "gemm_share_of_getrf_max_over_ranks": gemm_share,
                          "getrf_frac_of_aggregate_fp64_peak": (lu_flops(n) / (tf_ms * 1e-3) / 1e12) / (peak * world) if peak else None,
+                         "chain_ms": {"panel_factorizations": chain[0], "lookahead_block_updates": chain[1], "panel_hand_off": chain[2],
+                                      "sum": sum(chain), "profiled_getrf_ms": max_over_ranks(t_prof),
+                                      "how": "CUDA events on the owners' panel streams in one extra profiled factorization, "
+                                             "summed over all panels (every panel has exactly one owner)"},
                          "limiter": "the serial chain push -> look-ahead block update -> panel factorization -> push; "
                                     "the trailing GEMMs (1/N per rank) hide under it"}}
     assert check_bitwise, "distributed factors differ from the single-GPU factorization"

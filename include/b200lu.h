@@ -72,7 +72,12 @@ enum {
     B200LU_T_D2H = 3,      /* device -> host copy of ipiv/info or X            */
     B200LU_T_GEMM = 4,     /* of FACTOR: sum of trailing-update GEMM launches;
                               only with B200LU_OPT_PROFILE = 1                 */
-    B200LU_T_COUNT = 5
+    /* distributed getrf with B200LU_OPT_PROFILE = 1: the three phases of the critical chain, summed over the
+       panels THIS rank factored / pushed (CUDA events on its panel stream) */
+    B200LU_T_PANEL = 5,    /* panel factorizations (recursive panel of the blocks this rank owns)  */
+    B200LU_T_LOOKAHEAD = 6,/* update k of the block this rank factors next (laswp + TRSM + GEMM)   */
+    B200LU_T_PUSH = 7,     /* hand-off of the factored panels (peer stores / ncclBroadcast)        */
+    B200LU_T_COUNT = 8
 };
 
 /* counters for b200lu_last_counter (filled by the last factor call) */

@@ -143,6 +143,9 @@ struct b200lu_handle {
     // profiling (B200LU_OPT_PROFILE)
     std::vector<cudaEvent_t> prof_ev;
     int prof_used = 0;
+    // chain profile of the distributed getrf (B200LU_OPT_PROFILE): event pairs on the panel stream, by phase
+    std::vector<cudaEvent_t> chain_ev;
+    std::vector<int> chain_kind;
     double prof_flops = 0.0;
     double counters[B200LU_C_COUNT] = {0};
 
@@ -1475,6 +1478,7 @@ void b200lu_destroy(b200lu_handle* h) {
     for (cudaEvent_t e : h->ev_panel) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->chain_ev) cudaEventDestroy(e);
     cudaEvent_t evs[] = {h->ev_a, h->ev_b, h->ev_c, h->ev_d, h->ev_fork, h->ev_next, h->ev_h2d};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
