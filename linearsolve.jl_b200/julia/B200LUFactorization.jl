@@ -57,13 +57,23 @@ cache, so `cache.b = b2; solve!(cache)` only runs getrs.
 struct B200LUFactorization <: AbstractFactorization
     residualsafety::Bool
     device::Int
-    function B200LUFactorization(; throwerror = true, residualsafety::Bool = false, device::Int = 0)
+    devices::Vector{Cint}      # more than one entry: ONE cache drives all these GPUs (b200lu_create with ngpus > 1)
+    function B200LUFactorization(; throwerror = true, residualsafety::Bool = false, device::Int = 0,
+            devices = nothing)
         if throwerror && !useb200()
             error("B200LUFactorization requires libb200lu.so and an NVIDIA B200 (sm_100) GPU")
         end
-        return new(residualsafety, device)
+        devs = devices === nothing ? Cint[device] : collect(Cint, devices)    # e.g. devices = 0:7
+        length(devs) > 1 && residualsafety &&
+            error("residualsafety needs the single-GPU handle (the multi-GPU handle keeps no copy of A)")
+        return new(residualsafety, Int(first(devs)), devs)
     end
 end
+
+# smallest n at which `defaultalg` prefers the GPU path when it is available: above every CPU band of
+# src/default.jl:444-474 (the reference's own guidance for GPU offload is "around 1,000 x 1,000",
+# docs/src/tutorials/gpu.md:19-22), so machines without the library select exactly what they select today
+const B200LU_DEFAULT_MIN_N = 1024
 
 """
     B200LU32MixedLUFactorization(; refine = true, maxiters = 10, throwerror = true)
@@ -144,9 +154,12 @@ end
 function _b200lu_ensure_handle!(c::B200LUCache, alg)
     c.handle != C_NULL && return c
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    dev = Cint[alg.device]
+    dev = alg isa B200LUFactorization ? alg.devices : Cint[alg.device]
+    # ngpus > 1: the library distributes the host matrix 1-D block-cyclic over the GPUs itself (each GPU pulls
+    # its column blocks over its own PCIe link) and shards BlockDiagonal batches by index
     rc = ccall((:b200lu_create, libb200lu[]), Cint,
-        (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Cint}), h, c.dtype, 1, dev)
+        (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Cint}), h, c.dtype, length(dev), dev)
+    rc == 5 && error("b200lu_create: the devices $(Int.(dev)) are not all peers of each other (NVLink / NVSwitch)")
     rc == 0 || error("b200lu_create failed with status $rc (no usable sm_100 device; there is no CPU fallback)")
     c.handle = h[]
     if alg isa B200LU32MixedLUFactorization
@@ -203,7 +216,18 @@ end
 # The mixed-precision handle refines the TRANSPOSED system (FP32 transposed sweeps + FP64 residual
 # b - A'x), so both algorithms reuse their factors.
 const _B200LUAlgs = Union{B200LUFactorization, B200LU32MixedLUFactorization}
-_custom_can_reuse_adjoint_factorization(::_B200LUAlgs, c::B200LUCache) = c.handle != C_NULL
+_custom_can_reuse_adjoint_factorization(::B200LU32MixedLUFactorization, c::B200LUCache) = c.handle != C_NULL
+# (the multi-GPU handle solves with trans = 'N' only: its adjoint is refactorized by the generic path)
+_custom_can_reuse_adjoint_factorization(alg::B200LUFactorization, c::B200LUCache) =
+    c.handle != C_NULL && length(alg.devices) == 1
+# `defaultalg_adjoint_eval` (src/default.jl:1262-1348): dy is overwritten with adjoint(A) \ dy
+function _b200lu_solve_trans!(c::B200LUCache, dy::StridedVecOrMat{T}) where {T}
+    rc = ccall((:b200lu_solve, libb200lu[]), Cint,
+        (Ptr{Cvoid}, UInt8, Int64, Ptr{T}, Int64, Ptr{T}, Int64),
+        c.handle, UInt8('T'), size(dy, 2), dy, max(1, stride(dy, 2)), dy, max(1, stride(dy, 2)))
+    rc == 0 || _b200lu_error(c, rc)
+    return dy
+end
 function _custom_adjoint_factorization_solve(alg::_B200LUAlgs, c::B200LUCache, A, b)
     u = similar(b)
     return _direct_lu_solve!(c, u, b, alg; trans = 'T')
@@ -276,6 +300,22 @@ function _b200lu_factor_blocks!(c::B200LUCache, blocks::Vector{Matrix{T}}, alg) 
     rc == 0 || _b200lu_error(c, rc)
     c.n = m
     return all(iszero, info)                           # success = all(issuccess), :121-124
+end
+
+# `solve!` on a FRESH cache with a vector right-hand side, blocks of up to 64 rows: getrf of every block and
+# getrs of its segment of b in ONE kernel launch (A read once, factors written once and kept for later
+# solves) — per-block `lu!` followed by per-block `ldiv!`, ext/LinearSolveBlockDiagonalsExt.jl:119-125,183-205
+function _b200lu_factor_solve_blocks!(c::B200LUCache, x::Matrix{T}, packed::Array{T, 3}, rhs::Matrix{T}, alg) where {T}
+    m, _, batch = size(packed)
+    _b200lu_ensure_handle!(c, alg)
+    ipiv = Vector{BlasInt}(undef, m * batch)
+    info = Vector{BlasInt}(undef, batch)
+    rc = ccall((:b200lu_factor_solve_batched, libb200lu[]), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{T}, Int64, Int64, Ptr{T}, Int64, Ptr{T}, Int64, Ptr{BlasInt}, Ptr{BlasInt}),
+        c.handle, batch, m, packed, m, m * m, rhs, m, x, m, ipiv, info)
+    rc == 0 || _b200lu_error(c, rc)
+    c.n = m
+    return all(iszero, info)
 end
 
 # per-block ldiv! on views of b (:183-205); rhs[:, :, s] is the zero-padded m x nrhs block of b that
