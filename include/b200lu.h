@@ -106,8 +106,9 @@ enum {
     B200LU_OPT_PROFILE = 5,     /* 1: bracket every trailing GEMM with CUDA events */
     B200LU_OPT_PANEL_RPT = 6,   /* rows per thread in the base panel: 0 auto, 1, 2 */
     B200LU_OPT_GEMM_CFG = 7,    /* FP64 trailing-update tile configuration 0..2, 3 = auto (default) */
-    B200LU_OPT_PANEL_MODE = 8,  /* base panel: 0 auto (cluster/DSMEM kernel when the panel fits
-                                   16 CTAs, else L2 mailbox), 1 always L2 mailbox  */
+    B200LU_OPT_PANEL_MODE = 8,  /* base panel: 0 auto = the left-looking fused cluster/DSMEM kernel (2-4 sub-blocks of
+                                   8 / 16 / 32 columns per launch; FP64 panels of up to 32768 rows), L2 mailbox above;
+                                   1 always L2 mailbox; 2 = the round-1 cluster kernels, one block per launch     */
     B200LU_OPT_SGEMM_MODE = 9,  /* FP32 trailing update: 0 auto (tcgen05 3xTF32 kernel for large
                                    updates, FFMA otherwise), 1 always FFMA          */
     B200LU_OPT_TRSV_MODE = 10,  /* single-RHS getrs: 0 auto (n >= 6144: mode 3, else mode 2;

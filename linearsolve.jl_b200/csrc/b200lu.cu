@@ -464,15 +464,15 @@ static int launch_laswp(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda, in
 }
 
 // ------------------------------------------------------ cluster base panel --
-template <typename T, int W, int RPT, int NTV = PCL_NT>
+template <typename T, int W, int RPT, int NSUB = 1, int NTV = PCL_NT>
 static int launch_panel_cluster_cfg(b200lu_handle* h, cudaStream_t st, PanelArgs<T> p) {
     constexpr int PCL_NT = NTV;   // threads per CTA of this instantiation
-    auto kern = panel_cluster_kernel<T, W, RPT, PCL_NT>;
+    auto kern = panel_cluster_kernel<T, W, RPT, PCL_NT, NSUB>;
+    constexpr size_t smem = pcl_smem_bytes<T, W, RPT, PCL_NT, NSUB>();
     static std::atomic<bool> attr_dev[64]; std::atomic<bool>& attr_set = attr_dev[h->dev & 63];   /* function attributes are per device */
     if (!attr_set) {
         CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)pcl_tile_bytes<T, W, RPT, PCL_NT>()));
+        CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     int G = 1;
@@ -482,7 +482,7 @@ static int launch_panel_cluster_cfg(b200lu_handle* h, cudaStream_t st, PanelArgs
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G);
     cfg.blockDim = dim3(PCL_NT);
-    cfg.dynamicSmemBytes = pcl_tile_bytes<T, W, RPT, PCL_NT>();
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -503,25 +503,57 @@ static int launch_panel_cluster_cfg(b200lu_handle* h, cudaStream_t st, PanelArgs
     return 0;
 }
 
-// Base width of the cluster kernel for a panel of m rows (0 = does not fit: use the L2-mailbox
-// kernel of panel.cuh).  256 threads hold up to 128 data registers per thread: 32 doubles x 2
-// rows (16 CTAs x 512 rows = 8192 rows), 16 doubles x 4 rows or 32 floats x 4 rows (16384 rows).
+// Panel classes of the cluster kernel (rows m of the panel -> base width W, rows per thread, sub-blocks fused
+// into one launch; B200LU_OPT_PANEL_MODE 0 = fused, 2 = the round-1 kernels: one W-wide block per launch):
+//   FP64:  m <=  4096: 32 x 1, 4 sub-blocks (128 columns per launch)     FP32:  m <=  4096: 32 x 1, 4
+//          m <=  8192: 32 x 2, 2 sub-blocks ( 64)                                m <=  8192: 32 x 2, 4
+//          m <= 16384: 16 x 4, 4 sub-blocks ( 64)                                m <= 16384: 32 x 4, 2
+//          m <= 32768:  8 x 8, 4 sub-blocks ( 32)   [fused only; round 1: L2 mailbox]
+// 256 threads hold up to 128 data registers per thread: 32 doubles x 2 rows, 16 x 4, 8 x 8.
+constexpr int PCL_ROWS1 = PCL_GMAX * PCL_NT;       // 4096 rows at one row per thread
 constexpr int PCL_ROWS2 = PCL_GMAX * PCL_NT * 2;
+static bool panel_fused(const b200lu_handle* h) { return h->opt[B200LU_OPT_PANEL_MODE] == 0; }
+
+// Base width of the cluster kernel for an OUTER panel of m rows (0 = does not fit: L2-mailbox kernel of panel.cuh).
 template <typename T>
 static int cluster_base_width(const b200lu_handle* h, int m) {
     if (h->opt[B200LU_OPT_PANEL_MODE] == 1) return 0;
     if (m <= PCL_ROWS2) return 32;
     if (m <= 2 * PCL_ROWS2) return sizeof(T) == 8 ? 16 : 32;
+    if (m <= 4 * PCL_ROWS2 && sizeof(T) == 8 && panel_fused(h)) return 8;
     return 0;
+}
+// Columns one launch factors: the base width times the sub-blocks its class fuses
+template <typename T>
+static int cluster_group_width(const b200lu_handle* h, int m, int bw) {
+    if (!panel_fused(h) || bw == 0) return bw;
+    if (sizeof(T) == 8) {
+        if (bw == 32) return m <= PCL_ROWS1 ? 128 : 64;
+        if (bw == 16) return 64;
+        return 32;   // bw == 8
+    }
+    return m <= PCL_ROWS2 ? 128 : 64;
+}
+
+// can a panel of m rows with base width bw run on the cluster kernel?
+template <typename T>
+static bool cluster_usable(const b200lu_handle* h, int m, int bw) {
+    if (h->opt[B200LU_OPT_PANEL_MODE] == 1) return false;
+    if (m <= PCL_ROWS2) return true;
+    if (m <= 2 * PCL_ROWS2) return sizeof(T) == 4 || bw <= 16;
+    return m <= 4 * PCL_ROWS2 && sizeof(T) == 8 && panel_fused(h) && bw <= 8;
 }
 
 template <typename T>
 static int launch_panel_any(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda, int nrows, int j0,
                             int wc, int pc0, int pc1, int bw) {
     const int m = nrows - j0;
-    const bool cluster_ok = h->opt[B200LU_OPT_PANEL_MODE] != 1 && m <= 2 * PCL_ROWS2 &&
-                            (m <= PCL_ROWS2 || sizeof(T) == 4 || bw <= 16);
-    if (!cluster_ok) return launch_panel_base<T>(h, st, A, lda, nrows, j0, wc, pc0, pc1);
+    const bool fused = panel_fused(h);
+    const bool cluster_ok = cluster_usable<T>(h, m, bw);
+    if (!cluster_ok) {
+        if (wc > BASE_W) return -1000;   // the caller splits down to the mailbox kernel's width
+        return launch_panel_base<T>(h, st, A, lda, nrows, j0, wc, pc0, pc1);
+    }
     PanelArgs<T> p;
     p.A = A;
     p.lda = lda;
@@ -539,28 +571,49 @@ static int launch_panel_any(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda
     p.dbg = h->d_pdbg ? h->d_pdbg + 16 * (h->pdbg_n++ % 4096) : nullptr;
     int rc;
     if constexpr (sizeof(T) == 8) {
-        // one row per thread while 16 CTAs x 256 threads cover the panel (measured: n = 4096 10.3 -> 9.6 ms)
-        if (bw > 16) rc = (m <= PCL_GMAX * PCL_NT) ? launch_panel_cluster_cfg<T, 32, 1>(h, st, p)
-                                                   : launch_panel_cluster_cfg<T, 32, 2>(h, st, p);
-        else if (m <= PCL_ROWS2) rc = launch_panel_cluster_cfg<T, 16, 2>(h, st, p);
-        else rc = launch_panel_cluster_cfg<T, 16, 4>(h, st, p);
+        if (fused) {
+            if (bw > 16) rc = (m <= PCL_ROWS1) ? launch_panel_cluster_cfg<T, 32, 1, 4>(h, st, p)
+                                               : launch_panel_cluster_cfg<T, 32, 2, 2>(h, st, p);
+            else if (bw > 8) rc = launch_panel_cluster_cfg<T, 16, 4, 4>(h, st, p);
+            else rc = launch_panel_cluster_cfg<T, 8, 8, 4>(h, st, p);
+        } else {
+            // one row per thread while 16 CTAs x 256 threads cover the panel (measured: n = 4096 10.3 -> 9.6 ms)
+            if (bw > 16) rc = (m <= PCL_ROWS1) ? launch_panel_cluster_cfg<T, 32, 1>(h, st, p)
+                                               : launch_panel_cluster_cfg<T, 32, 2>(h, st, p);
+            else if (m <= PCL_ROWS2) rc = launch_panel_cluster_cfg<T, 16, 2>(h, st, p);
+            else rc = launch_panel_cluster_cfg<T, 16, 4>(h, st, p);
+        }
     } else {
-        if (m <= PCL_GMAX * PCL_NT) rc = launch_panel_cluster_cfg<T, 32, 1>(h, st, p);
-        else if (m <= PCL_ROWS2) rc = launch_panel_cluster_cfg<T, 32, 2>(h, st, p);
-        else rc = launch_panel_cluster_cfg<T, 32, 4>(h, st, p);
+        if (fused) {
+            if (m <= PCL_ROWS1) rc = launch_panel_cluster_cfg<T, 32, 1, 4>(h, st, p);
+            else if (m <= PCL_ROWS2) rc = launch_panel_cluster_cfg<T, 32, 2, 4>(h, st, p);
+            else rc = launch_panel_cluster_cfg<T, 32, 4, 2>(h, st, p);
+        } else {
+            if (m <= PCL_ROWS1) rc = launch_panel_cluster_cfg<T, 32, 1>(h, st, p);
+            else if (m <= PCL_ROWS2) rc = launch_panel_cluster_cfg<T, 32, 2>(h, st, p);
+            else rc = launch_panel_cluster_cfg<T, 32, 4>(h, st, p);
+        }
     }
-    if (rc == -1000) return launch_panel_base<T>(h, st, A, lda, nrows, j0, wc, pc0, pc1);
+    if (rc == -1000 && wc <= BASE_W) return launch_panel_base<T>(h, st, A, lda, nrows, j0, wc, pc0, pc1);
     return rc;
 }
 
 // ---------------------------------------------------------- recursive panel --
 // Factor columns [j0, j0+w) of the nrows x * matrix (rows j0..nrows-1) inside the
-// outer panel [pc0, pc1), recursing down to base blocks of width bw.  Interchanges
-// are applied to the whole outer panel by the base kernels, so no laswp appears here.
+// outer panel [pc0, pc1), recursing down to groups the base kernels take in one launch (bw columns
+// for the round-1 kernels and the L2 mailbox, bw x fused sub-blocks for the left-looking cluster kernel).
+// Interchanges are applied to the whole outer panel by the base kernels, so no laswp appears here.
 template <typename T>
 static int panel_recursive(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda, int nrows, int j0,
                            int w, int pc0, int pc1, int bw) {
-    if (w <= bw) return launch_panel_any<T>(h, st, A, lda, nrows, j0, w, pc0, pc1, bw);
+    const int gw = cluster_usable<T>(h, nrows - j0, bw) ? std::max(bw, cluster_group_width<T>(h, nrows - j0, bw)) : bw;
+    if (w <= gw) {
+        const int rc0 = launch_panel_any<T>(h, st, A, lda, nrows, j0, w, pc0, pc1, bw);
+        if (rc0 != -1000) return rc0;
+        // the cluster launch was refused (the handle has switched to the L2 mailbox): split down to its width
+        if (w <= BASE_W) return launch_panel_base<T>(h, st, A, lda, nrows, j0, w, pc0, pc1);
+        bw = BASE_W;
+    }
     const int w1 = ((w / 2 + bw - 1) / bw) * bw;
     const int w2 = w - w1;
     int rc = panel_recursive<T>(h, st, A, lda, nrows, j0, w1, pc0, pc1, bw);
@@ -1581,7 +1634,7 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_REFINE_MAXIT && value < 0) return -3;
     if (option == B200LU_OPT_PANEL_RPT && (value < 0 || value > 2)) return -3;
     if (option == B200LU_OPT_GEMM_CFG && (value < 0 || value > 3)) return -3;
-    if (option == B200LU_OPT_PANEL_MODE && (value < 0 || value > 1)) return -3;
+    if (option == B200LU_OPT_PANEL_MODE && (value < 0 || value > 2)) return -3;
     if (option == B200LU_OPT_SGEMM_MODE && (value < 0 || value > 2)) return -3;
     if (option == B200LU_OPT_TRSV_MODE && (value < 0 || value > 3)) return -3;
     if (option == B200LU_OPT_STREAM_H2D && (value < 0 || value > 1)) return -3;

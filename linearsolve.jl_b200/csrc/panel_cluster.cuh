@@ -149,6 +149,13 @@ struct PclShared {
 };
 template <typename T, int W, int RPT, int NT>
 constexpr size_t pcl_tile_bytes() { return (size_t)W * NT * RPT * sizeof(T); }
+// NSUB > 1 (left-looking fused kernel): behind the tile, U of the current sub-block's columns on the rows of the
+// earlier sub-blocks (MAXTOP x W) and the strictly lower triangle of their L11 (MAXTOP x MAXTOP)
+template <typename T, int W, int RPT, int NT, int NSUB>
+constexpr size_t pcl_smem_bytes() {
+    return pcl_tile_bytes<T, W, RPT, NT>() + (size_t)(NSUB - 1) * W * W * sizeof(T) +
+           (size_t)(NSUB - 1) * W * (NSUB - 1) * W * sizeof(T);
+}
 
 // local candidate of the current column (register index 0): strict '>' from amax = 0 (NaN never
 // wins), lowest position on ties; rows at positions < j are finished
@@ -165,7 +172,16 @@ __device__ __forceinline__ void pcl_local_cand(const T (&a)[RPT][W], const int (
     }
 }
 
-template <typename T, int W, int RPT, int NT>
+// NSUB > 1: ONE launch factors up to NSUB consecutive W-wide sub-blocks of the outer panel (p.wc = their total
+// width), LEFT-LOOKING: before sub-block s is eliminated, the cluster itself applies the updates of the sub-blocks
+// 0 .. s-1 of this launch to it — U = L11^{-1} A12 on the s W rows already pivoted (every CTA redundantly, warp-local
+// forward substitution in registers, L11 staged in shared memory), then a[c] -= sum_k L[row, k] U[k, c] for the
+// thread's own rows with its multipliers streamed from global memory (L2) and U broadcast from shared memory.
+// That replaces the unit-lower TRSM + Schur GEMM launch pairs of the recursive panel between these sub-blocks and
+// NSUB - 1 base-kernel launches (their load / exit / launch gaps); the arithmetic of an entry is the FMA sequence
+// pivot 0, 1, 2, ... of the unblocked algorithm.  Sub-blocks are separated by a cluster barrier (global-memory
+// visibility: barrier.cluster release / acquire + __threadfence, loads of data other CTAs wrote go through L2).
+template <typename T, int W, int RPT, int NT, int NSUB = 1>
 __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
     constexpr int NW = NT / 32;
     constexpr int EPV = 16 / (int)sizeof(T);       // elements per 16-byte vector
@@ -184,7 +200,13 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
     const int me = (int)pcl_cluster_rank();
     const int G = (int)pcl_cluster_size();   // power of two
     const int lgG = 31 - __clz(G);
-    const int wc = p.wc;
+    constexpr int MAXTOP = (NSUB - 1) * W;
+    T* Us = tile + (size_t)W * ROWS;           // [MAXTOP][W]   (NSUB > 1)
+    T* Ls = Us + (size_t)MAXTOP * W;           // [MAXTOP][MAXTOP]: Ls[k * MAXTOP + r] = L11[r, k], r > k
+    const int J0 = p.j0;                       // first row / column of the launch
+    const int wtot = p.wc;
+    const int nsub = NSUB > 1 ? (wtot + W - 1) / W : 1;
+    if (NSUB > 1) p.wc = min(W, wtot);
 
     if (tid == 0) {
         pcl_mbar_init(pcl_smem_u32(&sh.mbar[0]), 1);
@@ -195,6 +217,16 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
     const bool dbg = p.dbg != nullptr && me == 0 && tid == 0;
     if (dbg) p.dbg[0] = clock64();
 
+    // sender role / inbox addresses do not depend on the sub-block
+    const int s_dst = tid & (G - 1), s_k = tid >> lgG;
+    const unsigned raddr0 = pcl_mapa(pcl_smem_u32(&sh.box[0][me][1 + (s_k < NV ? s_k : 0)]), (unsigned)s_dst);
+    const unsigned rhdr0 = pcl_mapa(pcl_smem_u32(&sh.box[0][me][0]), (unsigned)s_dst);
+    const unsigned rbar0 = pcl_mapa(pcl_smem_u32(&sh.mbar[0]), (unsigned)s_dst);
+    constexpr unsigned BOXB = (unsigned)sizeof(sh.box[0]);   // parity stride of the inbox
+
+#pragma unroll 1
+    for (int sub = 0; sub < nsub; ++sub) {
+    const int wc = p.wc;
     T a[RPT][W];   // a[q][c]: column (j + c) of row q while column j is being eliminated
     int ri[RPT];   // panel-local ORIGINAL row of each owned row (where it is loaded from)
     int pos[RPT];  // its current position in the LAPACK row order
@@ -205,23 +237,87 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
         const T* src = p.A + (long long)p.j0 * p.lda + (p.j0 + (ri[q] < p.m ? ri[q] : 0));
 #pragma unroll
         for (int c = 0; c < W; ++c) {
-            a[q][c] = (ri[q] < p.m && c < wc) ? src[(long long)c * p.lda] : T(0);
+            // (NSUB > 1: other CTAs of the cluster moved these rows in the previous sub-block: read through L2)
+            a[q][c] = (ri[q] < p.m && c < wc) ? (NSUB > 1 ? __ldcg(src + (long long)c * p.lda) : src[(long long)c * p.lda]) : T(0);
         }
     }
-    // sender role: thread (dst, k) pushes row vector k of this CTA's message to CTA dst; the
-    // threads with k == 0 also push the header
-    const int s_dst = tid & (G - 1), s_k = tid >> lgG;
-    const unsigned raddr0 = pcl_mapa(pcl_smem_u32(&sh.box[0][me][1 + (s_k < NV ? s_k : 0)]), (unsigned)s_dst);
-    const unsigned rhdr0 = pcl_mapa(pcl_smem_u32(&sh.box[0][me][0]), (unsigned)s_dst);
-    const unsigned rbar0 = pcl_mapa(pcl_smem_u32(&sh.mbar[0]), (unsigned)s_dst);
-    constexpr unsigned BOXB = (unsigned)sizeof(sh.box[0]);   // parity stride of the inbox
+    if constexpr (NSUB > 1) {
+        if (sub > 0) {
+            const int sW = p.j0 - J0;   // rows / columns already factored in this launch
+            // ---- A: U = L11^{-1} A[J0 .. J0 + sW, sub-block] in every CTA: L11 to shared memory ...
+            for (int idx = tid; idx < sW * sW; idx += NT) {
+                const int k = idx / sW, r = idx - k * sW;
+                Ls[k * MAXTOP + r] = (r > k) ? __ldcg(p.A + (long long)(J0 + k) * p.lda + J0 + r) : T(0);
+            }
+            __syncthreads();
+            // ... each warp solves its CC columns in registers (lane l holds rows l, l + 32, ...)
+            constexpr int CC = (W + NW - 1) / NW, RR = (MAXTOP + 31) / 32;
+            T bt[RR][CC];
+#pragma unroll
+            for (int rr = 0; rr < RR; ++rr)
+#pragma unroll
+                for (int c = 0; c < CC; ++c) {
+                    const int row = rr * 32 + lane, col = warp * CC + c;
+                    bt[rr][c] = (row < sW && col < wc) ? __ldcg(p.A + (long long)(p.j0 + col) * p.lda + J0 + row) : T(0);
+                }
+#pragma unroll
+            for (int kr = 0; kr < RR; ++kr) {
+                if (kr * 32 < sW) {
+                    const int kend = min(32, sW - kr * 32);
+                    for (int kk = 0; kk < kend; ++kk) {
+                        const int k = kr * 32 + kk;
+                        T xk[CC];
+#pragma unroll
+                        for (int c = 0; c < CC; ++c) xk[c] = __shfl_sync(0xffffffffu, bt[kr][c], kk);
+#pragma unroll
+                        for (int rr = kr; rr < RR; ++rr) {
+                            const T l = (rr * 32 + lane < MAXTOP) ? Ls[k * MAXTOP + rr * 32 + lane] : T(0);   // 0 for rows <= k
+#pragma unroll
+                            for (int c = 0; c < CC; ++c) bt[rr][c] = tfma(-l, xk[c], bt[rr][c]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < RR; ++rr)
+#pragma unroll
+                for (int c = 0; c < CC; ++c) {
+                    const int row = rr * 32 + lane, col = warp * CC + c;
+                    // (global memory still holds the unsolved rows: every CTA reads them above, so the final U
+                    // entries are written out only after the column loop, when all CTAs are past this point)
+                    if (row < sW && col < W) Us[row * W + col] = bt[rr][c];
+                }
+            __syncthreads();
+            // ---- B: the thread's own rows: a[c] -= sum_k L[row, k] U[k, c], k ascending (4 multipliers in flight)
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) {
+                if (ri[q] < p.m) {
+                    const T* lrow = p.A + (long long)J0 * p.lda + (p.j0 + ri[q]);
+                    for (int k0 = 0; k0 < sW; k0 += 4) {   // sW is a multiple of W >= 8
+                        T l4[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) l4[i] = __ldcg(lrow + (long long)(k0 + i) * p.lda);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const T nl = -l4[i];
+                            const T* urow = Us + (k0 + i) * W;
+#pragma unroll
+                            for (int c = 0; c < W; ++c) a[q][c] = tfma(nl, urow[c], a[q][c]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // sender role (set up before the sub-block loop): thread (dst, k) pushes row vector k of this CTA's
+    // message to CTA dst; the threads with k == 0 also push the header
     // warp 0 of every CTA tracks which original row sits at each touched position
     int top_src = lane;      // lane l < W: original row now at position l
     int ext_row = -1;        // lane e: e-th position >= W that took part in an interchange
     int ext_src = -1;        //         and the original row now sitting there
     int ext_n = 0;
 
-    pcl_cluster_sync();  // mbarriers initialised cluster-wide before any st.async
+    if (sub == 0) pcl_cluster_sync();  // mbarriers initialised cluster-wide before any st.async
     if (dbg) p.dbg[1] = clock64();
 #ifdef PCL_TIMING
     long long tacc[6] = {0, 0, 0, 0, 0, 0};
@@ -429,6 +525,15 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
     // every finished entry of this CTA's rows now sits in the tile: write the block back, every
     // row at its final position
     __syncthreads();
+    if constexpr (NSUB > 1) {
+        if (sub > 0 && me == 0) {   // U of this sub-block's columns on the rows of the earlier sub-blocks
+            const int sW = p.j0 - J0;
+            for (int idx = tid; idx < sW * wc; idx += NT) {
+                const int c = idx / sW, r = idx - c * sW;
+                p.A[(long long)(p.j0 + c) * p.lda + J0 + r] = Us[r * W + c];
+            }
+        }
+    }
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
         if (ri[q] < p.m) {
@@ -471,7 +576,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
                     const int col = (c < nleft) ? (p.pc0 + c) : (p.j0 + wc + (c - nleft));
                     base[u] = p.A + (long long)col * p.lda + p.j0;
                     v[u] = T(0);
-                    if (on[u]) v[u] = base[u][src];
+                    if (on[u]) v[u] = NSUB > 1 ? __ldcg(base[u] + src) : base[u][src];
                 }
                 __syncthreads();
 #pragma unroll
@@ -481,8 +586,13 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
         }
     }
     if (dbg) p.dbg[4] = clock64();
-    pcl_cluster_sync();  // no CTA leaves while a peer could still address its shared memory
+    if (NSUB > 1) __threadfence();   // this sub-block's global writes before the barrier's release
+    pcl_cluster_sync();  // no CTA leaves (or starts the next sub-block) while a peer could still address its shared memory
     if (dbg) { p.dbg[5] = clock64(); p.dbg[6] = p.m; p.dbg[7] = G; }
+    p.j0 += W;
+    p.m -= W;
+    p.wc = min(W, wtot - (sub + 1) * W);
+    }   // sub-blocks
 }
 
 }  // namespace b200lu
