@@ -45,7 +45,10 @@ def test_mixed_adjoint_refines_transposed_system(gpu_required, ls, n):
     _, info = h.factor(A)
     assert info == 0
     x32 = h.solve(b, trans="T")
-    assert np.linalg.norm(x32 - xt) / np.linalg.norm(xt) < 1e-3
+    # FP32 accuracy class: the backward error bar of the FP32 element type (the forward error is that times the
+    # condition number: ~1e-3 at n = 2500 for this matrix, and it moves with the rounding order of the kernels)
+    assert _berr(A.T, x32, b) <= 10 * n * np.finfo(np.float32).eps
+    assert np.linalg.norm(x32 - xt) / np.linalg.norm(xt) < 1e-2
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
