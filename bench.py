@@ -678,7 +678,9 @@ def bench_dist(args, ls, torch, dist, dev, rank, world, local, barrier, max_over
     factors the panel and stores it into its peers' windows, look-ahead, distributed getrs.  Strong
     scaling: `value` = 2/3 n^3 / (max over ranks of the device time of factor_dist + solve_dist)."""
     C = ls._capi
-    n, nrhs, nb = args.n, args.nrhs, (args.nb or 256)
+    # outer panel width: 256 on one or two GPUs (the run is bound by the trailing GEMM), 128 from four GPUs on (the
+    # run is bound by the panel chain: narrower panels shorten every look-ahead update and every hand-off)
+    n, nrhs, nb = args.n, args.nrhs, (args.nb or (128 if world >= 4 else 256))
     eps = np.finfo(np.float64).eps
 
     def make_handle():

@@ -288,22 +288,29 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
                     if (row < sW && col < W) Us[row * W + col] = bt[rr][c];
                 }
             __syncthreads();
-            // ---- B: the thread's own rows: a[c] -= sum_k L[row, k] U[k, c], k ascending (4 multipliers in flight)
+            // ---- B: the thread's own rows: a[c] -= sum_k L[row, k] U[k, c], k ascending; the multipliers come from
+            // L2 (written by this launch's earlier sub-blocks): the next 4 are in flight under the 4 x W FMAs of the
+            // current ones (two warps per scheduler hide little latency on their own)
 #pragma unroll
             for (int q = 0; q < RPT; ++q) {
                 if (ri[q] < p.m) {
                     const T* lrow = p.A + (long long)J0 * p.lda + (p.j0 + ri[q]);
-                    for (int k0 = 0; k0 < sW; k0 += 4) {   // sW is a multiple of W >= 8
-                        T l4[4];
+                    T lc[4], ln[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) l4[i] = __ldcg(lrow + (long long)(k0 + i) * p.lda);
+                    for (int i = 0; i < 4; ++i) lc[i] = __ldcg(lrow + (long long)i * p.lda);
+                    for (int k0 = 0; k0 < sW; k0 += 4) {   // sW is a multiple of W >= 8
+                        const bool more = k0 + 4 < sW;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) ln[i] = more ? __ldcg(lrow + (long long)(k0 + 4 + i) * p.lda) : T(0);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const T nl = -l4[i];
+                            const T nl = -lc[i];
                             const T* urow = Us + (k0 + i) * W;
 #pragma unroll
                             for (int c = 0; c < W; ++c) a[q][c] = tfma(nl, urow[c], a[q][c]);
                         }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) lc[i] = ln[i];
                     }
                 }
             }
