@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb200lu.so")
+# B200LU_LIB: an instrumented build of the same library (e.g. -DPCL_TIMING for the panel kernels' clock64 stamps)
+LIB_PATH = os.environ.get("B200LU_LIB") or os.path.join(_HERE, "csrc", "libb200lu.so")
 
 F64, F32, MIXED = 0, 1, 2
 T_H2D, T_FACTOR, T_SOLVE, T_D2H, T_GEMM, T_PANEL, T_LOOKAHEAD, T_PUSH = range(8)

@@ -1496,11 +1496,12 @@ void b200lu_destroy(b200lu_handle* h) {
         const int cnt = std::min(h->pdbg_n, 4096);
         std::vector<long long> t((size_t)cnt * 16);
         cudaMemcpy(t.data(), h->d_pdbg, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        for (int i = std::max(0, cnt - 256); i < cnt; i += 8) {
+        const int step = std::max(1, cnt / 96);   // ~96 lines over the whole run (B200LU_PANEL_DBG=1)
+        for (int i = 0; i < cnt; i += step) {
             const long long* s = &t[(size_t)i * 16];
             fprintf(stderr, "[pdbg] launch %d m=%lld G=%lld: load %lld loop %lld store %lld swaps %lld exit %lld cycles\n", i, s[6], s[7],
                     s[1] - s[0], s[2] - s[1], s[3] - s[2], s[4] - s[3], s[5] - s[4]);
-            if (s[8] | s[9]) fprintf(stderr, "[pdbg]    per-column sums: argmax+stage %lld | bar+send %lld | wait %lld | reduce %lld | update %lld | loop-overhead %lld\n", s[8], s[9], s[10], s[11], s[12], s[13]);
+            if (s[8] | s[9]) fprintf(stderr, "[pdbg]    last sub-block, sums over its columns: publish-prep %lld | barrier+cta-reduce+send %lld | wait %lld | cluster-reduce %lld | freeze+positions+scale %lld | rank-1 update %lld | argmax-finish+stage %lld | loop-overhead %lld\n", s[8], s[9], s[10], s[11], s[14], s[15], s[12], s[13]);
         }
         cudaFree(h->d_pdbg);
     }

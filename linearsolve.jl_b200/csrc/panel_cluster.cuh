@@ -288,31 +288,43 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
                     if (row < sW && col < W) Us[row * W + col] = bt[rr][c];
                 }
             __syncthreads();
-            // ---- B: the thread's own rows: a[c] -= sum_k L[row, k] U[k, c], k ascending; the multipliers come from
-            // L2 (written by this launch's earlier sub-blocks): the next 4 are in flight under the 4 x W FMAs of the
-            // current ones (two warps per scheduler hide little latency on their own)
-#pragma unroll
-            for (int q = 0; q < RPT; ++q) {
-                if (ri[q] < p.m) {
-                    const T* lrow = p.A + (long long)J0 * p.lda + (p.j0 + ri[q]);
-                    T lc[4], ln[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) lc[i] = __ldcg(lrow + (long long)i * p.lda);
-                    for (int k0 = 0; k0 < sW; k0 += 4) {   // sW is a multiple of W >= 8
-                        const bool more = k0 + 4 < sW;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) ln[i] = more ? __ldcg(lrow + (long long)(k0 + 4 + i) * p.lda) : T(0);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const T nl = -lc[i];
-                            const T* urow = Us + (k0 + i) * W;
-#pragma unroll
-                            for (int c = 0; c < W; ++c) a[q][c] = tfma(nl, urow[c], a[q][c]);
+            // ---- B: the thread's own rows: a[c] -= sum_k L[row, k] U[k, c], k ascending.  The multipliers L[row, k]
+            // (written to global memory by this launch's earlier sub-blocks) are staged W columns at a time into the
+            // tile, which is idle until the column loop, with asynchronous 8-byte copies (cp.async: every copy of
+            // the CTA in flight at once; loading them into registers a few at a time is bound by L2 latency with two
+            // warps per scheduler: measured 30 k cycles per 8-column sub-block at 8 rows per thread)
+            for (int k0 = 0; k0 < sW; k0 += W) {
+                {
+                    const long long rbase = (long long)p.j0 + (long long)me * ROWS;
+                    const int nrow = min(ROWS, p.m - me * ROWS);        // rows of this CTA inside the panel
+                    for (int c = 0; c < W; ++c) {
+                        const T* gcol = p.A + (long long)(J0 + k0 + c) * p.lda + rbase;
+                        for (int r = tid; r < nrow; r += NT) {
+                            const unsigned sa = pcl_smem_u32(tile + c * ROWS + r);
+                            if constexpr (sizeof(T) == 8)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gcol + r) : "memory");
+                            else
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gcol + r) : "memory");
                         }
+                    }
+                    cp_async_commit();
+                    cp_async_wait<0>();
+                }
+                __syncthreads();
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) lc[i] = ln[i];
+                for (int q = 0; q < RPT; ++q) {
+                    if (ri[q] < p.m) {
+                        const T* lq = tile + q * NT + tid;
+#pragma unroll 4
+                        for (int c = 0; c < W; ++c) {
+                            const T nl = -lq[c * ROWS];
+                            const T* urow = Us + (k0 + c) * W;
+#pragma unroll
+                            for (int cc = 0; cc < W; ++cc) a[q][cc] = tfma(nl, urow[cc], a[q][cc]);
+                        }
                     }
                 }
+                __syncthreads();   // the tile is overwritten by the next round / the column loop
             }
         }
     }
@@ -327,7 +339,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
     if (sub == 0) pcl_cluster_sync();  // mbarriers initialised cluster-wide before any st.async
     if (dbg) p.dbg[1] = clock64();
 #ifdef PCL_TIMING
-    long long tacc[6] = {0, 0, 0, 0, 0, 0};
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
 #endif
 
@@ -420,6 +432,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
             if (scale) a[q][0] *= rinv;               /* garbage in frozen rows is never read */     \
             if (upd) tile[j * ROWS + q * NT + tid] = a[q][0];                                        \
         }                                                                                            \
+        PCL_T(6);                                                                                    \
         /* next column first, so that its arg-max is in flight under the rest of the update */       \
         {                                                                                            \
             const T pr1 = prow[1];                                                                   \
@@ -440,6 +453,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
             a[q][0] = a[q][1];                                                                       \
             _Pragma("unroll") for (int c = 2; c < (LIVE); ++c) a[q][c - 1] = tfma(nl, prow[c], a[q][c]); \
         }                                                                                            \
+        PCL_T(7);                                                                                    \
         if (warp == 0 && piv != j) PCL_BOOKKEEP()                                                    \
         wl = pcl_argmax_finish(best, bpos, akey, amax);                                              \
         if (lane == wl) {   /* stage the row in the coordinates of column j + 1 */                   \
@@ -527,7 +541,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
 #undef PCL_BOOKKEEP
     if (dbg) p.dbg[2] = clock64();
 #ifdef PCL_TIMING
-    if (dbg) for (int i = 0; i < 6; ++i) p.dbg[8 + i] = tacc[i];
+    if (dbg) for (int i = 0; i < 8; ++i) p.dbg[8 + i] = tacc[i];
 #endif
     // every finished entry of this CTA's rows now sits in the tile: write the block back, every
     // row at its final position
