@@ -17,3 +17,10 @@ h.comm_init(None, 0, 1)
 A = torch.empty((n, n), dtype=torch.float64, device="cuda:0")
 h.fill_uniform_device(A.data_ptr(), n, n, n, seed=123)
 print("info", h.factor_dist(A.data_ptr(), n, n), "ms", h.timing(C.T_FACTOR))
+if len(sys.argv) > 3 and sys.argv[3] == "solve":
+    b = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    x = torch.empty_like(b)
+    h.fill_uniform_device(b.data_ptr(), n, n, 1, seed=7)
+    for _ in range(2):
+        h.solve_dist(b.data_ptr(), n, x.data_ptr(), n, 1)
+    print("solve ms", h.timing(C.T_SOLVE))
