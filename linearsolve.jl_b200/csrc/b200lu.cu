@@ -508,7 +508,7 @@ static int launch_panel_cluster_cfg(b200lu_handle* h, cudaStream_t st, PanelArgs
 //   FP64:  m <=  4096: 32 x 1, 4 sub-blocks (128 columns per launch)     FP32:  m <=  4096: 32 x 1, 4
 //          m <=  8192: 32 x 2, 2 sub-blocks ( 64)                                m <=  8192: 32 x 2, 4
 //          m <= 16384: 16 x 4, 4 sub-blocks ( 64)                                m <= 16384: 32 x 4, 2
-//          m <= 32768:  8 x 8, 4 sub-blocks ( 32)   [fused only; round 1: L2 mailbox]
+//          m <= 32768:  8 x 8, 8 sub-blocks ( 64)   [fused only; round 1: L2 mailbox]
 // 256 threads hold up to 128 data registers per thread: 32 doubles x 2 rows, 16 x 4, 8 x 8.
 constexpr int PCL_ROWS1 = PCL_GMAX * PCL_NT;       // 4096 rows at one row per thread
 constexpr int PCL_ROWS2 = PCL_GMAX * PCL_NT * 2;
@@ -530,7 +530,7 @@ static int cluster_group_width(const b200lu_handle* h, int m, int bw) {
     if (sizeof(T) == 8) {
         if (bw == 32) return m <= PCL_ROWS1 ? 128 : 64;
         if (bw == 16) return 64;
-        return 32;   // bw == 8
+        return 64;   // bw == 8
     }
     return m <= PCL_ROWS2 ? 128 : 64;
 }
@@ -575,7 +575,7 @@ static int launch_panel_any(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda
             if (bw > 16) rc = (m <= PCL_ROWS1) ? launch_panel_cluster_cfg<T, 32, 1, 4>(h, st, p)
                                                : launch_panel_cluster_cfg<T, 32, 2, 2>(h, st, p);
             else if (bw > 8) rc = launch_panel_cluster_cfg<T, 16, 4, 4>(h, st, p);
-            else rc = launch_panel_cluster_cfg<T, 8, 8, 4>(h, st, p);
+            else rc = launch_panel_cluster_cfg<T, 8, 8, 8>(h, st, p);
         } else {
             // one row per thread while 16 CTAs x 256 threads cover the panel (measured: n = 4096 10.3 -> 9.6 ms)
             if (bw > 16) rc = (m <= PCL_ROWS1) ? launch_panel_cluster_cfg<T, 32, 1>(h, st, p)

@@ -26,14 +26,10 @@ struct LaswpPlan {
 // came from by walking the interchange sequence backwards — positions are
 // independent, so the jb sequential swaps cost O(jb) steps in parallel instead
 // of a serial simulation.
-__global__ void __launch_bounds__(2 * LASWP_MAXSW)
-    laswp_plan_kernel(const int* __restrict__ ipiv, int k0, int nsw, LaswpPlan* __restrict__ plan) {
-    __shared__ int s_piv[LASWP_MAXSW];
-    __shared__ int s_cnt;
+// body shared by laswp_plan_kernel and the distributed engine's receive kernel: s_piv[0 .. nsw) (shared memory)
+// holds the pivots; all 2 * LASWP_MAXSW threads of the CTA take part
+__device__ __forceinline__ void laswp_plan_body(const int* s_piv, int* s_cnt, int k0, int nsw, LaswpPlan* __restrict__ plan) {
     const int t = threadIdx.x;
-    if (t < nsw) s_piv[t] = ipiv[k0 + t];
-    if (t == 0) s_cnt = 0;
-    __syncthreads();
     // Both loops have a uniform trip count and no early exit: an early `break` here left
     // the warp diverged for the rest of the kernel and serialised the 256-step walks
     // thread by thread (110 us instead of a few).
@@ -53,12 +49,23 @@ __global__ void __launch_bounds__(2 * LASWP_MAXSW)
         y = (y == a) ? b : ((y == b) ? a : y);
     }
     if (pos >= 0 && y != pos) {
-        const int slot = atomicAdd(&s_cnt, 1);
+        const int slot = atomicAdd(s_cnt, 1);
         plan->dst[slot] = pos;
         plan->src[slot] = y;
     }
     __syncthreads();
-    if (t == 0) plan->n_tot = s_cnt;
+    if (t == 0) plan->n_tot = *s_cnt;
+}
+
+__global__ void __launch_bounds__(2 * LASWP_MAXSW)
+    laswp_plan_kernel(const int* __restrict__ ipiv, int k0, int nsw, LaswpPlan* __restrict__ plan) {
+    __shared__ int s_piv[LASWP_MAXSW];
+    __shared__ int s_cnt;
+    const int t = threadIdx.x;
+    if (t < nsw) s_piv[t] = ipiv[k0 + t];
+    if (t == 0) s_cnt = 0;
+    __syncthreads();
+    laswp_plan_body(s_piv, &s_cnt, k0, nsw, plan);
 }
 
 // Columns [c0, c1) of A get the planned row gather. Each CTA walks column
