@@ -508,7 +508,7 @@ static int launch_panel_cluster_cfg(b200lu_handle* h, cudaStream_t st, PanelArgs
 //   FP64:  m <=  4096: 32 x 1, 4 sub-blocks (128 columns per launch)     FP32:  m <=  4096: 32 x 1, 4
 //          m <=  8192: 32 x 2, 2 sub-blocks ( 64)                                m <=  8192: 32 x 2, 4
 //          m <= 16384: 16 x 4, 4 sub-blocks ( 64)                                m <= 16384: 32 x 4, 2
-//          m <= 32768:  8 x 8, 8 sub-blocks ( 64)   [fused only; round 1: L2 mailbox]
+//          m <= 32768:  8 x 8, 4 sub-blocks ( 32)   [fused only; round 1: L2 mailbox; 8 sub-blocks measured: no gain]
 // 256 threads hold up to 128 data registers per thread: 32 doubles x 2 rows, 16 x 4, 8 x 8.
 constexpr int PCL_ROWS1 = PCL_GMAX * PCL_NT;       // 4096 rows at one row per thread
 constexpr int PCL_ROWS2 = PCL_GMAX * PCL_NT * 2;
@@ -530,7 +530,7 @@ static int cluster_group_width(const b200lu_handle* h, int m, int bw) {
     if (sizeof(T) == 8) {
         if (bw == 32) return m <= PCL_ROWS1 ? 128 : 64;
         if (bw == 16) return 64;
-        return 64;   // bw == 8
+        return 32;   // bw == 8
     }
     return m <= PCL_ROWS2 ? 128 : 64;
 }
@@ -568,14 +568,14 @@ static int launch_panel_any(b200lu_handle* h, cudaStream_t st, T* A, int64_t lda
     p.epoch = 0;
     p.mail = nullptr;
     p.deverr = h->d_deverr;
-    p.dbg = h->d_pdbg ? h->d_pdbg + 16 * (h->pdbg_n++ % 4096) : nullptr;
+    p.dbg = h->d_pdbg ? h->d_pdbg + 24 * (h->pdbg_n++ % 4096) : nullptr;
     int rc;
     if constexpr (sizeof(T) == 8) {
         if (fused) {
             if (bw > 16) rc = (m <= PCL_ROWS1) ? launch_panel_cluster_cfg<T, 32, 1, 4>(h, st, p)
                                                : launch_panel_cluster_cfg<T, 32, 2, 2>(h, st, p);
             else if (bw > 8) rc = launch_panel_cluster_cfg<T, 16, 4, 4>(h, st, p);
-            else rc = launch_panel_cluster_cfg<T, 8, 8, 8>(h, st, p);
+            else rc = launch_panel_cluster_cfg<T, 8, 8, 4>(h, st, p);
         } else {
             // one row per thread while 16 CTAs x 256 threads cover the panel (measured: n = 4096 10.3 -> 9.6 ms)
             if (bw > 16) rc = (m <= PCL_ROWS1) ? launch_panel_cluster_cfg<T, 32, 1>(h, st, p)
@@ -1469,8 +1469,8 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     ok = ok && cudaMallocHost((void**)&h->h_small, 64) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&h->h_scal, 64) == cudaSuccess;
     if (ok && getenv("B200LU_PANEL_DBG")) {
-        ok = cudaMalloc((void**)&h->d_pdbg, 4096 * 16 * sizeof(long long)) == cudaSuccess;
-        ok = ok && cudaMemset(h->d_pdbg, 0, 4096 * 16 * sizeof(long long)) == cudaSuccess;
+        ok = cudaMalloc((void**)&h->d_pdbg, 4096 * 24 * sizeof(long long)) == cudaSuccess;
+        ok = ok && cudaMemset(h->d_pdbg, 0, 4096 * 24 * sizeof(long long)) == cudaSuccess;
     }
     if (!ok) {
         b200lu_destroy(h);
@@ -1494,13 +1494,14 @@ void b200lu_destroy(b200lu_handle* h) {
     if (h->s_copy) cudaStreamSynchronize(h->s_copy);
     if (h->d_pdbg) {
         const int cnt = std::min(h->pdbg_n, 4096);
-        std::vector<long long> t((size_t)cnt * 16);
+        std::vector<long long> t((size_t)cnt * 24);
         cudaMemcpy(t.data(), h->d_pdbg, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         const int step = std::max(1, cnt / 96);   // ~96 lines over the whole run (B200LU_PANEL_DBG=1)
         for (int i = 0; i < cnt; i += step) {
-            const long long* s = &t[(size_t)i * 16];
+            const long long* s = &t[(size_t)i * 24];
             fprintf(stderr, "[pdbg] launch %d m=%lld G=%lld: load %lld loop %lld store %lld swaps %lld exit %lld cycles\n", i, s[6], s[7],
                     s[1] - s[0], s[2] - s[1], s[3] - s[2], s[4] - s[3], s[5] - s[4]);
+            if (s[16] | s[17]) fprintf(stderr, "[pdbg]    last sub-block prologue: load rows %lld | L11 + TRSM (phase A) %lld | rank-k update (phase B) %lld cycles; whole launch %lld\n", s[16], s[17], s[18], s[19]);
             if (s[8] | s[9]) fprintf(stderr, "[pdbg]    last sub-block, sums over its columns: publish-prep %lld | barrier+cta-reduce+send %lld | wait %lld | cluster-reduce %lld | freeze+positions+scale %lld | rank-1 update %lld | argmax-finish+stage %lld | loop-overhead %lld\n", s[8], s[9], s[10], s[11], s[14], s[15], s[12], s[13]);
         }
         cudaFree(h->d_pdbg);

@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
     }
     const bool dbg = p.dbg != nullptr && me == 0 && tid == 0;
     if (dbg) p.dbg[0] = clock64();
+    const long long t_launch = dbg ? clock64() : 0;
 
     // sender role / inbox addresses do not depend on the sub-block
     const int s_dst = tid & (G - 1), s_k = tid >> lgG;
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
 #pragma unroll 1
     for (int sub = 0; sub < nsub; ++sub) {
     const int wc = p.wc;
+    long long t_pro = dbg ? clock64() : 0;
     T a[RPT][W];   // a[q][c]: column (j + c) of row q while column j is being eliminated
     int ri[RPT];   // panel-local ORIGINAL row of each owned row (where it is loaded from)
     int pos[RPT];  // its current position in the LAPACK row order
@@ -241,6 +243,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
             a[q][c] = (ri[q] < p.m && c < wc) ? (NSUB > 1 ? __ldcg(src + (long long)c * p.lda) : src[(long long)c * p.lda]) : T(0);
         }
     }
+    if (dbg) { const long long t_ = clock64(); p.dbg[16] = t_ - t_pro; t_pro = t_; p.dbg[17] = 0; p.dbg[18] = 0; }
     if constexpr (NSUB > 1) {
         if (sub > 0) {
             const int sW = p.j0 - J0;   // rows / columns already factored in this launch
@@ -288,6 +291,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
                     if (row < sW && col < W) Us[row * W + col] = bt[rr][c];
                 }
             __syncthreads();
+            if (dbg) { const long long t_ = clock64(); p.dbg[17] = t_ - t_pro; t_pro = t_; }
             // ---- B: the thread's own rows: a[c] -= sum_k L[row, k] U[k, c], k ascending.  The multipliers L[row, k]
             // (written to global memory by this launch's earlier sub-blocks) are staged W columns at a time into the
             // tile, which is idle until the column loop, with asynchronous 8-byte copies (cp.async: every copy of
@@ -311,21 +315,43 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
                     cp_async_wait<0>();
                 }
                 __syncthreads();
+                if constexpr (W <= 16 && RPT > 1) {
+                    // narrow blocks, several rows per thread: one row of U in registers serves all the thread's rows
+                    // (measured with the loops the other way round: 9.5 k cycles per round of 8 multiplier columns
+                    // at 8 rows per thread, five shared-memory loads per eight FMAs)
+#pragma unroll 2
+                    for (int c = 0; c < W; ++c) {
+                        const T* urow = Us + (k0 + c) * W;
+                        T u[W];
 #pragma unroll
-                for (int q = 0; q < RPT; ++q) {
-                    if (ri[q] < p.m) {
-                        const T* lq = tile + q * NT + tid;
+                        for (int cc = 0; cc < W; ++cc) u[cc] = urow[cc];
+#pragma unroll
+                        for (int q = 0; q < RPT; ++q) {
+                            if (ri[q] < p.m) {
+                                const T nl = -tile[c * ROWS + q * NT + tid];
+#pragma unroll
+                                for (int cc = 0; cc < W; ++cc) a[q][cc] = tfma(nl, u[cc], a[q][cc]);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < RPT; ++q) {
+                        if (ri[q] < p.m) {
+                            const T* lq = tile + q * NT + tid;
 #pragma unroll 4
-                        for (int c = 0; c < W; ++c) {
-                            const T nl = -lq[c * ROWS];
-                            const T* urow = Us + (k0 + c) * W;
+                            for (int c = 0; c < W; ++c) {
+                                const T nl = -lq[c * ROWS];
+                                const T* urow = Us + (k0 + c) * W;
 #pragma unroll
-                            for (int cc = 0; cc < W; ++cc) a[q][cc] = tfma(nl, urow[cc], a[q][cc]);
+                                for (int cc = 0; cc < W; ++cc) a[q][cc] = tfma(nl, urow[cc], a[q][cc]);
+                            }
                         }
                     }
                 }
                 __syncthreads();   // the tile is overwritten by the next round / the column loop
             }
+            if (dbg) { const long long t_ = clock64(); p.dbg[18] = t_ - t_pro; t_pro = t_; }
         }
     }
     // sender role (set up before the sub-block loop): thread (dst, k) pushes row vector k of this CTA's
@@ -609,7 +635,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
     if (dbg) p.dbg[4] = clock64();
     if (NSUB > 1) __threadfence();   // this sub-block's global writes before the barrier's release
     pcl_cluster_sync();  // no CTA leaves (or starts the next sub-block) while a peer could still address its shared memory
-    if (dbg) { p.dbg[5] = clock64(); p.dbg[6] = p.m; p.dbg[7] = G; }
+    if (dbg) { p.dbg[5] = clock64(); p.dbg[6] = p.m; p.dbg[7] = G; p.dbg[19] = clock64() - t_launch; }
     p.j0 += W;
     p.m -= W;
     p.wc = min(W, wtot - (sub + 1) * W);
