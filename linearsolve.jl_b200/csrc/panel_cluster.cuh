@@ -143,6 +143,7 @@ struct PclShared {
     T s_val[NW];
     int s_pos[NW];
     unsigned long long mbar[2];
+    unsigned long long mbar_bulk;          // TMA bulk copies of the multipliers (fused kernel)
     int s_mv_dst[2 * W], s_mv_src[2 * W];
     int s_nmv;
     int s_has_top;
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
     if (tid == 0) {
         pcl_mbar_init(pcl_smem_u32(&sh.mbar[0]), 1);
         pcl_mbar_init(pcl_smem_u32(&sh.mbar[1]), 1);
+        pcl_mbar_init(pcl_smem_u32(&sh.mbar_bulk), 1);
         sh.s_has_top = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -225,6 +227,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
     const unsigned rbar0 = pcl_mapa(pcl_smem_u32(&sh.mbar[0]), (unsigned)s_dst);
     constexpr unsigned BOXB = (unsigned)sizeof(sh.box[0]);   // parity stride of the inbox
 
+    unsigned bulk_parity = 0;   // phase of sh.mbar_bulk
 #pragma unroll 1
     for (int sub = 0; sub < nsub; ++sub) {
     const int wc = p.wc;
@@ -299,20 +302,35 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
             // warps per scheduler: measured 30 k cycles per 8-column sub-block at 8 rows per thread)
             for (int k0 = 0; k0 < sW; k0 += W) {
                 {
+                    // one TMA bulk copy per multiplier column: this CTA's rows are contiguous in global memory and in
+                    // the tile (8-byte cp.async copies took ~8 k cycles per round: 16 B per clock and SM)
                     const long long rbase = (long long)p.j0 + (long long)me * ROWS;
-                    const int nrow = min(ROWS, p.m - me * ROWS);        // rows of this CTA inside the panel
-                    for (int c = 0; c < W; ++c) {
-                        const T* gcol = p.A + (long long)(J0 + k0 + c) * p.lda + rbase;
-                        for (int r = tid; r < nrow; r += NT) {
-                            const unsigned sa = pcl_smem_u32(tile + c * ROWS + r);
-                            if constexpr (sizeof(T) == 8)
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gcol + r) : "memory");
-                            else
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gcol + r) : "memory");
+                    const int nrow = max(0, min(ROWS, p.m - me * ROWS));   // rows of this CTA inside the panel
+                    constexpr int EPB = 16 / (int)sizeof(T);
+                    const int nbulk = nrow & ~(EPB - 1);                    // 16-byte multiple
+                    const unsigned mb = pcl_smem_u32(&sh.mbar_bulk);
+                    if (tid == 0 && nbulk > 0) {
+                        // the tile was last touched through the generic proxy (all of it behind a CTA barrier)
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        pcl_mbar_expect_tx(mb, (unsigned)(W * nbulk * (int)sizeof(T)));
+                        for (int c = 0; c < W; ++c) {
+                            const T* gcol = p.A + (long long)(J0 + k0 + c) * p.lda + rbase;
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         ::"r"(pcl_smem_u32(tile + c * ROWS)), "l"(gcol), "r"((unsigned)(nbulk * (int)sizeof(T))), "r"(mb)
+                                         : "memory");
                         }
                     }
-                    cp_async_commit();
-                    cp_async_wait<0>();
+                    for (int i = tid; i < (nrow - nbulk) * W; i += NT) {   // the odd tail rows
+                        const int c = i / (nrow - nbulk), r = nbulk + (i - c * (nrow - nbulk));
+                        tile[c * ROWS + r] = __ldcg(p.A + (long long)(J0 + k0 + c) * p.lda + rbase + r);
+                    }
+                    if (nbulk > 0) {
+                        if (!pcl_mbar_wait(mb, bulk_parity)) {
+                            atomicExch(p.deverr, DEV_ERR_PANEL_TIMEOUT);
+                            return;
+                        }
+                        bulk_parity ^= 1u;
+                    }
                 }
                 __syncthreads();
                 if constexpr (W <= 16 && RPT > 1) {
