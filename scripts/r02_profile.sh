@@ -9,7 +9,7 @@ N="ncu --set full --clock-control none --import-source on -f"
 timeout 400 $N -k regex:dgemm_sub_kernel --launch-skip 1 --launch-count 1 -o gpurun_out/r02_ncu_dgemm_n32768 python scripts/prof_driver.py 32768 lu > gpurun_out/r02_ncu_dgemm.log 2>&1
 timeout 300 $N -k regex:dgemm_sub_kernel --launch-skip 1 --launch-count 1 -o gpurun_out/r02_ncu_dgemm_n8192 python scripts/prof_driver.py 8192 lu > gpurun_out/r02_ncu_dgemm2.log 2>&1
 timeout 300 $N -k regex:panel_cluster_kernel --launch-skip 1 --launch-count 1 -o gpurun_out/r02_ncu_panel_fused_8x8 python scripts/dist_one.py 32768 > gpurun_out/r02_ncu_panel1.log 2>&1
-timeout 300 $N -k regex:panel_cluster_kernel --launch-skip 40 --launch-count 1 -o gpurun_out/r02_ncu_panel_fused_32x1 python scripts/dist_one.py 4096 > gpurun_out/r02_ncu_panel2.log 2>&1
+timeout 300 $N -k regex:panel_cluster_kernel --launch-skip 4 --launch-count 1 -o gpurun_out/r02_ncu_panel_fused_32x1 python scripts/dist_one.py 4096 > gpurun_out/r02_ncu_panel2.log 2>&1
 timeout 300 $N -k regex:getrf_batched_warp_kernel --launch-skip 1 --launch-count 1 -o gpurun_out/r02_ncu_batched_warp python scripts/prof_driver.py 0 batched > gpurun_out/r02_ncu_batched.log 2>&1
 timeout 300 $N -k regex:dist_step_kernel --launch-skip 300 --launch-count 1 -o gpurun_out/r02_ncu_dist_step python scripts/dist_one.py 32768 256 solve > gpurun_out/r02_ncu_step.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 14000 --csv --log-file gpurun_out/r02_launches_default_bench.csv \
