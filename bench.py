@@ -299,7 +299,10 @@ def newest_profile_traffic(pattern, key_read="dram__bytes_read.sum", key_write="
                     tot += float(m.group(2).replace(",", "")) * scale
                     found += 1
         if found == 2:
-            best = {"bytes": tot, "file": os.path.relpath(f, ROOT)}
+            m = re.search(r"algorithmic_bytes\s+-\s+([0-9]+)", txt)
+            s = re.search(r"shape\s+-\s+(\S+)", txt)
+            best = {"bytes": tot, "file": os.path.relpath(f, ROOT), "algorithmic": float(m.group(1)) if m else None,
+                    "shape": s.group(1) if s else None}
     return best
 
 
@@ -390,14 +393,16 @@ def bench_single(args, ls, torch, dev, local, n, nrhs, workload, steps, warmup, 
                 "launches_profiled": int(g_n), "gemm_share_of_getrf": (g_ms / nprof) / t_fact_prof if t_fact_prof else None,
             }
         else:
-            tr = newest_profile_traffic("*ncu_dgemm*details*.txt")
+            tr = newest_profile_traffic("*ncu_dgemm*metrics*.txt")
             roofline = {
                 "bound": "tensor", "kernel": "dgemm_sub_kernel (FP64 DMMA trailing update)",
                 "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma if peak_dmma else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (the first trailing update at n = 8192),
-                # parsed from the newest committed ncu capture of this kernel under profiles/
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (the first full trailing update of this
+                # size as a stand-alone launch, scripts/prof_gemm.py), parsed from the newest committed ncu capture
+                # of this kernel under profiles/ together with that launch's shape and algorithmic bytes
                 "traffic": tr["bytes"] if tr else None, "traffic_source": tr["file"] if tr else None,
-                "traffic_algorithmic_of_that_launch": 2 * 7936 * 7680 * 8 + (7936 + 7680) * 256 * 8,
+                "traffic_algorithmic_of_that_launch": tr["algorithmic"] if tr else None,
+                "traffic_launch_shape": tr["shape"] if tr else None,
                 "peak_source": "library DMMA.8x8x4 register-resident probe on this GPU (no FP64 entry in MEASURED_PEAKS.json)",
                 "launches_profiled": int(g_n), "gemm_share_of_getrf": (g_ms / nprof) / t_fact_prof if t_fact_prof else None,
                 "dfma_probe_tflops": h.probe_peak(C.PEAK_FP64_DFMA), "hbm_copy_probe_gbs": h.probe_peak(C.PEAK_HBM_COPY),
@@ -798,6 +803,7 @@ def bench_dist(args, ls, torch, dist, dev, rank, world, local, barrier, max_over
     ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     gemm_share = max_over_ranks(g_ms / t_prof if t_prof else 0.0)
     value = lu_flops(n) / (ms * 1e-3) / 1e9
+    trd = newest_profile_traffic("*ncu_dgemm*metrics*.txt")
     line = {"metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
@@ -816,7 +822,11 @@ def bench_dist(args, ls, torch, dist, dev, rank, world, local, barrier, max_over
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "dgemm_sub_kernel (FP64 DMMA trailing update, this rank's column blocks)",
                          "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                         "traffic": None, "gemm_share_of_getrf_max_over_ranks": gemm_share,
+                         # ncu runs one GPU at a time: the same kernel's stand-alone capture on one GPU
+                         "traffic": trd["bytes"] if trd else None, "traffic_source": trd["file"] if trd else None,
+                         "traffic_algorithmic_of_that_launch": trd["algorithmic"] if trd else None,
+                         "traffic_launch_shape": trd["shape"] if trd else None,
+                         "gemm_share_of_getrf_max_over_ranks": gemm_share,
                          "getrf_frac_of_aggregate_fp64_peak": (lu_flops(n) / (tf_ms * 1e-3) / 1e12) / (peak * world) if peak else None,
                          "chain_ms": {"panel_factorizations": chain[0], "lookahead_block_updates": chain[1], "panel_hand_off": chain[2],
                                       "sum": sum(chain), "profiled_getrf_ms": max_over_ranks(t_prof),

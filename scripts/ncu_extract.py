@@ -1,6 +1,6 @@
 """pull the handful of metrics the roofline entries quote out of an .ncu-rep (ncu -i rep --page raw --csv) and write
 them as `name unit value` lines — small enough to commit under profiles/; bench.py reads dram__bytes_* from there.
-usage: ncu_extract.py in.ncu-rep out.txt"""
+usage: ncu_extract.py in.ncu-rep out.txt [note-key note-value ...]   (notes are appended as `key - value` lines)"""
 import csv
 import io
 import subprocess
@@ -23,3 +23,5 @@ with open(sys.argv[2], "w") as f:
         for i, h in enumerate(hdr):
             if h in WANT or h.startswith("dram__bytes"):
                 f.write(f"{h} {units[i] or '-'} {r[i]}\n")
+    for k, v in zip(sys.argv[3::2], sys.argv[4::2]):
+        f.write(f"{k} - {v}\n")
