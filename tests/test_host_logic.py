@@ -398,3 +398,19 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_roofline_traffic_comes_from_a_committed_capture():
+    """`roofline.traffic` is parsed from the newest ncu capture of the DGEMM under profiles/ (dram bytes read +
+    written of ONE launch), with that launch's shape and algorithmic bytes beside it — not typed into bench.py."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    tr = bench.newest_profile_traffic("*ncu_dgemm*metrics*.txt")
+    assert tr is not None and os.path.exists(os.path.join(ROOT, tr["file"]))
+    M, N, K = (int(v) for v in tr["shape"].split("x"))
+    assert tr["algorithmic"] == 2 * M * N * 8 + (M + N) * K * 8
+    # C is read and written once, the panels come from L2: within 1.25x of the algorithmic bytes
+    assert tr["algorithmic"] <= tr["bytes"] <= 1.25 * tr["algorithmic"]
+    assert bench.newest_profile_traffic("*no_such_capture*.txt") is None
