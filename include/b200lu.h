@@ -133,7 +133,15 @@ enum {
     B200LU_OPT_BATCHED_MODE = 14, /* batched getrf of systems of <= 64 rows: 0 (default) = one WARP per system, the
                                    system in shared memory, 8-column register panels (and b200lu_factor_solve_batched
                                    fuses the first getrs into it); 1 = the round-1 kernel, one row per thread    */
-    B200LU_OPT_COUNT = 15
+    B200LU_OPT_HOST_REGISTER = 15, /* b200lu_factor from a HOST matrix in pageable memory: 1 = page-lock the caller's
+                                   buffer once (cudaHostRegister, portable across the handle's GPUs) and keep it
+                                   registered until another buffer is factored or the handle is destroyed, so that
+                                   every factorization from that buffer gets the streamed, DMA-direct upload a pinned
+                                   buffer gets.  For callers that own the buffer for the lifetime of the cache
+                                   (reference: a LinearCache with alias_A = false, src/common.jl:818-842) and cannot
+                                   allocate pinned memory themselves.  Default 0: pageable buffers are staged by the
+                                   driver.  The registration costs about as much as one pageable upload.          */
+    B200LU_OPT_COUNT = 16
 };
 
 /* library/ABI version: major*10000 + minor*100 + patch */

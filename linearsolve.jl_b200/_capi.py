@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("B200LU_LIB") or os.path.join(_HERE, "csrc", "libb200l
 
 F64, F32, MIXED = 0, 1, 2
 T_H2D, T_FACTOR, T_SOLVE, T_D2H, T_GEMM, T_PANEL, T_LOOKAHEAD, T_PUSH = range(8)
-OPT_NB, OPT_LOOKAHEAD, OPT_REFINE_MAXIT, OPT_PANEL_CTAS, OPT_SOLVE_NRHS_TILE, OPT_PROFILE, OPT_PANEL_RPT, OPT_GEMM_CFG, OPT_PANEL_MODE, OPT_SGEMM_MODE, OPT_TRSV_MODE, OPT_STREAM_H2D, OPT_MAPPED_RHS, OPT_KEEP_A, OPT_BATCHED_MODE = range(15)
+OPT_NB, OPT_LOOKAHEAD, OPT_REFINE_MAXIT, OPT_PANEL_CTAS, OPT_SOLVE_NRHS_TILE, OPT_PROFILE, OPT_PANEL_RPT, OPT_GEMM_CFG, OPT_PANEL_MODE, OPT_SGEMM_MODE, OPT_TRSV_MODE, OPT_STREAM_H2D, OPT_MAPPED_RHS, OPT_KEEP_A, OPT_BATCHED_MODE, OPT_HOST_REGISTER = range(16)
 C_GEMM_FLOPS, C_GEMM_LAUNCHES, C_REFINE_ITERS = range(3)
 PEAK_FP64_DMMA, PEAK_FP64_DFMA, PEAK_HBM_COPY = range(3)
 

@@ -34,7 +34,7 @@ std::atomic<unsigned long long> g_launch_count{0};
 }
 using namespace b200lu;
 
-#define B200LU_VERSION 200   // 0.2.0: transposed batched solves, residual norms, KEEP_A, batched n <= 160
+#define B200LU_VERSION 300   // 0.3.0: ngpus > 1 in b200lu_create, fused batched factor+solve, dist transport query, HOST_REGISTER
 
 // ------------------------------------------------------------------ handle --
 struct b200lu_handle {
@@ -48,6 +48,8 @@ struct b200lu_handle {
     // streamed upload of A (B200LU_OPT_STREAM_H2D): column chunks in flight on s_copy
     std::vector<cudaEvent_t> ev_chunk;   // chunk c has landed
     std::vector<int> chunk_end;          // one past its last column (multiples of nb; last = n)
+    void* reg_ptr = nullptr;             // B200LU_OPT_HOST_REGISTER: the caller's matrix this handle page-locked
+    size_t reg_bytes = 0;
     char err[512] = {0};
     double timing[B200LU_T_COUNT] = {0};
     int64_t opt[B200LU_OPT_COUNT];
@@ -1450,6 +1452,7 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     h->opt[B200LU_OPT_MAPPED_RHS] = 1;
     h->opt[B200LU_OPT_KEEP_A] = 0;
     h->opt[B200LU_OPT_BATCHED_MODE] = 0;
+    h->opt[B200LU_OPT_HOST_REGISTER] = 0;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     bool ok = cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) == cudaSuccess;
@@ -1480,10 +1483,12 @@ int b200lu_create(b200lu_handle** out, int dtype, int ngpus, const int* devices)
     return 0;
 }
 
+static void host_unregister(b200lu_handle* h);
 void b200lu_destroy(b200lu_handle* h) {
     if (!h) return;
     if (h->team) {   // the sub-handles own every device resource
         team_destroy(h);
+        host_unregister(h);
         delete h;
         return;
     }
@@ -1492,6 +1497,7 @@ void b200lu_destroy(b200lu_handle* h) {
     if (h->s_main) cudaStreamSynchronize(h->s_main);
     if (h->s_panel) cudaStreamSynchronize(h->s_panel);
     if (h->s_copy) cudaStreamSynchronize(h->s_copy);
+    host_unregister(h);
     if (h->d_pdbg) {
         const int cnt = std::min(h->pdbg_n, 4096);
         std::vector<long long> t((size_t)cnt * 24);
@@ -1640,6 +1646,7 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_SGEMM_MODE && (value < 0 || value > 2)) return -3;
     if (option == B200LU_OPT_TRSV_MODE && (value < 0 || value > 3)) return -3;
     if (option == B200LU_OPT_STREAM_H2D && (value < 0 || value > 1)) return -3;
+    if (option == B200LU_OPT_HOST_REGISTER && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_MAPPED_RHS && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_KEEP_A && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_BATCHED_MODE && (value < 0 || value > 1)) return -3;
@@ -1727,9 +1734,41 @@ static int factor_resident(b200lu_handle* h, int64_t n, int64_t* info, int nchun
     return 0;
 }
 
+// B200LU_OPT_HOST_REGISTER: page-lock the caller's matrix once; a buffer that is already pinned (cudaMallocHost,
+// cudaHostRegister by the caller, or by an earlier call) is left alone.  A failed registration is not an error:
+// the upload then goes through the driver's staging like any pageable copy.
+static void host_unregister(b200lu_handle* h) {
+    if (h->reg_ptr) {
+        cudaHostUnregister(h->reg_ptr);
+        (void)cudaGetLastError();
+        h->reg_ptr = nullptr;
+        h->reg_bytes = 0;
+    }
+}
+static void host_register(b200lu_handle* h, const void* A_host, size_t bytes) {
+    if (!h->opt[B200LU_OPT_HOST_REGISTER] || !A_host || bytes == 0) return;
+    if (h->reg_ptr == A_host && h->reg_bytes >= bytes) return;
+    cudaSetDevice(h->dev);
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, A_host) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return;
+    }
+    if (at.type != cudaMemoryTypeUnregistered && h->reg_ptr != A_host) return;   // pinned by somebody else
+    host_unregister(h);
+    if (cudaHostRegister(const_cast<void*>(A_host), bytes, cudaHostRegisterPortable) == cudaSuccess) {
+        h->reg_ptr = const_cast<void*>(A_host);
+        h->reg_bytes = bytes;
+    } else {
+        (void)cudaGetLastError();
+    }
+}
+
 int b200lu_factor(b200lu_handle* h, int64_t n, const void* A_host, int64_t lda, int64_t* ipiv_out,
                   int64_t* info) {
     if (!h) return -1;
+    if (n > 0 && A_host && lda >= n && n <= 131072)
+        host_register(h, A_host, ((size_t)lda * (size_t)(n - 1) + (size_t)n) * iface_size(h));
     if (h->team) return team_factor(h, n, A_host, lda, ipiv_out, info);
     if (n < 0 || n > 131072) return set_err(h, -2, "n out of range");
     if (!A_host && n > 0) return set_err(h, -3, "A is NULL");

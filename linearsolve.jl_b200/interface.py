@@ -85,11 +85,14 @@ class B200LUFactorization(AbstractFactorization):
     _dtype_code = {np.dtype(np.float64): _capi.F64, np.dtype(np.float32): _capi.F32}
 
     def __init__(self, throwerror: bool = True, residualsafety: bool = False, device: int = 0,
-                 nb: int | None = None, lookahead: bool | None = None, devices=None):
+                 nb: int | None = None, lookahead: bool | None = None, devices=None, host_register: bool = False):
         """`devices = (0, 1, ..., 7)`: ONE cache drives all these GPUs from this process (Julia:
         `B200LUFactorization(; devices = 0:7)`): a dense A is factored 1-D block-cyclic over them, the
         blocks of a BlockDiagonal are sharded over them.  Float32/Float64; `solve!(cache; adjoint = true)`
-        and `residualsafety` need the single-GPU handle."""
+        and `residualsafety` need the single-GPU handle.
+        `host_register = True`: the library page-locks the matrix it is handed (B200LU_OPT_HOST_REGISTER) — the
+        cache's private copy of A with `alias_A = false`, src/common.jl:818-842 — once, so that every
+        refactorization from that buffer gets the streamed upload a pinned buffer gets."""
         if throwerror and not useb200():
             raise RuntimeError("B200LUFactorization requires libb200lu.so and a B200 (sm_100) GPU; "
                                "there is no CPU fallback")
@@ -100,6 +103,7 @@ class B200LUFactorization(AbstractFactorization):
             raise ValueError("residualsafety needs the single-GPU handle (the multi-GPU handle keeps no copy of A)")
         self.nb = nb
         self.lookahead = lookahead
+        self.host_register = bool(host_register)
 
     def handle_dtype(self, eltype):
         try:
@@ -264,6 +268,8 @@ def _configure(handle, alg):
         handle.set_option(_capi.OPT_NB, alg.nb)
     if alg.lookahead is not None:
         handle.set_option(_capi.OPT_LOOKAHEAD, int(alg.lookahead))
+    if getattr(alg, "host_register", False):
+        handle.set_option(_capi.OPT_HOST_REGISTER, 1)
     if isinstance(alg, B200LU32MixedLUFactorization):
         handle.set_option(_capi.OPT_REFINE_MAXIT, alg.maxiters if alg.refine else 0)
     elif alg.residualsafety:

@@ -58,15 +58,16 @@ struct B200LUFactorization <: AbstractFactorization
     residualsafety::Bool
     device::Int
     devices::Vector{Cint}      # more than one entry: ONE cache drives all these GPUs (b200lu_create with ngpus > 1)
+    host_register::Bool        # the library page-locks the cache's copy of A once (B200LU_OPT_HOST_REGISTER)
     function B200LUFactorization(; throwerror = true, residualsafety::Bool = false, device::Int = 0,
-            devices = nothing)
+            devices = nothing, host_register::Bool = false)
         if throwerror && !useb200()
             error("B200LUFactorization requires libb200lu.so and an NVIDIA B200 (sm_100) GPU")
         end
         devs = devices === nothing ? Cint[device] : collect(Cint, devices)    # e.g. devices = 0:7
         length(devs) > 1 && residualsafety &&
             error("residualsafety needs the single-GPU handle (the multi-GPU handle keeps no copy of A)")
-        return new(residualsafety, Int(first(devs)), devs)
+        return new(residualsafety, Int(first(devs)), devs, host_register)
     end
 end
 
@@ -168,6 +169,12 @@ function _b200lu_ensure_handle!(c::B200LUCache, alg)
     elseif alg.residualsafety
         ccall((:b200lu_set_option, libb200lu[]), Cint, (Ptr{Cvoid}, Cint, Int64),
             c.handle, 13, 1)                                     # B200LU_OPT_KEEP_A
+    end
+    if alg isa B200LUFactorization && alg.host_register
+        # cache.A is the cache's own copy (alias_A = false, src/common.jl:818-842) and lives as long as the cache:
+        # pinned once, every refactorization streams its upload under the factorization
+        ccall((:b200lu_set_option, libb200lu[]), Cint, (Ptr{Cvoid}, Cint, Int64),
+            c.handle, 15, 1)                                     # B200LU_OPT_HOST_REGISTER
     end
     return c
 end

@@ -226,3 +226,42 @@ def test_residualsafety_on_device(gpu_required, ls):
     sol = ls.solve(ls.LinearProblem(bd, rng.random(93)), ls.B200LUFactorization(residualsafety=True))
     assert sol.retcode == ls.ReturnCode.Success
 
+
+
+def _is_pinned(arr):
+    """cudaPointerGetAttributes through cuda-python: is this host buffer page-locked / registered?"""
+    from cuda.bindings import runtime as cudart
+    err, at = cudart.cudaPointerGetAttributes(arr.ctypes.data)
+    assert int(err) == 0
+    return int(at.type) == int(cudart.cudaMemoryType.cudaMemoryTypeHost)
+
+
+def test_host_register_option(gpu_required, ls):
+    """B200LU_OPT_HOST_REGISTER: the library page-locks the caller's pageable matrix once (the cache's own copy of
+    A with alias_A = false, reference src/common.jl:818-842), keeps it registered across refactorizations, moves
+    the registration when another buffer arrives, releases it with the handle; factors are the same either way."""
+    C = ls._capi
+    n = 3000
+    rng = np.random.default_rng(31)
+    A = np.asfortranarray(rng.random((n, n)))
+    A2 = np.asfortranarray(rng.random((n, n)))
+    h0 = C.Handle(C.F64)
+    ipiv0, info0 = h0.factor(A)
+    LU0 = h0.get_factors()
+    assert not _is_pinned(A)                       # default: the caller's buffer is left alone
+    h = C.Handle(C.F64)
+    h.set_option(C.OPT_HOST_REGISTER, 1)
+    assert h.get_option(C.OPT_HOST_REGISTER) == 1
+    for _ in range(2):                             # second call: same buffer, already registered
+        ipiv, info = h.factor(A)
+        assert info == info0 == 0 and np.array_equal(ipiv, ipiv0) and np.array_equal(h.get_factors(), LU0)
+        assert _is_pinned(A)
+    h.factor(A2)                                   # another buffer: the registration moves
+    assert _is_pinned(A2) and not _is_pinned(A)
+    h.close()
+    assert not _is_pinned(A2)
+    # through the public interface
+    b = rng.random(n)
+    cache = ls.init(ls.LinearProblem(A, b), ls.B200LUFactorization(host_register=True))
+    sol = ls.solve_(cache)
+    assert sol.retcode == ls.ReturnCode.Success and _berr(A, sol.u, b) <= 10 * n * EPS
