@@ -112,6 +112,8 @@ struct b200lu_handle {
     double* d_r = nullptr;     // residual (n)
     float* d_r32 = nullptr;    // residual cast / correction (n)
     double* d_scal = nullptr;  // [4] norms
+    double* d_rpart = nullptr; // partial sums of the deterministic residual / norm reductions (ensure_rpart)
+    int64_t cap_rpart = 0;
     double* d_cscal = nullptr; // [2 * cap_cscal] per-column norms of the matrix-RHS refinement
     double* h_cscal = nullptr;
     int cap_cscal = 0;
@@ -211,10 +213,26 @@ static int set_err(b200lu_handle* h, int status, const char* fmt, ...) {
 static size_t elem_size(const b200lu_handle* h) { return h->dtype == B200LU_F64 ? 8 : 4; }
 static size_t iface_size(const b200lu_handle* h) { return h->dtype == B200LU_F32 ? 4 : 8; }
 
+
+
 template <typename P>
 static void free_dev(P*& p) {
     if (p) cudaFree(p);
     p = nullptr;
+}
+
+// columns per CTA of residual_gemv_kernel: at most 32 chunks of partial sums per row
+static int residual_chunk(int64_t n) { return (int)std::max<int64_t>(512, (cdiv(n, 32) + 3) / 4 * 4); }
+// scratch of the fixed-order reductions: 32 partial sums per row (residual), one per CTA (Frobenius norm)
+static int ensure_rpart(b200lu_handle* h, int64_t n) {
+    const int64_t need = std::max<int64_t>(32 * n, (int64_t)cdiv(n, 256) * 256);
+    if (need <= h->cap_rpart) return 0;
+    CU_TRY(h, cudaStreamSynchronize(h->s_main));
+    free_dev(h->d_rpart);
+    h->cap_rpart = 0;
+    CU_TRY(h, cudaMalloc((void**)&h->d_rpart, (size_t)need * sizeof(double)));
+    h->cap_rpart = need;
+    return 0;
 }
 
 // ------------------------------------------------------------ kernel launch --
@@ -1315,10 +1333,9 @@ static int refine_solve_block_device(b200lu_handle* h, const double* B, int64_t 
         CU_TRY(h, cudaMemcpy2DAsync(R, (size_t)ldr * 8, B, (size_t)ldb * 8, (size_t)n * 8, nrhs, cudaMemcpyDeviceToDevice, st));
         rc = launch_gemm(h, st, n, nrhs, n, h->dA64, h->ldd, X, ldx, R, ldr);
         if (rc) return rc;
-        CU_TRY(h, cudaMemsetAsync(h->d_cscal, 0, (size_t)2 * nrhs * sizeof(double), st));
-        colsumsq_kernel<<<dim3(std::min(cdiv(n, 256), 64), grid_y(nrhs)), 256, 0, st>>>(R, ldr, n, h->d_cscal, nrhs);
+        colsumsq_kernel<<<std::min(nrhs, 4096), 256, 0, st>>>(R, ldr, n, h->d_cscal, nrhs);
         LAUNCH_CHECK(h);
-        colsumsq_kernel<<<dim3(std::min(cdiv(n, 256), 64), grid_y(nrhs)), 256, 0, st>>>(X, ldx, n, h->d_cscal + nrhs, nrhs);
+        colsumsq_kernel<<<std::min(nrhs, 4096), 256, 0, st>>>(X, ldx, n, h->d_cscal + nrhs, nrhs);
         LAUNCH_CHECK(h);
         CU_TRY(h, cudaMemcpyAsync(h->h_cscal, h->d_cscal, (size_t)2 * nrhs * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU_TRY(h, cudaStreamSynchronize(st));
@@ -1357,6 +1374,7 @@ static int refine_solve_device(b200lu_handle* h, const double* B, int64_t ldb, d
     const double eps = 2.220446049250313e-16;
     int rc = ensure_rhs(h, trans ? 2 : 1);
     if (rc) return rc;
+    if ((rc = ensure_rpart(h, n))) return rc;
     float* w32 = (float*)h->d_X;  // n floats of scratch
     // the copy of b: column 0 of d_B, or column 1 when the transposed sweeps use column 0 for x = P^T z
     double* const bcopy = (double*)h->d_B + (trans ? h->cap_n : 0);
@@ -1377,17 +1395,18 @@ static int refine_solve_device(b200lu_handle* h, const double* B, int64_t ldb, d
         for (int it = 0; it < maxit; ++it) {
             // r = b - A x in FP64
             CU_TRY(h, cudaMemcpyAsync(h->d_r, bcopy, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
-            const int cchunk = 512;
-            if (trans)
+            if (trans) {
                 residual_gemvT_kernel<double><<<cdiv(n, 8), 256, 0, st>>>(h->dA64, h->ldd, n, x, h->d_r);
-            else
-                residual_gemv_kernel<double><<<dim3(cdiv(n, 256), cdiv(n, cchunk)), 256, 0, st>>>(
-                    h->dA64, h->ldd, n, x, h->d_r, cchunk);
+            } else {
+                const int cchunk = residual_chunk(n), nch = cdiv(n, cchunk);
+                residual_gemv_kernel<double><<<dim3(cdiv(n, 256), nch), 256, 0, st>>>(h->dA64, h->ldd, n, x, h->d_rpart, cchunk);
+                LAUNCH_CHECK(h);
+                residual_finish_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->d_rpart, n, nch, h->d_r);
+            }
             LAUNCH_CHECK(h);
-            CU_TRY(h, cudaMemsetAsync(h->d_scal, 0, 4 * sizeof(double), st));
-            sumsq_kernel<<<std::min(cdiv(n, 256), 1024), 256, 0, st>>>(h->d_r, n, h->d_scal + 0);
+            sumsq_kernel<<<1, 1024, 0, st>>>(h->d_r, n, h->d_scal + 0);
             LAUNCH_CHECK(h);
-            sumsq_kernel<<<std::min(cdiv(n, 256), 1024), 256, 0, st>>>(x, n, h->d_scal + 1);
+            sumsq_kernel<<<1, 1024, 0, st>>>(x, n, h->d_scal + 1);
             LAUNCH_CHECK(h);
             CU_TRY(h, cudaMemcpyAsync(h->h_scal, h->d_scal, 2 * sizeof(double),
                                       cudaMemcpyDeviceToHost, st));
@@ -1527,7 +1546,7 @@ void b200lu_destroy(b200lu_handle* h) {
     free_dev(h->d_dinvL); free_dev(h->d_dinvU); free_dev(h->d_wL); free_dev(h->d_wU); free_dev(h->d_wLt); free_dev(h->d_wUt); free_dev(h->d_tflags); free_dev(h->d_tticket); free_dev(h->d_t2items); free_dev(h->d_t2x); free_dev(h->d_t2p); free_dev(h->d_t2ticket);
     free_dev(h->d_t3items); free_dev(h->d_t3x); free_dev(h->d_t3p); free_dev(h->d_t3ticket);
     free_dev(h->dA_keep);
-    free_dev(h->d_B); free_dev(h->d_X); free_dev(h->d_r); free_dev(h->d_r32); free_dev(h->d_scal); free_dev(h->d_cscal);
+    free_dev(h->d_B); free_dev(h->d_X); free_dev(h->d_r); free_dev(h->d_r32); free_dev(h->d_scal); free_dev(h->d_cscal); free_dev(h->d_rpart);
     if (h->h_cscal) cudaFreeHost(h->h_cscal);
     free_dev(h->dB_LU); free_dev(h->dB_ipiv); free_dev(h->dB_info); free_dev(h->dB_perm); free_dev(h->dB_in);
     free_dev(h->dB_rhs); free_dev(h->dB_x);
@@ -1691,9 +1710,11 @@ static int factor_resident(b200lu_handle* h, int64_t n, int64_t* info, int nchun
         rc = getrf_device<double>(h, (double*)h->dA, h->ldd, (int)n, nchunks);
     } else {
         if (h->dtype == B200LU_MIXED) {
+            if ((rc = ensure_rpart(h, n))) return rc;
             CU_TRY(h, cudaMemsetAsync(h->d_scal, 0, 4 * sizeof(double), h->s_main));
-            sumsq2d_kernel<<<dim3(cdiv(n, 256), 256), 256, 0, h->s_main>>>(h->dA64, h->ldd, (int)n,
-                                                                             h->d_scal + 2);
+            sumsq2d_kernel<<<dim3(cdiv(n, 256), 256), 256, 0, h->s_main>>>(h->dA64, h->ldd, (int)n, h->d_rpart);
+            LAUNCH_CHECK(h);
+            sum_partials_kernel<<<1, 1024, 0, h->s_main>>>(h->d_rpart, (long long)cdiv(n, 256) * 256, h->d_scal + 2);
             LAUNCH_CHECK(h);
             cast2d_kernel<double, float><<<dim3(cdiv(n, 256), 512), 256, 0, h->s_main>>>(
                 h->dA64, h->ldd, (float*)h->dA, h->ldd, (int)n, (int)n);
@@ -2007,6 +2028,7 @@ int b200lu_residual_norms(b200lu_handle* h, int64_t nrhs, const void* B_host, in
     cudaStream_t st = h->s_main;
     int rc = ensure_rhs(h, 2 * nrhs + 2);
     if (rc) return rc;
+    if ((rc = ensure_rpart(h, n))) return rc;
     if (nrhs > h->cap_cscal) {
         CU_TRY(h, cudaStreamSynchronize(st));
         free_dev(h->d_cscal);
@@ -2038,19 +2060,20 @@ int b200lu_residual_norms(b200lu_handle* h, int64_t nrhs, const void* B_host, in
         CU_TRY(h, cudaMemcpyAsync(R, dBs, (size_t)n * nrhs * 8, cudaMemcpyDeviceToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(X64, dXs, (size_t)n * nrhs * 8, cudaMemcpyDeviceToDevice, st));
     }
-    CU_TRY(h, cudaMemsetAsync(h->d_cscal, 0, (size_t)2 * nrhs * sizeof(double), st));
-    const dim3 gn(std::min(cdiv(n, 256), 64), grid_y(nrhs));
+    const int gn = (int)std::min<int64_t>(nrhs, 4096);
     colsumsq_kernel<<<gn, 256, 0, st>>>(R, n, (int)n, h->d_cscal + nrhs, (int)nrhs);     // ||b||^2 before R becomes the residual
     LAUNCH_CHECK(h);
-    const int cchunk = 512;
+    const int cchunk = residual_chunk(n), nch = cdiv(n, cchunk);
     for (int64_t c = 0; c < nrhs; ++c) {
-        const dim3 gr(cdiv(n, 256), cdiv(n, cchunk));
+        const dim3 gr(cdiv(n, 256), nch);
         if (h->dtype == B200LU_F64)
-            residual_gemv_kernel<double><<<gr, 256, 0, st>>>((const double*)h->dA_keep, h->ldd, (int)n, X64 + c * n, R + c * n, cchunk);
+            residual_gemv_kernel<double><<<gr, 256, 0, st>>>((const double*)h->dA_keep, h->ldd, (int)n, X64 + c * n, h->d_rpart, cchunk);
         else if (h->dtype == B200LU_F32)
-            residual_gemv_kernel<float><<<gr, 256, 0, st>>>((const float*)h->dA_keep, h->ldd, (int)n, X64 + c * n, R + c * n, cchunk);
+            residual_gemv_kernel<float><<<gr, 256, 0, st>>>((const float*)h->dA_keep, h->ldd, (int)n, X64 + c * n, h->d_rpart, cchunk);
         else
-            residual_gemv_kernel<double><<<gr, 256, 0, st>>>(h->dA64, h->ldd, (int)n, X64 + c * n, R + c * n, cchunk);
+            residual_gemv_kernel<double><<<gr, 256, 0, st>>>(h->dA64, h->ldd, (int)n, X64 + c * n, h->d_rpart, cchunk);
+        LAUNCH_CHECK(h);
+        residual_finish_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->d_rpart, (int)n, nch, R + c * n);
         LAUNCH_CHECK(h);
     }
     colsumsq_kernel<<<gn, 256, 0, st>>>(R, n, (int)n, h->d_cscal, (int)nrhs);

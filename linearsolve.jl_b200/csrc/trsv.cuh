@@ -532,11 +532,13 @@ __global__ void __launch_bounds__(256, 1) trsv2_kernel(const T* __restrict__ A, 
 }
 
 // y = b - A x  (FP64 residual for the refinement loop; A n x n column-major).
-// CTA: 256 rows x `cchunk` columns; one atomicAdd per row per CTA.
+// CTA (bx, by): 256 rows x `cchunk` columns, partial sums to part[by * n + row]; residual_finish_kernel then
+// subtracts the chunks' partial sums from y in ascending chunk order — one writer per entry, no atomics: the
+// residual, and with it the refined solution, is the same bits on every run.
 template <typename TA>
 __global__ void __launch_bounds__(256) residual_gemv_kernel(const TA* __restrict__ A, long long lda,
                                                             int n, const double* __restrict__ x,
-                                                            double* __restrict__ y, int cchunk) {
+                                                            double* __restrict__ part, int cchunk) {
     const int row = blockIdx.x * 256 + threadIdx.x;
     const int c0 = blockIdx.y * cchunk;
     const int c1 = min(n, c0 + cchunk);
@@ -555,7 +557,15 @@ __global__ void __launch_bounds__(256) residual_gemv_kernel(const TA* __restrict
         s0 = fma((double)ap[0], x[c], s0);
         ap += lda;
     }
-    atomicAdd(y + row, -((s0 + s1) + (s2 + s3)));
+    part[(long long)blockIdx.y * n + row] = (s0 + s1) + (s2 + s3);
+}
+__global__ void __launch_bounds__(256) residual_finish_kernel(const double* __restrict__ part, int n, int nchunks,
+                                                              double* __restrict__ y) {
+    const int row = blockIdx.x * 256 + threadIdx.x;
+    if (row >= n) return;
+    double s = 0.0;
+    for (int k = 0; k < nchunks; ++k) s += part[(long long)k * n + row];
+    y[row] -= s;
 }
 
 // y -= A^T x (the residual of the transposed system, MIXED refinement with trans = 'T'): one warp per

@@ -26,52 +26,64 @@ __global__ void cast2d_kernel(const TS* __restrict__ S, long long lds, TD* __res
         D[(long long)c * ldd + r] = (TD)S[(long long)c * lds + r];
 }
 
-// out[0] += sum x^2
-__global__ void sumsq_kernel(const double* __restrict__ x, long long n, double* out) {
-    double s = 0.0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x)
-        s = fma(x[i], x[i], s);
+// Sums of squares for the refinement loop and the residual check.  Every reduction here has ONE fixed shape
+// (strided per-thread sums, shuffle tree, shared-memory tree, a single writer): the norms — and with them the
+// sweep count of the refinement — are the same bits on every run.
+__device__ __forceinline__ double block_sum_fixed(double s) {
+    __shared__ double sh[32];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    __shared__ double sh[32];
+    __syncthreads();   // sh may still be read by the previous call
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
     __syncthreads();
+    s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
     if (threadIdx.x < 32) {
-        s = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (threadIdx.x == 0) atomicAdd(out, s);
     }
+    return s;   // valid in thread 0
 }
 
-// Frobenius norm^2 of an n x n column-major matrix with leading dimension lda
-__global__ void sumsq2d_kernel(const double* __restrict__ A, long long lda, int n, double* out) {
+// out[0] = sum x^2 (one CTA)
+__global__ void sumsq_kernel(const double* __restrict__ x, long long n, double* out) {
     double s = 0.0;
-    for (int c = blockIdx.y; c < n; c += gridDim.y) {
-        const int r = blockIdx.x * blockDim.x + threadIdx.x;
-        if (r < n) {
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s = fma(x[i], x[i], s);
+    s = block_sum_fixed(s);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// Frobenius norm^2 of an n x n column-major matrix with leading dimension lda, stage 1: CTA (bx, by) sums its
+// 256-row strip over the columns by, by + gridDim.y, ... into part[by * gridDim.x + bx]
+__global__ void sumsq2d_kernel(const double* __restrict__ A, long long lda, int n, double* __restrict__ part) {
+    double s = 0.0;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) {
+        for (int c = blockIdx.y; c < n; c += gridDim.y) {
             const double v = A[(long long)c * lda + r];
             s = fma(v, v, s);
         }
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+    s = block_sum_fixed(s);
+    if (threadIdx.x == 0) part[(long long)blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+// stage 2 (one CTA): out[0] = sum of the np partial sums, fixed order
+__global__ void sum_partials_kernel(const double* __restrict__ part, long long np, double* out) {
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < np; i += blockDim.x) s += part[i];
+    s = block_sum_fixed(s);
+    if (threadIdx.x == 0) out[0] = s;
 }
 
-// x += (double) d
-// per-column sums of squares of an n x ncols block: out[c] += sum_i A[i, c]^2
+// per-column sums of squares of an n x ncols block: out[c] = sum_i A[i, c]^2 (one CTA per column)
 __global__ void colsumsq_kernel(const double* __restrict__ A, long long lda, int n, double* __restrict__ out, int ncols) {
-    for (int c = blockIdx.y; c < ncols; c += gridDim.y) {   // gridDim.y is clamped by grid_y()
+    for (int c = blockIdx.x; c < ncols; c += gridDim.x) {
         double s = 0.0;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const double v = A[(long long)c * lda + i];
             s = fma(v, v, s);
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if ((threadIdx.x & 31) == 0) atomicAdd(out + c, s);
+        s = block_sum_fixed(s);
+        if (threadIdx.x == 0) out[c] = s;
     }
 }
 

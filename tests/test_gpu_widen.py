@@ -265,3 +265,31 @@ def test_host_register_option(gpu_required, ls):
     cache = ls.init(ls.LinearProblem(A, b), ls.B200LUFactorization(host_register=True))
     sol = ls.solve_(cache)
     assert sol.retcode == ls.ReturnCode.Success and _berr(A, sol.u, b) <= 10 * n * EPS
+
+
+@pytest.mark.parametrize("n", [1500, 6000])
+def test_mixed_refinement_is_deterministic(gpu_required, ls, n):
+    """FP32 factors + FP64 refinement give the SAME bits on every run: the FP64 residual and the norms that decide
+    the sweep count are reduced in one fixed order (no atomics), like every other kernel of the path."""
+    import torch
+    C = ls._capi
+    dev = torch.device("cuda", 0)
+    A = torch.empty((n, n), dtype=torch.float64, device=dev)
+    b = torch.empty((2, n), dtype=torch.float64, device=dev)
+    xs = []
+    for rep in range(4):
+        h = ls.Handle(C.MIXED)
+        h.fill_uniform_device(A.data_ptr(), n, n, n, seed=77)
+        h.fill_uniform_device(b.data_ptr(), n, n, 2, seed=78)
+        assert h.factor_device(A.data_ptr(), n, n) == 0
+        x1 = torch.empty((1, n), dtype=torch.float64, device=dev)
+        x2 = torch.empty((2, n), dtype=torch.float64, device=dev)
+        h.solve_device(b.data_ptr(), n, x1.data_ptr(), n, 1)          # vector right-hand side
+        h.solve_device(b.data_ptr(), n, x2.data_ptr(), n, 2)          # matrix right-hand side
+        torch.cuda.synchronize()
+        xs.append((x1.clone(), x2.clone(), int(h.counter(C.C_REFINE_ITERS))))
+        h.close()
+    r = torch.mv(A.t(), xs[0][0][0]) - b[0]
+    assert float(r.norm() / (A.norm() * xs[0][0][0].norm())) <= 10 * n * EPS
+    for x1, x2, it in xs[1:]:
+        assert torch.equal(x1, xs[0][0]) and torch.equal(x2, xs[0][1]) and it == xs[0][2]
