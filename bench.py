@@ -690,14 +690,15 @@ def bench_dist(args, ls, torch, dist, dev, rank, world, local, barrier, max_over
     factors the panel and stores it into its peers' windows, look-ahead, distributed getrs.  Strong
     scaling: `value` = 2/3 n^3 / (max over ranks of the device time of factor_dist + solve_dist)."""
     C = ls._capi
-    # outer panel width: 256 on one or two GPUs (the run is bound by the trailing GEMM), 128 from four GPUs on (the
-    # run is bound by the panel chain: narrower panels shorten every look-ahead update and every hand-off)
-    n, nrhs, nb = args.n, args.nrhs, (args.nb or (128 if world >= 4 else 256))
+    # outer panel width: the library's own choice by GPU count (256; 128 from eight GPUs on, where the panel chain
+    # outweighs the better GEMM shape) unless --nb is given
+    n, nrhs = args.n, args.nrhs
     eps = np.finfo(np.float64).eps
 
     def make_handle():
         h = C.Handle(C.F64, device=local)
-        h.set_option(C.OPT_NB, nb)
+        if args.nb:
+            h.set_option(C.OPT_NB, args.nb)
         if args.gemm_cfg >= 0:
             h.set_option(C.OPT_GEMM_CFG, args.gemm_cfg)
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
@@ -709,6 +710,7 @@ def bench_dist(args, ls, torch, dist, dev, rank, world, local, barrier, max_over
         return h
 
     h = make_handle()
+    nb = h.get_option(C.OPT_NB)
     transport = h.dist_transport() if world > 1 else "single rank"
 
     # ---- in-run self-check (the driver's test box has one GPU): distributed factors == single-GPU factors, bitwise
@@ -738,6 +740,7 @@ def bench_dist(args, ls, torch, dist, dev, rank, world, local, barrier, max_over
 
     check_bitwise = self_check(4096)
     torch.cuda.empty_cache()
+    peak_before = h.probe_peak(C.PEAK_FP64_DMMA)      # the yardstick on a cool GPU; probed again after the load
 
     nloc = h.dist_local_cols(n)
     Aloc = torch.empty((nloc, n), dtype=torch.float64, device=dev)
@@ -806,7 +809,7 @@ def bench_dist(args, ls, torch, dist, dev, rank, world, local, barrier, max_over
         dist.all_reduce(ct)                      # every panel has one owner: the sum over ranks is the whole chain
         chain = [float(x) for x in ct.tolist()]
     h.set_option(C.OPT_PROFILE, 0)
-    peak = h.probe_peak(C.PEAK_FP64_DMMA)
+    peak = max(peak_before, h.probe_peak(C.PEAK_FP64_DMMA))
     ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     gemm_share = max_over_ranks(g_ms / t_prof if t_prof else 0.0)
     value = lu_flops(n) / (ms * 1e-3) / 1e9

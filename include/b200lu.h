@@ -98,7 +98,8 @@ enum {
 
 /* tuning / test knobs for b200lu_set_option */
 enum {
-    B200LU_OPT_NB = 0,          /* outer panel width (multiple of 16, <= 256)    */
+    B200LU_OPT_NB = 0,          /* outer panel width (multiple of 16, <= 256); default 256, and 128 for one
+                                   system over 8 or more GPUs unless the caller sets it              */
     B200LU_OPT_LOOKAHEAD = 1,   /* 0/1: factor panel k+1 under trailing update k */
     B200LU_OPT_REFINE_MAXIT = 2,/* B200LU_MIXED: max refinement sweeps (def. 10) */
     B200LU_OPT_PANEL_CTAS = 3,  /* max CTAs of the cooperative base-panel kernel */

@@ -53,6 +53,7 @@ struct b200lu_handle {
     char err[512] = {0};
     double timing[B200LU_T_COUNT] = {0};
     int64_t opt[B200LU_OPT_COUNT];
+    bool nb_user = false;                // B200LU_OPT_NB was set by the caller (no automatic choice by GPU count)
 
     // single large system
     int64_t n = 0, ldd = 0, cap_n = 0, cap_meta = 0;
@@ -1669,6 +1670,7 @@ int b200lu_set_option(b200lu_handle* h, int option, int64_t value) {
     if (option == B200LU_OPT_MAPPED_RHS && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_KEEP_A && (value < 0 || value > 1)) return -3;
     if (option == B200LU_OPT_BATCHED_MODE && (value < 0 || value > 1)) return -3;
+    if (option == B200LU_OPT_NB) h->nb_user = true;
     if (h->team) return team_set_option(h, option, value);
     h->opt[option] = value;
     return 0;
