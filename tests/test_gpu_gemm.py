@@ -62,3 +62,11 @@ def test_dgemm_dmma(gpu_required, ls, shape):
     import torch
     err = _run(ls, ls._capi.F64, torch.float64, M, N, K)
     assert err < 8 * np.finfo(np.float64).eps, err
+
+
+def test_sgemm_tcgen05_more_than_65535_columns(gpu_required, ls):
+    """The FP32 / MIXED trailing update of a factorization with n > 65535 + 2 nb has more columns than gridDim.y
+    allows: the operand-split kernel strides over the columns (round-1 finding: 'invalid configuration argument')."""
+    import torch
+    err = _run(ls, ls._capi.F32, torch.float32, 256, 70000, 128, sgemm_mode=2)
+    assert err < 8 * np.finfo(np.float32).eps, err
