@@ -7,6 +7,10 @@ import linearsolve_jl_b200 as ls
 C = ls._capi
 dev = torch.device("cuda", 0)
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+# memcheck rejects st.async into the CTA's own shared::cluster window when the cluster has ONE CTA ("Cluster needs to
+# have at least 2 blocks": every factorization ends with such panels; the hardware executes them): panel mode 1
+# (the L2-mailbox kernel, no DSMEM) lets memcheck see the rest of the path
+PANEL_MODE = int(os.environ.get("SAN_PANEL_MODE", "0"))
 rng = np.random.default_rng(0)
 
 
@@ -14,6 +18,7 @@ def dense(code, n, nrhs=(1, 3)):
     dt = np.float32 if code == C.F32 else np.float64
     A = np.asfortranarray(rng.random((n, n)).astype(dt) + (5.0 * np.eye(n, dtype=dt) if code == C.MIXED else 0))
     h = C.Handle(code)
+    h.set_option(C.OPT_PANEL_MODE, PANEL_MODE)
     ipiv, info = h.factor(A)
     for k in nrhs:
         b = rng.random((n, k)).astype(dt) if k > 1 else rng.random(n).astype(dt)
@@ -48,6 +53,7 @@ if which in ("all", "dist"):
     n, nb = 1000, 128
     h = C.Handle(C.F64)
     h.set_option(C.OPT_NB, nb)
+    h.set_option(C.OPT_PANEL_MODE, PANEL_MODE)
     h.comm_init(None, 0, 1)
     Aloc = torch.rand((n, n), dtype=torch.float64, device=dev)
     assert h.factor_dist(Aloc.data_ptr(), n, n) == 0
