@@ -138,10 +138,14 @@ struct PclShared {
     static constexpr int EPV = 16 / (int)sizeof(T);
     static constexpr int NV = W / EPV;
     ulonglong2 box[2][PCL_GMAX][1 + NV];   // inbox: one message {header, row} per source CTA
-    T stage[NW][W];                        // per-warp candidate rows (coordinates of their column)
+    // per-warp candidate rows (coordinates of their column) and candidates, double-buffered by column parity like the
+    // inbox: the readers of column j (after that column's CTA barrier) and the writers of column j + 1 (before the next
+    // barrier) are not ordered by any barrier — a warp that stalls right behind the barrier must not find its
+    // candidates overwritten by a warp that is a whole column ahead (racecheck: profiles/r02_sanitizer_racecheck_*)
+    T stage[2][NW][W];
     T s_top[W];                            // zero/NaN-pivot path only
-    T s_val[NW];
-    int s_pos[NW];
+    T s_val[2][NW];
+    int s_pos[2][NW];
     unsigned long long mbar[2];
     unsigned long long mbar_bulk;          // TMA bulk copies of the multipliers (fused kernel)
     int s_mv_dst[2 * W], s_mv_src[2 * W];
@@ -396,7 +400,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
         for (int q = 0; q < RPT; ++q) {
             if (pos[q] == bpos) {
 #pragma unroll
-                for (int c = 0; c < W; ++c) sh.stage[warp][c] = a[q][c];
+                for (int c = 0; c < W; ++c) sh.stage[0][warp][c] = a[q][c];
             }
         }
     }
@@ -405,20 +409,20 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
 #define PCL_PUBLISH(jn)                                                                              \
     {                                                                                                \
         const int par_ = (jn) & 1;                                                                   \
-        if (lane == wl) { sh.s_val[warp] = best; sh.s_pos[warp] = bpos; }                            \
-        if (wl < 0 && lane == 0) { sh.s_val[warp] = T(0); sh.s_pos[warp] = INT_MAX; }                \
+        if (lane == wl) { sh.s_val[par_][warp] = best; sh.s_pos[par_][warp] = bpos; }                \
+        if (wl < 0 && lane == 0) { sh.s_val[par_][warp] = T(0); sh.s_pos[par_][warp] = INT_MAX; }    \
         const int nv_ = (W - (jn) + EPV - 1) / EPV;   /* live row vectors of that column */          \
         if (tid == 0) pcl_mbar_expect_tx(pcl_smem_u32(&sh.mbar[par_]), (unsigned)(G * (1 + nv_)) * 16u); \
         PCL_T(0);                                                                                    \
         __syncthreads();                                                                             \
-        const T cv_ = lane < NW ? sh.s_val[lane] : T(0);                                             \
-        const int cpos_ = lane < NW ? sh.s_pos[lane] : INT_MAX;                                      \
+        const T cv_ = lane < NW ? sh.s_val[par_][lane] : T(0);                                       \
+        const int cpos_ = lane < NW ? sh.s_pos[par_][lane] : INT_MAX;                                \
         int cw_ = pcl_warp_argmax(cv_, cpos_);                                                       \
         const int cp_ = cw_ < 0 ? INT_MAX : __shfl_sync(0xffffffffu, cpos_, cw_);                    \
         if (cw_ < 0) cw_ = 0;                                                                        \
         const unsigned rb_ = rbar0 + (unsigned)par_ * 8u;                                            \
         if (s_k < nv_) {                                                                             \
-            const ulonglong2 v_ = reinterpret_cast<const ulonglong2*>(&sh.stage[cw_][0])[s_k];       \
+            const ulonglong2 v_ = reinterpret_cast<const ulonglong2*>(&sh.stage[par_][cw_][0])[s_k]; \
             pcl_st_async_v2(raddr0 + (unsigned)par_ * BOXB, v_.x, v_.y, rb_);                        \
         }                                                                                            \
         if (s_k == 0) pcl_st_async_v2(rhdr0 + (unsigned)par_ * BOXB, (unsigned long long)(unsigned)cp_, 0ull, rb_); \
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
             const unsigned ob = __ballot_sync(0xffffffffu, own >= 0);                                \
             if (ob) {                                                                                \
                 const int orow = __shfl_sync(0xffffffffu, own, __ffs(ob) - 1);                       \
-                const T* srow = none ? sh.s_top : &sh.stage[warp][0];                                \
+                const T* srow = none ? sh.s_top : &sh.stage[par][warp][0];                           \
                 if (lane < W - j && lane < W) tile[(j + lane) * ROWS + orow] = srow[lane];           \
             }                                                                                        \
         }                                                                                            \
@@ -503,7 +507,7 @@ __global__ void __launch_bounds__(NT, 1) panel_cluster_kernel(PanelArgs<T> p) {
         if (lane == wl) {   /* stage the row in the coordinates of column j + 1 */                   \
             _Pragma("unroll") for (int q = 0; q < RPT; ++q) {                                        \
                 if (pos[q] == bpos) {                                                                \
-                    _Pragma("unroll") for (int c = 0; c < (LIVE) - 1; ++c) sh.stage[warp][c] = a[q][c]; \
+                    _Pragma("unroll") for (int c = 0; c < (LIVE) - 1; ++c) sh.stage[par ^ 1][warp][c] = a[q][c]; \
                 }                                                                                    \
             }                                                                                        \
         }                                                                                            \

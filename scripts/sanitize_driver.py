@@ -25,7 +25,7 @@ def dense(code, n, nrhs=(1, 3)):
         x = h.solve(b)
         r = np.linalg.norm(A.astype(np.float64) @ x.reshape(n, -1) - b.reshape(n, -1)) / (np.linalg.norm(A) * np.linalg.norm(x))
         assert r < 1e-3 if code == C.F32 else r < 1e-12, r
-    if code != C.MIXED:
+    if code != C.MIXED and nrhs:
         x = h.solve(rng.random(n).astype(dt), trans="T")
     h.close()
     print("dense", code, n, "ok", flush=True)
@@ -36,6 +36,13 @@ if which in ("all", "dense"):
     dense(C.F64, 4500)      # 32 x 2 class
     dense(C.F32, 2500)      # FP32 fused panels + tcgen05 update
     dense(C.MIXED, 2500)    # + refinement (residual partial sums, norms)
+if which == "panels":       # every fused panel class (racecheck: shared-memory hazards inside the cluster kernels)
+    dense(C.F64, 1500, nrhs=())
+    dense(C.F32, 2500, nrhs=())
+    dense(C.F64, 4500, nrhs=())     # 32 x 2
+    dense(C.F32, 9000, nrhs=())     # FP32 32 x 4
+    dense(C.F64, 9000, nrhs=())     # 16 x 4
+    dense(C.F64, 17000, nrhs=())    # 8 x 8
 if which in ("all", "batched"):
     A = rng.random((300, 64, 64)) + 64 * np.eye(64)
     b = rng.random((300, 64))
