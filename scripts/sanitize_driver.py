@@ -36,6 +36,8 @@ if which in ("all", "dense"):
     dense(C.F64, 4500)      # 32 x 2 class
     dense(C.F32, 2500)      # FP32 fused panels + tcgen05 update
     dense(C.MIXED, 2500)    # + refinement (residual partial sums, norms)
+if which == "panel1":
+    dense(C.F64, 1500, nrhs=())
 if which == "panels":       # every fused panel class (racecheck: shared-memory hazards inside the cluster kernels)
     dense(C.F64, 1500, nrhs=())
     dense(C.F32, 2500, nrhs=())
