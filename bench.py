@@ -576,6 +576,8 @@ def batched_entry(ms_f, ms_s, per, world, hbm):
     ms = ms_f + ms_s
     ach = per * bytes_sys / (ms * 1e-3) / 1e9
     ach_f = per * (2 * n * n * 8 + n * 4 + 4) / (ms_f * 1e-3) / 1e9
+    # dram bytes of ONE launch of the factor-only kernel on 16384 systems (the committed ncu capture)
+    tr = newest_profile_traffic("*ncu_batched_warp*metrics*.txt")
     return {"value": world * per / (ms * 1e-3), "unit": "systems/s", "ms_per_step": ms, "getrf_ms": ms_f, "getrs_ms": ms_s,
             "variant": "factor + solve of one right-hand side in ONE kernel, factors written out and kept (LinearCache contract)"
                        if ms_s == 0.0 else "factor, then solve (two kernels), factors kept",
@@ -583,7 +585,10 @@ def batched_entry(ms_f, ms_s, per, world, hbm):
             "roofline": {"bound": "hbm", "kernel": "getrf_batched_warp_kernel<double,64,SOLVE> (warp per system, shared-memory resident)"
                          if ms_s == 0.0 else "getrf_batched_*_kernel + getrs_batched_kernel", "achieved": ach, "peak": hbm,
                          "unit": "GB/s", "frac": ach / hbm, "getrf_only_frac": ach_f / hbm,
-                         "algorithmic_bytes_per_system": bytes_sys, "hbm_bound_systems_per_s_per_gpu": hbm * 1e9 / bytes_sys}}
+                         "algorithmic_bytes_per_system": bytes_sys, "hbm_bound_systems_per_s_per_gpu": hbm * 1e9 / bytes_sys,
+                         "traffic": tr["bytes"] if tr else None, "traffic_source": tr["file"] if tr else None,
+                         "traffic_launch": "getrf_batched_warp_kernel<double,64> (factor only: A in, LU + pivots out) on 16384 "
+                                           "systems: %.0f B per system" % (tr["bytes"] / 16384) if tr else None}}
 
 
 # --------------------------------------------------------------------------------- main ----
