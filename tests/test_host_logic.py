@@ -386,6 +386,12 @@ def test_dense_solve_protocol_with_oracle_backend(ls, monkeypatch):
     assert cm.cacheval.handle.dtype == ls._capi.MIXED and cm.cacheval.handle.options == {ls._capi.OPT_REFINE_MAXIT: 0}
     with pytest.raises(TypeError):
         ls.init(ls.LinearProblem(A.astype(np.float32), b.astype(np.float32)), mixed).alg.handle_dtype(np.float32)
+    # host_register: the library is told to page-lock the cache's own copy of A (B200LU_OPT_HOST_REGISTER); default off
+    ch = ls.init(ls.LinearProblem(A, b), ls.B200LUFactorization(throwerror=False, host_register=True))
+    assert ls.solve_(ch).retcode == ls.ReturnCode.Success
+    assert ch.cacheval.handle.options == {ls._capi.OPT_HOST_REGISTER: 1}
+    with pytest.raises(ValueError):                            # the multi-GPU handle keeps no copy of A
+        ls.B200LUFactorization(throwerror=False, residualsafety=True, devices=(0, 1))
 
 
 def test_bench_reference_arm_runs_on_cpu():
