@@ -141,7 +141,9 @@ enum {
                                    buffer gets.  For callers that own the buffer for the lifetime of the cache
                                    (reference: a LinearCache with alias_A = false, src/common.jl:818-842) and cannot
                                    allocate pinned memory themselves.  Default 0: pageable buffers are staged by the
-                                   driver.  The registration costs about as much as one pageable upload.          */
+                                   driver.  The registration costs about as much as one pageable upload.  The
+                                   buffer must stay allocated while it is registered: destroy the handle (or factor
+                                   from another buffer) before freeing it.                                        */
     B200LU_OPT_COUNT = 16
 };
 

@@ -113,18 +113,20 @@ mutable struct B200LUCache
     ipiv::Vector{BlasInt}       # 1-based LAPACK interchange sequence (BlasInt == Int64)
     info::Base.RefValue{BlasInt}
     n::Int
+    registered::Any             # the host matrix the library page-locked (host_register): kept alive with the handle
 end
 
 function _b200lu_finalize(c::B200LUCache)
     if c.handle != C_NULL
-        ccall((:b200lu_destroy, libb200lu[]), Cvoid, (Ptr{Cvoid},), c.handle)
+        ccall((:b200lu_destroy, libb200lu[]), Cvoid, (Ptr{Cvoid},), c.handle)   # also releases the registration
         c.handle = C_NULL
     end
+    c.registered = nothing
     return nothing
 end
 
 function _b200lu_cache(dtype::Cint)
-    c = B200LUCache(C_NULL, dtype, Vector{BlasInt}(undef, 0), Ref{BlasInt}(0), 0)
+    c = B200LUCache(C_NULL, dtype, Vector{BlasInt}(undef, 0), Ref{BlasInt}(0), 0, nothing)
     finalizer(_b200lu_finalize, c)      # pattern: AMGX handles, src/extension_algs.jl:1555-1556
     return c
 end
@@ -172,7 +174,9 @@ function _b200lu_ensure_handle!(c::B200LUCache, alg)
     end
     if alg isa B200LUFactorization && alg.host_register
         # cache.A is the cache's own copy (alias_A = false, src/common.jl:818-842) and lives as long as the cache:
-        # pinned once, every refactorization streams its upload under the factorization
+        # pinned once, every refactorization streams its upload under the factorization (the cacheval's finalizer
+        # destroys the handle — and with it the registration — so it must run before cache.A is collected: the
+        # cacheval keeps a reference to that array, see B200LUCache.registered)
         ccall((:b200lu_set_option, libb200lu[]), Cint, (Ptr{Cvoid}, Cint, Int64),
             c.handle, 15, 1)                                     # B200LU_OPT_HOST_REGISTER
     end
@@ -190,6 +194,9 @@ end
         c.handle, n, A, max(1, stride(A, 2)), c.ipiv, c.info)
     rc == 0 || _b200lu_error(c, rc)
     c.n = n
+    if alg isa B200LUFactorization && alg.host_register
+        c.registered = A        # the registration moved to this buffer (or stayed on it)
+    end
     return c.info[]
 end
 
